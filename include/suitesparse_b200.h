@@ -1,0 +1,243 @@
+/* suitesparse_b200.h — C ABI of the B200-native supernodal Cholesky hot path.
+ *
+ * Two layers, both `extern "C"`, plain pointers and sizes only:
+ *
+ *  (1) DROP-IN layer: the symbols CHOLMOD's own driver binds for this path.  They keep the
+ *      reference's names, argument meaning, return values and Common->status protocol, so that
+ *      this library placed ahead of libcholmod in link order (or LD_PRELOAD / RTLD_GLOBAL) takes
+ *      over the calls made by cholmod_l_factorize_p (CHOLMOD/Cholesky/cholmod_factorize.c:265)
+ *      and cholmod_l_solve2 (CHOLMOD/Cholesky/cholmod_solve.c:1568-1577):
+ *          cholmod_l_super_numeric   replaces CHOLMOD/Supernodal/cholmod_super_numeric.c:97
+ *                                    (+ t_cholmod_super_numeric.c:93, GPU/t_cholmod_gpu.c)
+ *          cholmod_l_super_lsolve    replaces CHOLMOD/Supernodal/cholmod_super_solve.c:43
+ *          cholmod_l_super_ltsolve   replaces CHOLMOD/Supernodal/cholmod_super_solve.c:136
+ *          cholmod_l_gpu_*           replaces CHOLMOD/GPU/cholmod_gpu.c:71,170,208,255,364
+ *      The object layouts below restate CHOLMOD 3.0.14's public structs
+ *      (CHOLMOD/Include/cholmod_core.h:416-1026, 1243-1270, 1673-1798, 1976-1990) field for field;
+ *      tests/test_abi.py checks sizeof/offsetof against the reference headers.
+ *
+ *  (2) PLAIN layer (ssb200_*): the same computation on raw arrays — the supernodal symbolic
+ *      structure (super/pi/px/s of cholmod_factor, cholmod_core.h:1723-1732), a CSC matrix and
+ *      the dense block array Lx.  This is what another language's FFI (ctypes / cgo / JNI) binds.
+ *
+ * Only the `long` (64-bit index, `cholmod_l_`) real double-precision case is accelerated: the
+ * reference enables its GPU path for exactly that case (CHOLMOD/Include/cholmod_internal.h:249-252).
+ * There is no CPU fallback: if no sm_100 device is usable the calls fail with CHOLMOD_GPU_PROBLEM.
+ */
+#ifndef SUITESPARSE_B200_H
+#define SUITESPARSE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef int64_t ssb_long;           /* SuiteSparse_long on LP64 (SuiteSparse_config.h) */
+
+/* status codes, cholmod_core.h:386-394 */
+#define SSB_CHOLMOD_OK              0
+#define SSB_CHOLMOD_NOT_INSTALLED (-1)
+#define SSB_CHOLMOD_OUT_OF_MEMORY (-2)
+#define SSB_CHOLMOD_TOO_LARGE     (-3)
+#define SSB_CHOLMOD_INVALID       (-4)
+#define SSB_CHOLMOD_GPU_PROBLEM   (-5)
+#define SSB_CHOLMOD_NOT_POSDEF      1
+#define SSB_CHOLMOD_DSMALL          2
+/* xtype / itype / dtype, cholmod_core.h:310-333 */
+#define SSB_CHOLMOD_PATTERN 0
+#define SSB_CHOLMOD_REAL    1
+#define SSB_CHOLMOD_COMPLEX 2
+#define SSB_CHOLMOD_ZOMPLEX 3
+#define SSB_CHOLMOD_LONG    2
+#define SSB_CHOLMOD_DOUBLE  0
+#define SSB_CHOLMOD_MAXMETHODS 9
+#define SSB_CHOLMOD_HOST_SUPERNODE_BUFFERS 8
+
+#ifndef SSB200_NO_CHOLMOD_TYPES
+/* ---- cholmod_sparse, cholmod_core.h:1243 ------------------------------------------------- */
+typedef struct ssb_cholmod_sparse {
+    size_t nrow, ncol, nzmax;
+    void *p, *i, *nz, *x, *z;
+    int stype, itype, xtype, dtype, sorted, packed;
+} ssb_cholmod_sparse;
+
+/* ---- cholmod_dense, cholmod_core.h:1976 -------------------------------------------------- */
+typedef struct ssb_cholmod_dense {
+    size_t nrow, ncol, nzmax, d;
+    void *x, *z;
+    int xtype, dtype;
+} ssb_cholmod_dense;
+
+/* ---- cholmod_factor, cholmod_core.h:1673 ------------------------------------------------- */
+typedef struct ssb_cholmod_factor {
+    size_t n, minor;
+    void *Perm, *ColCount, *IPerm;
+    size_t nzmax;                                   /* simplicial part */
+    void *p, *i, *x, *z, *nz, *next, *prev;
+    size_t nsuper, ssize, xsize, maxcsize, maxesize;/* supernodal part */
+    void *super, *pi, *px, *s;
+    int ordering, is_ll, is_super, is_monotonic, itype, xtype, dtype, useGPU;
+} ssb_cholmod_factor;
+
+/* ---- cholmod_common, cholmod_core.h:416 -------------------------------------------------- */
+typedef struct ssb_cholmod_method {
+    double lnz, fl, prune_dense, prune_dense2, nd_oksep, other_1[4];
+    size_t nd_small, other_2[4];
+    int aggressive, order_for_lu, nd_compress, nd_camd, nd_components, ordering;
+    size_t other_3[4];
+} ssb_cholmod_method;
+
+typedef struct ssb_cholmod_common {
+    double dbound, grow0, grow1;
+    size_t grow2, maxrank;
+    double supernodal_switch;
+    int supernodal, final_asis, final_super, final_ll, final_pack, final_monotonic, final_resymbol;
+    double zrelax[3];
+    size_t nrelax[3];
+    int prefer_zomplex, prefer_upper, quick_return_if_not_posdef, prefer_binary, print, precise, try_catch;
+    void (*error_handler)(int status, const char *file, int line, const char *message);
+    int nmethods, current, selected;
+    ssb_cholmod_method method[SSB_CHOLMOD_MAXMETHODS + 1];
+    int postorder, default_nesdis;
+    double metis_memory, metis_dswitch;
+    size_t metis_nswitch;
+    size_t nrow;
+    ssb_long mark;
+    size_t iworksize, xworksize;
+    void *Flag, *Head, *Xwork, *Iwork;
+    int itype, dtype, no_workspace_reallocate, status;
+    double fl, lnz, anz, modfl;
+    size_t malloc_count, memory_usage, memory_inuse;
+    double nrealloc_col, nrealloc_factor, ndbounds_hit, rowfacfl, aatfl;
+    int called_nd, blas_ok;
+    double SPQR_grain, SPQR_small;
+    int SPQR_shrink, SPQR_nthreads;
+    double SPQR_flopcount, SPQR_analyze_time, SPQR_factorize_time, SPQR_solve_time,
+           SPQR_flopcount_bound, SPQR_tol_used, SPQR_norm_E_fro;
+    ssb_long SPQR_istat[10];
+    /* GPU configuration and statistics (cholmod_core.h:954-1024); handles are void* in a non-GPU_BLAS build */
+    int useGPU;
+    size_t maxGpuMemBytes;
+    double maxGpuMemFraction;
+    size_t gpuMemorySize;
+    double gpuKernelTime;
+    ssb_long gpuFlops;
+    int gpuNumKernelLaunches;
+    void *cublasHandle;
+    void *gpuStream[SSB_CHOLMOD_HOST_SUPERNODE_BUFFERS];
+    void *cublasEventPotrf[3];
+    void *updateCKernelsComplete;
+    void *updateCBuffersFree[SSB_CHOLMOD_HOST_SUPERNODE_BUFFERS];
+    void *dev_mempool;
+    size_t dev_mempool_size;
+    void *host_pinned_mempool;
+    size_t host_pinned_mempool_size;
+    size_t devBuffSize;
+    int ibuffer;
+    double syrkStart;
+    double cpu_gemm_time, cpu_syrk_time, cpu_trsm_time, cpu_potrf_time;
+    double gpu_gemm_time, gpu_syrk_time, gpu_trsm_time, gpu_potrf_time;
+    double assemble_time, assemble_time2;
+    size_t cpu_gemm_calls, cpu_syrk_calls, cpu_trsm_calls, cpu_potrf_calls;
+    size_t gpu_gemm_calls, gpu_syrk_calls, gpu_trsm_calls, gpu_potrf_calls;
+} ssb_cholmod_common;
+
+/* =========================== (1) DROP-IN layer ============================================== */
+/* Prototypes are those of CHOLMOD/Include/cholmod_supernodal.h:112-127,137-152,162-177 and
+ * CHOLMOD/Include/cholmod_gpu.h:59-93 (struct tags differ in name only). */
+
+#ifndef SSB200_NO_DROPIN_PROTOTYPES   /* define when cholmod.h is included in the same unit */
+/* Numeric supernodal LL' of A (stype<0: lower triangle of the permuted symmetric matrix) or of
+ * A*F (stype==0, F=A').  Returns 1 (TRUE) on success AND when the matrix is not positive definite
+ * (Common->status = CHOLMOD_NOT_POSDEF, L->minor = failing column, t_cholmod_super_numeric.c:905-968);
+ * returns 0 with Common->status<0 on invalid input / out of memory / GPU failure. */
+int cholmod_l_super_numeric(ssb_cholmod_sparse *A, ssb_cholmod_sparse *F, double beta[2],
+                            ssb_cholmod_factor *L, ssb_cholmod_common *Common);
+/* X <- L \ X (forward) and X <- L' \ X (backward), X is n-by-nrhs with leading dimension X->d;
+ * E is the caller's workspace of >= nrhs*L->maxesize entries (checked, unused on the device). */
+int cholmod_l_super_lsolve (ssb_cholmod_factor *L, ssb_cholmod_dense *X, ssb_cholmod_dense *E,
+                            ssb_cholmod_common *Common);
+int cholmod_l_super_ltsolve(ssb_cholmod_factor *L, ssb_cholmod_dense *X, ssb_cholmod_dense *E,
+                            ssb_cholmod_common *Common);
+
+int  cholmod_l_gpu_memorysize(size_t *total_mem, size_t *available_mem, ssb_cholmod_common *Common);
+int  cholmod_l_gpu_probe     (ssb_cholmod_common *Common);
+int  cholmod_l_gpu_allocate  (ssb_cholmod_common *Common);
+int  cholmod_l_gpu_deallocate(ssb_cholmod_common *Common);
+void cholmod_l_gpu_end       (ssb_cholmod_common *Common);
+#endif /* SSB200_NO_DROPIN_PROTOTYPES */
+#endif /* SSB200_NO_CHOLMOD_TYPES */
+
+/* =========================== (2) PLAIN layer ================================================ */
+typedef struct ssb200_plan ssb200_plan;       /* opaque: device-resident symbolic plan + factor storage */
+
+/* Build the device plan from the symbolic supernodal structure (host arrays, read once).
+ *   n, nsuper           cholmod_factor.n / .nsuper
+ *   super[nsuper+1]     first column of each supernode         (cholmod_factor.super)
+ *   pi[nsuper+1]        offsets into s                          (cholmod_factor.pi)
+ *   px[nsuper+1]        offsets into Lx; px[nsuper] = xsize     (cholmod_factor.px)
+ *   s[pi[nsuper]]       row indices, first nscol of a supernode are its own columns (cholmod_factor.s)
+ *   device              CUDA device ordinal; -1 = current device
+ * Returns NULL on failure (ssb200_last_error() says why).  The descendant-update lists that the
+ * reference discovers with Head/Next/Lpos at run time (t_cholmod_super_numeric.c:442-460,583-611,
+ * 787-808) are a pure function of this structure and are precomputed here. */
+ssb200_plan *ssb200_plan_create(ssb_long n, ssb_long nsuper, const ssb_long *super, const ssb_long *pi,
+                                const ssb_long *px, const ssb_long *s, int device);
+void ssb200_plan_destroy(ssb200_plan *plan);
+
+/* Restrict the plan to a shard: supernode j is factorized by this plan iff owner[j]==rank
+ * (owner==NULL: all).  Used for the elimination-tree subtree split across GPUs. */
+int ssb200_plan_set_owner(ssb200_plan *plan, const int32_t *owner, int rank);
+
+/* Numeric factorization.  A (and F for stype==0) are HOST CSC arrays with 64-bit indices:
+ * Ap[n+1], Ai, Ax and optional Anz (unpacked).  stype<0 symmetric-lower input, stype==0 A*F.
+ * Lx_host (xsize doubles) receives the factor if not NULL.  *minor_out = n on success, else the
+ * failing column.  Returns 0 ok, 1 not positive definite, <0 error (SSB_CHOLMOD_* codes). */
+int ssb200_factorize(ssb200_plan *plan, int stype,
+                     const ssb_long *Ap, const ssb_long *Ai, const ssb_long *Anz, const double *Ax, ssb_long ncolA,
+                     const ssb_long *Fp, const ssb_long *Fi, const ssb_long *Fnz, const double *Fx,
+                     const double beta[2], int quick_return_if_not_posdef,
+                     double *Lx_host, ssb_long *minor_out);
+
+/* Device-resident variants: upload A once, factorize on the device only (no host traffic), read back. */
+int ssb200_upload_A(ssb200_plan *plan, int stype,
+                    const ssb_long *Ap, const ssb_long *Ai, const ssb_long *Anz, const double *Ax, ssb_long ncolA,
+                    const ssb_long *Fp, const ssb_long *Fi, const ssb_long *Fnz, const double *Fx);
+int ssb200_factorize_resident(ssb200_plan *plan, const double beta[2], int quick_return_if_not_posdef,
+                              ssb_long *minor_out);
+int ssb200_download_L(ssb200_plan *plan, double *Lx_host);
+int ssb200_upload_L(ssb200_plan *plan, const double *Lx_host);
+
+/* Triangular solves with the device-resident factor.  X is a HOST n-by-nrhs column-major array,
+ * leading dimension ldx.  which: 0 = L\X, 1 = L'\X, 2 = both (L then L'). */
+int ssb200_solve(ssb200_plan *plan, int which, double *X, ssb_long nrhs, ssb_long ldx);
+/* same with X already on the device (device pointer) */
+int ssb200_solve_resident(ssb200_plan *plan, int which, double *dX, ssb_long nrhs, ssb_long ldx);
+
+/* Raw device pointers / sizes for callers that manage their own streams or collectives. */
+double  *ssb200_device_Lx(ssb200_plan *plan);
+ssb_long ssb200_xsize(const ssb200_plan *plan);
+void    *ssb200_stream(ssb200_plan *plan);            /* cudaStream_t the plan launches on */
+
+/* Statistics of the last factorize / solve on this plan. */
+typedef struct ssb200_stats {
+    ssb_long nsuper, nlevels, nupdates;       /* symbolic sizes: supernodes, etree levels, (d,s) update pairs */
+    ssb_long kernel_launches;                 /* kernels launched by the last call */
+    ssb_long kernel_launches_total;           /* since plan creation */
+    double   flops_update, flops_potrf, flops_trsm; /* dense flops executed (incl. amalgamation zeros) */
+    double   ms_total, ms_assemble, ms_update, ms_factor, ms_d2h, ms_h2d; /* device time (CUDA events), last call */
+    double   bytes_update_panel, bytes_update_scatter;  /* algorithmic bytes of the update kernel */
+    ssb_long device_bytes;                    /* HBM held by the plan */
+} ssb200_stats;
+int ssb200_get_stats(const ssb200_plan *plan, ssb200_stats *out);
+
+const char *ssb200_last_error(void);
+const char *ssb200_version(void);
+int ssb200_device_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
