@@ -1,0 +1,776 @@
+// ssb_cuda.cu — device plan, launch orchestration and the C ABI (plain layer + CHOLMOD drop-in layer) declared in
+// include/suitesparse_b200.h.  No CPU fallback: every numeric step below is a kernel from ssb_kernels.cuh.
+#include "ssb_kernels.cuh"
+#include "../../include/suitesparse_b200.h"
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <climits>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+#include <algorithm>
+
+using namespace ssb;
+
+static thread_local std::string g_last_error;
+static void set_error(const std::string &s) { g_last_error = s; }
+
+#define CU_TRY(expr)                                                                                   \
+    do {                                                                                               \
+        cudaError_t _e = (expr);                                                                       \
+        if (_e != cudaSuccess) {                                                                       \
+            set_error(std::string(#expr) + ": " + cudaGetErrorString(_e) + " @" + std::to_string(__LINE__)); \
+            return SSB_CHOLMOD_GPU_PROBLEM;                                                            \
+        }                                                                                              \
+    } while (0)
+
+// device-side job arrays of one schedule (the plan's own, or a temporary one for the not-posdef repeat)
+struct DevJobs {
+    GemmJob *gemm_jobs = nullptr; int *gemm_tiles = nullptr;
+    PanelJob *potrf_jobs = nullptr, *trsm_jobs = nullptr; int *trsm_tiles = nullptr;
+};
+
+struct CscBuf { long long *p = nullptr, *i = nullptr, *nz = nullptr; double *x = nullptr; size_t capP = 0, capI = 0, capNz = 0, capX = 0; bool haveNz = false; };
+static void free_cscbuf(CscBuf *b) { if (!b) return; if (b->p) cudaFree(b->p); if (b->i) cudaFree(b->i); if (b->nz) cudaFree(b->nz); if (b->x) cudaFree(b->x); delete b; }
+
+struct ssb200_plan {
+    HostPlan hp;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int *d_super = nullptr, *d_ls = nullptr, *d_supermap = nullptr, *d_relmap = nullptr, *d_info = nullptr;
+    long long *d_pi = nullptr, *d_px = nullptr;
+    double *d_Lx = nullptr;
+    DevJobs jobs;
+    SolveJob *d_solve_jobs = nullptr; int *d_solve_tiles = nullptr;
+    int *h_info = nullptr;                 // pinned
+    // matrix on the device
+    struct CscBuf *bufA = nullptr, *bufF = nullptr;
+    bool haveA = false;
+    int stype = -1;
+    double *d_X = nullptr; size_t capX = 0;
+    bool factor_on_device = false;
+    std::vector<cudaEvent_t> events;
+    ssb200_stats stats{};
+    size_t device_bytes = 0;
+};
+
+template <typename T> static int dev_alloc_copy(ssb200_plan *p, T **dst, const std::vector<T> &src)
+{
+    const size_t bytes = std::max<size_t>(src.size(), 1) * sizeof(T);
+    CU_TRY(cudaMalloc((void **) dst, bytes));
+    p->device_bytes += bytes;
+    if (!src.empty()) CU_TRY(cudaMemcpyAsync(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice, p->stream));
+    return 0;
+}
+
+static DevSym dev_sym(const ssb200_plan *p)
+{
+    DevSym s; s.super = p->d_super; s.pi = p->d_pi; s.px = p->d_px; s.ls = p->d_ls; s.supermap = p->d_supermap;
+    s.n = p->hp.n; s.nsuper = p->hp.nsuper; return s;
+}
+
+static int configure_kernels_once()
+{
+    static std::once_flag once; static cudaError_t err = cudaSuccess;
+    // attributes are per device context; set them every time a plan is created (cheap)
+    cudaError_t e1 = cudaFuncSetAttribute(gemm_nt_sub_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) gemm_smem_bytes<128>());
+    cudaError_t e2 = cudaFuncSetAttribute(gemm_nt_sub_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) gemm_smem_bytes<64>());
+    (void) once; (void) err;
+    if (e1 != cudaSuccess || e2 != cudaSuccess) { set_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : e2)); return SSB_CHOLMOD_GPU_PROBLEM; }
+    return 0;
+}
+
+extern "C" const char *ssb200_last_error(void) { return g_last_error.c_str(); }
+extern "C" const char *ssb200_version(void) { return "suitesparse_b200 0.1 (sm_100a; CHOLMOD 3.0.14 ABI)"; }
+extern "C" int ssb200_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) return 0; return n; }
+
+static void plan_free(ssb200_plan *p)
+{
+    if (!p) return;
+    cudaSetDevice(p->device);
+    void *ptrs[] = {p->d_super, p->d_ls, p->d_supermap, p->d_relmap, p->d_info, p->d_pi, p->d_px, p->d_Lx, p->jobs.gemm_jobs,
+                    p->jobs.gemm_tiles, p->jobs.potrf_jobs, p->jobs.trsm_jobs, p->jobs.trsm_tiles, p->d_solve_jobs, p->d_solve_tiles,
+                    p->d_X};
+    for (void *q : ptrs) if (q) cudaFree(q);
+    free_cscbuf(p->bufA); free_cscbuf(p->bufF);
+    if (p->h_info) cudaFreeHost(p->h_info);
+    for (auto e : p->events) cudaEventDestroy(e);
+    if (p->stream) cudaStreamDestroy(p->stream);
+    delete p;
+}
+
+static int upload_jobs(ssb200_plan *p, const HostPlan &hp, DevJobs &dj)
+{
+    if (dev_alloc_copy(p, &dj.gemm_jobs, hp.gemm_jobs)) return SSB_CHOLMOD_GPU_PROBLEM;
+    if (dev_alloc_copy(p, &dj.gemm_tiles, hp.gemm_tiles)) return SSB_CHOLMOD_GPU_PROBLEM;
+    if (dev_alloc_copy(p, &dj.potrf_jobs, hp.potrf_jobs)) return SSB_CHOLMOD_GPU_PROBLEM;
+    if (dev_alloc_copy(p, &dj.trsm_jobs, hp.trsm_jobs)) return SSB_CHOLMOD_GPU_PROBLEM;
+    if (dev_alloc_copy(p, &dj.trsm_tiles, hp.trsm_tiles)) return SSB_CHOLMOD_GPU_PROBLEM;
+    return 0;
+}
+static void free_jobs(DevJobs &dj)
+{
+    void *ptrs[] = {dj.gemm_jobs, dj.gemm_tiles, dj.potrf_jobs, dj.trsm_jobs, dj.trsm_tiles};
+    for (void *q : ptrs) if (q) cudaFree(q);
+    dj = DevJobs();
+}
+
+static int plan_build_device(ssb200_plan *p)
+{
+    HostPlan &hp = p->hp;
+    if (configure_kernels_once()) return SSB_CHOLMOD_GPU_PROBLEM;
+    if (dev_alloc_copy(p, &p->d_super, hp.super)) return SSB_CHOLMOD_GPU_PROBLEM;
+    if (dev_alloc_copy(p, &p->d_pi, hp.pi)) return SSB_CHOLMOD_GPU_PROBLEM;
+    if (dev_alloc_copy(p, &p->d_px, hp.px)) return SSB_CHOLMOD_GPU_PROBLEM;
+    if (dev_alloc_copy(p, &p->d_ls, hp.ls)) return SSB_CHOLMOD_GPU_PROBLEM;
+    if (dev_alloc_copy(p, &p->d_supermap, hp.supermap)) return SSB_CHOLMOD_GPU_PROBLEM;
+    if (upload_jobs(p, hp, p->jobs)) return SSB_CHOLMOD_GPU_PROBLEM;
+    if (dev_alloc_copy(p, &p->d_solve_jobs, hp.solve_jobs)) return SSB_CHOLMOD_GPU_PROBLEM;
+    if (dev_alloc_copy(p, &p->d_solve_tiles, hp.solve_tiles)) return SSB_CHOLMOD_GPU_PROBLEM;
+    const size_t xbytes = std::max<long long>(hp.xsize, 1) * sizeof(double);
+    CU_TRY(cudaMalloc((void **) &p->d_Lx, xbytes)); p->device_bytes += xbytes;
+    const size_t ibytes = std::max<long long>(hp.nsuper, 1) * sizeof(int);
+    CU_TRY(cudaMalloc((void **) &p->d_info, ibytes)); p->device_bytes += ibytes;
+    CU_TRY(cudaMallocHost((void **) &p->h_info, ibytes));
+    const size_t rbytes = std::max<long long>(hp.relmap_size, 1) * sizeof(int);
+    CU_TRY(cudaMalloc((void **) &p->d_relmap, rbytes)); p->device_bytes += rbytes;
+    // relative maps of all updates, computed on the device
+    if (!hp.updates.empty()) {
+        std::vector<DevUpdate> du(hp.updates.size());
+        for (size_t t = 0; t < du.size(); t++) {
+            const Update &u = hp.updates[t];
+            du[t].ls_d = hp.pi[u.d] + u.p0; du[t].ls_s = hp.pi[u.s]; du[t].map_off = u.map_off;
+            du[t].nsrow_s = (int) (hp.pi[u.s + 1] - hp.pi[u.s]); du[t].nd2 = u.nd2;
+        }
+        DevUpdate *d_du = nullptr;
+        CU_TRY(cudaMalloc((void **) &d_du, du.size() * sizeof(DevUpdate)));
+        CU_TRY(cudaMemcpyAsync(d_du, du.data(), du.size() * sizeof(DevUpdate), cudaMemcpyHostToDevice, p->stream));
+        const size_t chunk = 1u << 30;
+        for (size_t b = 0; b < du.size(); b += chunk) {
+            const unsigned g = (unsigned) std::min(chunk, du.size() - b);
+            relmap_kernel<<<g, 128, 0, p->stream>>>(d_du + b, p->d_ls, p->d_relmap);
+        }
+        CU_TRY(cudaGetLastError());
+        CU_TRY(cudaStreamSynchronize(p->stream));
+        cudaFree(d_du);
+    }
+    CU_TRY(cudaStreamSynchronize(p->stream));
+    p->stats.nsuper = hp.nsuper; p->stats.nlevels = hp.nlevels; p->stats.nupdates = (ssb_long) hp.updates.size();
+    p->stats.flops_update = hp.flops_update; p->stats.flops_potrf = hp.flops_potrf; p->stats.flops_trsm = hp.flops_trsm;
+    p->stats.bytes_update_panel = hp.bytes_update_panel; p->stats.bytes_update_scatter = hp.bytes_update_scatter;
+    p->stats.device_bytes = (ssb_long) p->device_bytes;
+    return 0;
+}
+
+static ssb200_plan *plan_create_impl(ssb_long n, ssb_long nsuper, const ssb_long *super, const ssb_long *pi, const ssb_long *px,
+                                     const ssb_long *s, int device, const int *owner, int rank)
+{
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_error("no CUDA device: the hot path has no CPU fallback"); return nullptr; }
+    if (device < 0) { if (cudaGetDevice(&device) != cudaSuccess) device = 0; }
+    if (device >= ndev) { set_error("device ordinal out of range"); return nullptr; }
+    if (cudaSetDevice(device) != cudaSuccess) { set_error("cudaSetDevice failed"); return nullptr; }
+    ssb200_plan *p = new ssb200_plan();
+    p->device = device; p->bufA = new CscBuf(); p->bufF = new CscBuf();
+    if (!build_host_plan(n, nsuper, (const long long *) super, (const long long *) pi, (const long long *) px, (const long long *) s,
+                         owner, rank, p->hp)) {
+        set_error("invalid symbolic factor: " + p->hp.error); delete p; return nullptr;
+    }
+    if (cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("cudaStreamCreate failed"); delete p; return nullptr; }
+    if (plan_build_device(p) != 0) { plan_free(p); return nullptr; }
+    return p;
+}
+
+extern "C" ssb200_plan *ssb200_plan_create(ssb_long n, ssb_long nsuper, const ssb_long *super, const ssb_long *pi, const ssb_long *px,
+                                           const ssb_long *s, int device)
+{
+    return plan_create_impl(n, nsuper, super, pi, px, s, device, nullptr, 0);
+}
+
+extern "C" void ssb200_plan_destroy(ssb200_plan *plan) { plan_free(plan); }
+
+extern "C" int ssb200_plan_set_owner(ssb200_plan *plan, const int32_t *owner, int rank)
+{
+    (void) plan; (void) owner; (void) rank;
+    set_error("ssb200_plan_set_owner: elimination-tree sharding is not implemented in this round");
+    return SSB_CHOLMOD_NOT_INSTALLED;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// matrix upload
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T> static int ensure_cap(ssb200_plan *p, T **ptr, size_t *cap, size_t need)
+{
+    if (*cap >= need && *ptr) return 0;
+    if (*ptr) { cudaFree(*ptr); p->device_bytes -= *cap * sizeof(T); }
+    *cap = std::max<size_t>(need, 1);
+    CU_TRY(cudaMalloc((void **) ptr, *cap * sizeof(T)));
+    p->device_bytes += *cap * sizeof(T);
+    return 0;
+}
+
+static int upload_csc(ssb200_plan *p, const ssb_long *Hp, const ssb_long *Hi, const ssb_long *Hnz, const double *Hx, ssb_long ncol, CscBuf &b)
+{
+    const long long nz = Hp[ncol];     // also bounds the entries an unpacked matrix can reference
+    if (ensure_cap(p, &b.p, &b.capP, (size_t) ncol + 1)) return SSB_CHOLMOD_GPU_PROBLEM;
+    if (ensure_cap(p, &b.i, &b.capI, (size_t) std::max<long long>(nz, 1))) return SSB_CHOLMOD_GPU_PROBLEM;
+    if (ensure_cap(p, &b.x, &b.capX, (size_t) std::max<long long>(nz, 1))) return SSB_CHOLMOD_GPU_PROBLEM;
+    CU_TRY(cudaMemcpyAsync(b.p, Hp, (ncol + 1) * sizeof(long long), cudaMemcpyHostToDevice, p->stream));
+    if (nz > 0) {
+        CU_TRY(cudaMemcpyAsync(b.i, Hi, nz * sizeof(long long), cudaMemcpyHostToDevice, p->stream));
+        CU_TRY(cudaMemcpyAsync(b.x, Hx, nz * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    }
+    b.haveNz = (Hnz != nullptr);
+    if (Hnz) {
+        if (ensure_cap(p, &b.nz, &b.capNz, (size_t) std::max<long long>(ncol, 1))) return SSB_CHOLMOD_GPU_PROBLEM;
+        CU_TRY(cudaMemcpyAsync(b.nz, Hnz, ncol * sizeof(long long), cudaMemcpyHostToDevice, p->stream));
+    }
+    return 0;
+}
+
+extern "C" int ssb200_upload_A(ssb200_plan *p, int stype, const ssb_long *Ap, const ssb_long *Ai, const ssb_long *Anz, const double *Ax,
+                               ssb_long ncolA, const ssb_long *Fp, const ssb_long *Fi, const ssb_long *Fnz, const double *Fx)
+{
+    if (!p) { set_error("null plan"); return SSB_CHOLMOD_INVALID; }
+    if (stype > 0) { set_error("symmetric upper case not supported"); return SSB_CHOLMOD_INVALID; }
+    if (!Ap || (Ap[ncolA] > 0 && (!Ai || !Ax))) { set_error("null matrix arrays"); return SSB_CHOLMOD_INVALID; }
+    if (stype < 0 && ncolA != p->hp.n) { set_error("invalid dimensions"); return SSB_CHOLMOD_INVALID; }
+    if (stype == 0 && (!Fp || (Fp[p->hp.n] > 0 && (!Fi || !Fx)))) { set_error("F invalid"); return SSB_CHOLMOD_INVALID; }
+    CU_TRY(cudaSetDevice(p->device));
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0, p->stream);
+    if (upload_csc(p, Ap, Ai, Anz, Ax, ncolA, *p->bufA)) return SSB_CHOLMOD_GPU_PROBLEM;
+    if (stype == 0)
+        if (upload_csc(p, Fp, Fi, Fnz, Fx, p->hp.n, *p->bufF)) return SSB_CHOLMOD_GPU_PROBLEM;
+    cudaEventRecord(e1, p->stream);
+    CU_TRY(cudaStreamSynchronize(p->stream));
+    float ms = 0; cudaEventElapsedTime(&ms, e0, e1); p->stats.ms_h2d = ms;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    p->stype = stype; p->haveA = true;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// launches
+// ---------------------------------------------------------------------------------------------------------------
+static int run_launch(ssb200_plan *p, const Launch &L, const DevJobs &dj)
+{
+    switch (L.kind) {
+    case L_GEMM_BIG:
+        gemm_nt_sub_kernel<128><<<L.ntiles, gemm_threads<128>(), gemm_smem_bytes<128>(), p->stream>>>(dj.gemm_jobs + L.job0, dj.gemm_tiles + L.tile0, p->d_Lx, p->d_relmap);
+        break;
+    case L_GEMM_SMALL:
+        gemm_nt_sub_kernel<64><<<L.ntiles, gemm_threads<64>(), gemm_smem_bytes<64>(), p->stream>>>(dj.gemm_jobs + L.job0, dj.gemm_tiles + L.tile0, p->d_Lx, p->d_relmap);
+        break;
+    case L_POTRF:
+        potrf_block_kernel<<<L.njobs, POTRF_THREADS, 0, p->stream>>>(dj.potrf_jobs + L.job0, p->d_Lx, p->d_info);
+        break;
+    case L_TRSM:
+        trsm_rows_kernel<<<L.ntiles, TRSM_ROWS, 0, p->stream>>>(dj.trsm_jobs + L.job0, dj.trsm_tiles + L.tile0, p->d_Lx);
+        break;
+    default: set_error("bad launch kind"); return SSB_CHOLMOD_GPU_PROBLEM;
+    }
+    p->stats.kernel_launches++;
+    return 0;
+}
+
+static cudaEvent_t get_event(ssb200_plan *p, size_t idx)
+{
+    while (p->events.size() <= idx) { cudaEvent_t e; cudaEventCreate(&e); p->events.push_back(e); }
+    return p->events[idx];
+}
+
+static int scatter_A(ssb200_plan *p, double beta0, long long kfirst, long long kcount)
+{
+    if (kcount <= 0) return 0;
+    DevCsc A{p->bufA->p, p->bufA->i, p->bufA->haveNz ? p->bufA->nz : nullptr, p->bufA->x};
+    DevCsc F{p->bufF->p, p->bufF->i, p->bufF->haveNz ? p->bufF->nz : nullptr, p->bufF->x};
+    const int T = 128;
+    const long long g = (kcount + T - 1) / T;
+    scatter_A_kernel<<<(unsigned) g, T, 0, p->stream>>>(dev_sym(p), p->stype, A, F, beta0, p->d_Lx, kfirst, kcount, nullptr);
+    p->stats.kernel_launches++;
+    CU_TRY(cudaGetLastError());
+    return 0;
+}
+
+// Not positive definite: reproduce the reference's protocol (t_cholmod_super_numeric.c:905-968, 1052-1064).
+static int handle_not_posdef(ssb200_plan *p, int sfail, int info, double beta0, int quick_return, ssb_long *minor_out)
+{
+    HostPlan &hp = p->hp;
+    *minor_out = hp.super[sfail] + info - 1;
+    const long long psx = hp.px[sfail];
+    CU_TRY(cudaMemsetAsync(p->d_Lx + psx, 0, (size_t) (hp.xsize - psx) * sizeof(double), p->stream));
+    if (info == 1 || quick_return) { CU_TRY(cudaStreamSynchronize(p->stream)); return 0; }
+    // repeat supernode sfail, factorizing only its first info-1 columns
+    const int nscol = hp.super[sfail + 1] - hp.super[sfail];
+    const int nsrow = (int) (hp.pi[sfail + 1] - hp.pi[sfail]);
+    const int ncol_new = info - 1;
+    if (scatter_A(p, beta0, hp.super[sfail], nscol)) return SSB_CHOLMOD_GPU_PROBLEM;
+    HostPlan tmp;
+    {   // descendant updates of sfail
+        std::vector<GemmJob> all;
+        for (const Update &u : hp.updates) {
+            if (u.s != sfail) continue;
+            GemmJob g{};
+            g.a_off = hp.px[u.d] + u.p0; g.c_off = psx; g.map_off = u.map_off;
+            g.lda = (int) (hp.pi[u.d + 1] - hp.pi[u.d]); g.ldc = nsrow; g.K = hp.super[u.d + 1] - hp.super[u.d];
+            g.nd1 = u.nd1; g.nd2 = u.nd2; g.atomic = 1;
+            all.push_back(g);
+        }
+        // reuse the plan builder's tiling through a one-level fake: route everything through the 128-tile kernel
+        std::vector<int> &tiles = tmp.gemm_tiles;
+        Launch L{}; L.kind = L_GEMM_BIG; L.phase = 0; L.job0 = 0; L.tile0 = 0;
+        long long nt = 0; int nj = 0;
+        for (GemmJob g : all) {
+            g.nti = (g.nd2 + 127) / 128; g.ntj = (g.nd1 + 127) / 128; g.tile_start = (int) nt;
+            long long t = 0; for (int tj = 0; tj < g.ntj; tj++) t += g.nti - tj;
+            for (long long q = 0; q < t; q++) tiles.push_back(nj);
+            tmp.gemm_jobs.push_back(g); nt += t; nj++;
+        }
+        L.njobs = nj; L.ntiles = (int) nt;
+        if (nj) tmp.launches.push_back(L);
+    }
+    std::vector<int> one{sfail};
+    append_factor_jobs(hp, one, ncol_new, tmp);
+    DevJobs dj;
+    size_t saved = p->device_bytes;
+    if (upload_jobs(p, tmp, dj)) return SSB_CHOLMOD_GPU_PROBLEM;
+    for (const Launch &L : tmp.launches) if (run_launch(p, L, dj)) return SSB_CHOLMOD_GPU_PROBLEM;
+    CU_TRY(cudaGetLastError());
+    // zero the columns that were not factorized
+    CU_TRY(cudaMemsetAsync(p->d_Lx + psx + (long long) nsrow * ncol_new, 0, (size_t) nsrow * (nscol - ncol_new) * sizeof(double), p->stream));
+    CU_TRY(cudaStreamSynchronize(p->stream));
+    free_jobs(dj); p->device_bytes = saved;
+    return 0;
+}
+
+extern "C" int ssb200_factorize_resident(ssb200_plan *p, const double beta[2], int quick_return_if_not_posdef, ssb_long *minor_out)
+{
+    if (!p) { set_error("null plan"); return SSB_CHOLMOD_INVALID; }
+    if (!p->haveA) { set_error("no matrix uploaded"); return SSB_CHOLMOD_INVALID; }
+    HostPlan &hp = p->hp;
+    CU_TRY(cudaSetDevice(p->device));
+    p->stats.kernel_launches = 0;
+    if (minor_out) *minor_out = hp.n;
+    p->factor_on_device = false;
+    if (hp.nsuper == 0) { p->factor_on_device = true; return 0; }
+    const double beta0 = beta ? beta[0] : 0.0;
+    size_t ev = 0;
+    cudaEventRecord(get_event(p, ev++), p->stream);                               // 0: start
+    CU_TRY(cudaMemsetAsync(p->d_Lx, 0, (size_t) hp.xsize * sizeof(double), p->stream));   // zero all supernodes (:305-317)
+    {
+        const long long g = (hp.nsuper + 255) / 256;
+        fill_int_kernel<<<(unsigned) g, 256, 0, p->stream>>>(p->d_info, hp.nsuper, INT_MAX);
+        p->stats.kernel_launches++;
+    }
+    if (scatter_A(p, beta0, 0, hp.n)) return SSB_CHOLMOD_GPU_PROBLEM;
+    cudaEventRecord(get_event(p, ev++), p->stream);                               // 1: assembled
+    const char *stop = getenv("SSB200_DEBUG_STOP_LEVEL");                          // debugging aid: stop after this many levels
+    const int stop_level = stop ? atoi(stop) : INT_MAX;
+    // phase boundaries are timed with events: (phase, event index) pairs
+    std::vector<std::pair<int, size_t>> marks;
+    int cur_phase = -1;
+    for (int l = 0; l < hp.nlevels && l < stop_level; l++) {
+        for (int t = hp.level_launch_begin[l]; t < hp.level_launch_begin[l + 1]; t++) {
+            const Launch &L = hp.launches[t];
+            if (L.phase != cur_phase) { cudaEventRecord(get_event(p, ev), p->stream); marks.push_back({L.phase, ev}); ev++; cur_phase = L.phase; }
+            if (run_launch(p, L, p->jobs)) return SSB_CHOLMOD_GPU_PROBLEM;
+        }
+    }
+    cudaEventRecord(get_event(p, ev), p->stream); marks.push_back({-1, ev}); ev++;
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpyAsync(p->h_info, p->d_info, hp.nsuper * sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+    CU_TRY(cudaStreamSynchronize(p->stream));
+    // timings
+    float ms = 0;
+    cudaEventElapsedTime(&ms, p->events[0], p->events[1]); p->stats.ms_assemble = ms;
+    p->stats.ms_update = p->stats.ms_factor = 0;
+    for (size_t t = 0; t + 1 < marks.size(); t++) {
+        cudaEventElapsedTime(&ms, p->events[marks[t].second], p->events[marks[t + 1].second]);
+        if (marks[t].first == 0) p->stats.ms_update += ms; else p->stats.ms_factor += ms;
+    }
+    int status = 0;
+    int sfail = -1;
+    for (long long s = 0; s < hp.nsuper; s++) if (p->h_info[s] != INT_MAX) { sfail = (int) s; break; }
+    if (sfail >= 0) {
+        status = SSB_CHOLMOD_NOT_POSDEF;
+        ssb_long minor = hp.n;
+        if (handle_not_posdef(p, sfail, p->h_info[sfail], beta0, quick_return_if_not_posdef, &minor)) return SSB_CHOLMOD_GPU_PROBLEM;
+        if (minor_out) *minor_out = minor;
+    }
+    cudaEventRecord(get_event(p, ev), p->stream);
+    CU_TRY(cudaStreamSynchronize(p->stream));
+    cudaEventElapsedTime(&ms, p->events[0], p->events[ev]); p->stats.ms_total = ms;
+    p->stats.kernel_launches_total += p->stats.kernel_launches;
+    p->factor_on_device = true;
+    return status;
+}
+
+extern "C" int ssb200_download_L(ssb200_plan *p, double *Lx_host)
+{
+    if (!p || !Lx_host) { set_error("null argument"); return SSB_CHOLMOD_INVALID; }
+    CU_TRY(cudaSetDevice(p->device));
+    if (p->hp.xsize == 0) return 0;
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0, p->stream);
+    CU_TRY(cudaMemcpyAsync(Lx_host, p->d_Lx, (size_t) p->hp.xsize * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    cudaEventRecord(e1, p->stream);
+    CU_TRY(cudaStreamSynchronize(p->stream));
+    float ms = 0; cudaEventElapsedTime(&ms, e0, e1); p->stats.ms_d2h = ms;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return 0;
+}
+
+extern "C" int ssb200_upload_L(ssb200_plan *p, const double *Lx_host)
+{
+    if (!p || !Lx_host) { set_error("null argument"); return SSB_CHOLMOD_INVALID; }
+    CU_TRY(cudaSetDevice(p->device));
+    if (p->hp.xsize > 0) CU_TRY(cudaMemcpyAsync(p->d_Lx, Lx_host, (size_t) p->hp.xsize * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    CU_TRY(cudaStreamSynchronize(p->stream));
+    p->factor_on_device = true;
+    return 0;
+}
+
+extern "C" int ssb200_factorize(ssb200_plan *p, int stype, const ssb_long *Ap, const ssb_long *Ai, const ssb_long *Anz, const double *Ax,
+                                ssb_long ncolA, const ssb_long *Fp, const ssb_long *Fi, const ssb_long *Fnz, const double *Fx,
+                                const double beta[2], int quick_return_if_not_posdef, double *Lx_host, ssb_long *minor_out)
+{
+    int rc = ssb200_upload_A(p, stype, Ap, Ai, Anz, Ax, ncolA, Fp, Fi, Fnz, Fx);
+    if (rc) return rc;
+    rc = ssb200_factorize_resident(p, beta, quick_return_if_not_posdef, minor_out);
+    if (rc < 0) return rc;
+    if (Lx_host) { int r2 = ssb200_download_L(p, Lx_host); if (r2) return r2; }
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// solves
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" int ssb200_solve_resident(ssb200_plan *p, int which, double *dX, ssb_long nrhs, ssb_long ldx)
+{
+    if (!p || (!dX && p->hp.n > 0 && nrhs > 0)) { set_error("null argument"); return SSB_CHOLMOD_INVALID; }
+    if (!p->factor_on_device) { set_error("no numeric factor on the device"); return SSB_CHOLMOD_INVALID; }
+    if (which < 0 || which > 2) { set_error("which must be 0 (L), 1 (L') or 2 (both)"); return SSB_CHOLMOD_INVALID; }
+    CU_TRY(cudaSetDevice(p->device));
+    p->stats.kernel_launches = 0;
+    if (p->hp.n == 0 || nrhs == 0) return 0;
+    const HostPlan &hp = p->hp;
+    cudaEvent_t e0 = get_event(p, 0), e1 = get_event(p, 1);
+    cudaEventRecord(e0, p->stream);
+    const int nsteps = (int) hp.solve_steps.size();
+    if (which == 0 || which == 2) {
+        for (int t = 0; t < nsteps; t++) {
+            const SolveStep &st = hp.solve_steps[t];
+            lsolve_diag_kernel<<<st.njobs, SOLVE_THREADS, 0, p->stream>>>(p->d_solve_jobs + st.job0, p->d_Lx, dX, (int) nrhs, ldx);
+            p->stats.kernel_launches++;
+            if (st.ntiles > 0) {
+                lsolve_update_kernel<<<st.ntiles, SOLVE_THREADS, 0, p->stream>>>(p->d_solve_jobs + st.job0, p->d_solve_tiles + st.tile0, p->d_Lx, p->d_ls, dX, (int) nrhs, ldx);
+                p->stats.kernel_launches++;
+            }
+        }
+    }
+    if (which == 1 || which == 2) {
+        for (int t = nsteps - 1; t >= 0; t--) {
+            const SolveStep &st = hp.solve_steps[t];
+            if (st.ntiles > 0) {
+                ltsolve_update_kernel<<<st.ntiles, SOLVE_THREADS, 0, p->stream>>>(p->d_solve_jobs + st.job0, p->d_solve_tiles + st.tile0, p->d_Lx, p->d_ls, dX, (int) nrhs, ldx);
+                p->stats.kernel_launches++;
+            }
+            ltsolve_diag_kernel<<<st.njobs, SOLVE_THREADS, 0, p->stream>>>(p->d_solve_jobs + st.job0, p->d_Lx, dX, (int) nrhs, ldx);
+            p->stats.kernel_launches++;
+        }
+    }
+    cudaEventRecord(e1, p->stream);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaStreamSynchronize(p->stream));
+    float ms = 0; cudaEventElapsedTime(&ms, e0, e1); p->stats.ms_total = ms;
+    p->stats.kernel_launches_total += p->stats.kernel_launches;
+    return 0;
+}
+
+extern "C" int ssb200_solve(ssb200_plan *p, int which, double *X, ssb_long nrhs, ssb_long ldx)
+{
+    if (!p || (!X && p->hp.n > 0 && nrhs > 0)) { set_error("null argument"); return SSB_CHOLMOD_INVALID; }
+    const long long n = p->hp.n;
+    if (n == 0 || nrhs == 0) return 0;
+    if (ldx < n) { set_error("X and L dimensions must match"); return SSB_CHOLMOD_INVALID; }
+    CU_TRY(cudaSetDevice(p->device));
+    if (ensure_cap(p, &p->d_X, &p->capX, (size_t) n * nrhs)) return SSB_CHOLMOD_GPU_PROBLEM;
+    CU_TRY(cudaMemcpy2DAsync(p->d_X, n * sizeof(double), X, ldx * sizeof(double), n * sizeof(double), nrhs, cudaMemcpyHostToDevice, p->stream));
+    int rc = ssb200_solve_resident(p, which, p->d_X, nrhs, n);
+    if (rc) return rc;
+    CU_TRY(cudaMemcpy2DAsync(X, ldx * sizeof(double), p->d_X, n * sizeof(double), n * sizeof(double), nrhs, cudaMemcpyDeviceToHost, p->stream));
+    CU_TRY(cudaStreamSynchronize(p->stream));
+    return 0;
+}
+
+extern "C" double *ssb200_device_Lx(ssb200_plan *p) { return p ? p->d_Lx : nullptr; }
+extern "C" ssb_long ssb200_xsize(const ssb200_plan *p) { return p ? p->hp.xsize : 0; }
+extern "C" void *ssb200_stream(ssb200_plan *p) { return p ? (void *) p->stream : nullptr; }
+extern "C" int ssb200_get_stats(const ssb200_plan *p, ssb200_stats *out)
+{
+    if (!p || !out) return SSB_CHOLMOD_INVALID;
+    *out = p->stats; out->device_bytes = (ssb_long) p->device_bytes;
+    return 0;
+}
+
+// debugging aid for tests: copy the relative maps back (size = sum of ndrow2 over updates)
+extern "C" ssb_long ssb200_debug_relmap(ssb200_plan *p, int32_t *out, ssb_long cap)
+{
+    if (!p) return -1;
+    if (out && cap >= p->hp.relmap_size && p->hp.relmap_size > 0)
+        cudaMemcpy(out, p->d_relmap, p->hp.relmap_size * sizeof(int), cudaMemcpyDeviceToHost);
+    return p->hp.relmap_size;
+}
+
+// ===============================================================================================================
+// CHOLMOD drop-in layer
+// ===============================================================================================================
+typedef int (*change_factor_fn)(int, int, int, int, int, ssb_cholmod_factor *, ssb_cholmod_common *);
+typedef int (*error_fn)(int, const char *, int, const char *, ssb_cholmod_common *);
+
+static void *host_sym(const char *name) { return dlsym(RTLD_DEFAULT, name); }
+
+static int raise_error(ssb_cholmod_common *cm, int status, int line, const char *msg)
+{
+    static error_fn f = (error_fn) host_sym("cholmod_l_error");
+    if (!f) f = (error_fn) host_sym("cholmod_l_error");
+    if (f) return f(status, "suitesparse_b200/csrc/ssb_cuda.cu", line, msg, cm);
+    cm->status = status;                      // host libcholmod not loaded: keep the status protocol at least
+    return 1;
+}
+#define RAISE(cm, st, msg) raise_error(cm, st, __LINE__, msg)
+
+// plan cache keyed by the factor object, validated by a fingerprint of its symbolic structure
+struct CacheEntry {
+    const ssb_cholmod_factor *L = nullptr;
+    ssb200_plan *plan = nullptr;
+    size_t n = 0, nsuper = 0, ssize = 0, xsize = 0;
+    unsigned long long sym_hash = 0;
+    std::vector<long long> sample_idx; std::vector<double> sample_val;   // fingerprint of the numeric values last written to L->x
+    const void *xptr = nullptr;
+};
+static std::mutex g_cache_mu;
+static std::vector<CacheEntry> g_cache;
+
+static unsigned long long hash_symbolic(const ssb_cholmod_factor *L)
+{
+    unsigned long long h = 1469598103934665603ULL;
+    auto mix = [&](unsigned long long v) { h ^= v; h *= 1099511628211ULL; };
+    const long long *super = (const long long *) L->super, *pi = (const long long *) L->pi, *px = (const long long *) L->px, *s = (const long long *) L->s;
+    for (size_t t = 0; t <= L->nsuper; t++) { mix(super[t]); mix(pi[t]); mix(px[t]); }
+    const size_t ss = L->ssize ? (size_t) pi[L->nsuper] : 0;
+    const size_t step = std::max<size_t>(1, ss / 65536);
+    for (size_t t = 0; t < ss; t += step) mix(s[t]);
+    return h;
+}
+
+static size_t cache_capacity()
+{
+    const char *e = getenv("SSB200_PLAN_CACHE");
+    int c = e ? atoi(e) : 2;
+    return (size_t) std::max(1, c);
+}
+
+static CacheEntry *cache_find(const ssb_cholmod_factor *L)
+{
+    for (auto &e : g_cache) if (e.L == L) return &e;
+    return nullptr;
+}
+
+static void cache_drop(CacheEntry *e) { plan_free(e->plan); g_cache.erase(g_cache.begin() + (e - g_cache.data())); }
+
+// returns the (possibly new) entry for L; nullptr on failure
+static CacheEntry *cache_get_plan(ssb_cholmod_factor *L)
+{
+    const unsigned long long h = hash_symbolic(L);
+    CacheEntry *e = cache_find(L);
+    if (e && (e->n != L->n || e->nsuper != L->nsuper || e->ssize != L->ssize || e->xsize != L->xsize || e->sym_hash != h)) { cache_drop(e); e = nullptr; }
+    if (e) return e;
+    while (g_cache.size() >= cache_capacity()) cache_drop(&g_cache.front());
+    int dev = -1;
+    if (const char *d = getenv("SSB200_DEVICE")) dev = atoi(d);
+    ssb200_plan *plan = ssb200_plan_create((ssb_long) L->n, (ssb_long) L->nsuper, (const ssb_long *) L->super, (const ssb_long *) L->pi,
+                                           (const ssb_long *) L->px, (const ssb_long *) L->s, dev);
+    if (!plan) return nullptr;
+    CacheEntry ne; ne.L = L; ne.plan = plan; ne.n = L->n; ne.nsuper = L->nsuper; ne.ssize = L->ssize; ne.xsize = L->xsize; ne.sym_hash = h;
+    g_cache.push_back(ne);
+    return &g_cache.back();
+}
+
+static void take_value_fingerprint(CacheEntry *e, const ssb_cholmod_factor *L)
+{
+    const double *x = (const double *) L->x;
+    e->sample_idx.clear(); e->sample_val.clear(); e->xptr = L->x;
+    const size_t cnt = std::min<size_t>(L->xsize, 4096);
+    if (!cnt) return;
+    const size_t step = L->xsize / cnt;
+    for (size_t t = 0; t < cnt; t++) { const long long idx = (long long) (t * step); e->sample_idx.push_back(idx); e->sample_val.push_back(x[idx]); }
+}
+static bool value_fingerprint_ok(const CacheEntry *e, const ssb_cholmod_factor *L)
+{
+    if (!e->plan->factor_on_device || e->xptr != L->x) return false;
+    const double *x = (const double *) L->x;
+    for (size_t t = 0; t < e->sample_idx.size(); t++)
+        if (memcmp(&x[e->sample_idx[t]], &e->sample_val[t], sizeof(double)) != 0) return false;
+    return true;
+}
+
+static bool gpu_enabled_by_env()
+{
+    const char *e = getenv("CHOLMOD_USE_GPU");      // same switch the reference reads (cholmod_super_symbolic.c:257-296)
+    return !(e && atoi(e) == 0);
+}
+
+extern "C" int cholmod_l_super_numeric(ssb_cholmod_sparse *A, ssb_cholmod_sparse *F, double beta[2], ssb_cholmod_factor *L,
+                                       ssb_cholmod_common *Common)
+{
+    // ---- checks: same order and codes as cholmod_super_numeric.c:120-175 ----
+    if (!Common) return 0;
+    if (Common->itype != SSB_CHOLMOD_LONG || Common->dtype != SSB_CHOLMOD_DOUBLE) { Common->status = SSB_CHOLMOD_INVALID; return 0; }
+    if (!L || !A) { if (Common->status != SSB_CHOLMOD_OUT_OF_MEMORY) RAISE(Common, SSB_CHOLMOD_INVALID, "argument missing"); return 0; }
+    if (A->xtype < SSB_CHOLMOD_REAL || A->xtype > SSB_CHOLMOD_ZOMPLEX || !A->x || (A->xtype == SSB_CHOLMOD_ZOMPLEX && !A->z)) {
+        if (Common->status != SSB_CHOLMOD_OUT_OF_MEMORY) RAISE(Common, SSB_CHOLMOD_INVALID, "invalid xtype"); return 0; }
+    if (L->xtype < SSB_CHOLMOD_PATTERN || L->xtype > SSB_CHOLMOD_COMPLEX || (L->xtype != SSB_CHOLMOD_PATTERN && !L->x)) {
+        if (Common->status != SSB_CHOLMOD_OUT_OF_MEMORY) RAISE(Common, SSB_CHOLMOD_INVALID, "invalid xtype"); return 0; }
+    const int stype = A->stype;
+    if (stype < 0) {
+        if (A->nrow != A->ncol || A->nrow != L->n) { RAISE(Common, SSB_CHOLMOD_INVALID, "invalid dimensions"); return 0; }
+    } else if (stype == 0) {
+        if (A->nrow != L->n) { RAISE(Common, SSB_CHOLMOD_INVALID, "invalid dimensions"); return 0; }
+        if (!F) { if (Common->status != SSB_CHOLMOD_OUT_OF_MEMORY) RAISE(Common, SSB_CHOLMOD_INVALID, "argument missing"); return 0; }
+        if (F->xtype < SSB_CHOLMOD_REAL || F->xtype > SSB_CHOLMOD_ZOMPLEX || !F->x) { RAISE(Common, SSB_CHOLMOD_INVALID, "invalid xtype"); return 0; }
+        if (A->nrow != F->ncol || A->ncol != F->nrow || F->stype != 0) { RAISE(Common, SSB_CHOLMOD_INVALID, "F invalid"); return 0; }
+        if (A->xtype != F->xtype) { RAISE(Common, SSB_CHOLMOD_INVALID, "A and F must have same xtype"); return 0; }
+    } else { RAISE(Common, SSB_CHOLMOD_INVALID, "symmetric upper case not supported"); return 0; }
+    if (!L->is_super) { RAISE(Common, SSB_CHOLMOD_INVALID, "L not supernodal"); return 0; }
+    if (L->xtype != SSB_CHOLMOD_PATTERN) {
+        const bool ok = (A->xtype == SSB_CHOLMOD_REAL && L->xtype == SSB_CHOLMOD_REAL) || (A->xtype == SSB_CHOLMOD_COMPLEX && L->xtype == SSB_CHOLMOD_COMPLEX) ||
+                        (A->xtype == SSB_CHOLMOD_ZOMPLEX && L->xtype == SSB_CHOLMOD_COMPLEX);
+        if (!ok) { RAISE(Common, SSB_CHOLMOD_INVALID, "complex type mismatch"); return 0; }
+    }
+    Common->status = SSB_CHOLMOD_OK;
+    // ---- scope of the B200 path: real, 64-bit indices.  No CPU fallback. ----
+    if (A->xtype != SSB_CHOLMOD_REAL) { RAISE(Common, SSB_CHOLMOD_NOT_INSTALLED, "suitesparse_b200: complex/zomplex supernodal factorization is not provided on the GPU path"); return 0; }
+    if (A->itype != SSB_CHOLMOD_LONG || L->itype != SSB_CHOLMOD_LONG) { RAISE(Common, SSB_CHOLMOD_INVALID, "suitesparse_b200: only the cholmod_l_ (64-bit index) interface is accelerated"); return 0; }
+    if (!gpu_enabled_by_env()) { RAISE(Common, SSB_CHOLMOD_GPU_PROBLEM, "suitesparse_b200: CHOLMOD_USE_GPU=0 but this library has no CPU path; unload it to use the CPU"); return 0; }
+    // ---- numeric part of L (cholmod_super_numeric.c:206-228) ----
+    const bool symbolic = (L->xtype == SSB_CHOLMOD_PATTERN);
+    if (symbolic) {
+        static change_factor_fn cf = nullptr;
+        if (!cf) cf = (change_factor_fn) host_sym("cholmod_l_change_factor");
+        if (!cf) { RAISE(Common, SSB_CHOLMOD_INVALID, "suitesparse_b200: host libcholmod (cholmod_l_change_factor) not found in the process"); return 0; }
+        cf(SSB_CHOLMOD_REAL, 1, 1, 1, 1, L, Common);
+        if (Common->status < SSB_CHOLMOD_OK) return 0;               // L stays symbolic
+    }
+    L->is_ll = 1;
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    CacheEntry *e = cache_get_plan(L);
+    if (!e) { RAISE(Common, SSB_CHOLMOD_GPU_PROBLEM, ssb200_last_error()); return 0; }
+    ssb_long minor = (ssb_long) L->n;
+    const int rc = ssb200_factorize(e->plan, stype, (const ssb_long *) A->p, (const ssb_long *) A->i, A->packed ? nullptr : (const ssb_long *) A->nz,
+                                    (const double *) A->x, (ssb_long) A->ncol,
+                                    F ? (const ssb_long *) F->p : nullptr, F ? (const ssb_long *) F->i : nullptr,
+                                    (F && !F->packed) ? (const ssb_long *) F->nz : nullptr, F ? (const double *) F->x : nullptr,
+                                    beta, Common->quick_return_if_not_posdef, (double *) L->x, &minor);
+    if (rc < 0) { RAISE(Common, rc == SSB_CHOLMOD_INVALID ? SSB_CHOLMOD_INVALID : SSB_CHOLMOD_GPU_PROBLEM, ssb200_last_error()); return 0; }
+    take_value_fingerprint(e, L);
+    // statistics the reference keeps in Common (cholmod_core.h:1002-1048)
+    const ssb200_stats &st = e->plan->stats;
+    Common->gpu_syrk_calls = (size_t) st.nupdates; Common->gpu_gemm_calls = (size_t) st.nupdates;
+    Common->gpu_potrf_calls = (size_t) st.nsuper; Common->gpu_trsm_calls = (size_t) st.nsuper;
+    Common->cpu_syrk_calls = Common->cpu_gemm_calls = Common->cpu_potrf_calls = Common->cpu_trsm_calls = 0;
+    Common->gpu_syrk_time = st.ms_update * 1e-3; Common->gpu_gemm_time = 0; Common->gpu_potrf_time = st.ms_factor * 1e-3; Common->gpu_trsm_time = 0;
+    Common->assemble_time = st.ms_assemble * 1e-3; Common->assemble_time2 = st.ms_d2h * 1e-3;
+    Common->gpuKernelTime = st.ms_total * 1e-3; Common->gpuNumKernelLaunches = (int) st.kernel_launches;
+    Common->gpuFlops = (ssb_long) (st.flops_update + st.flops_potrf + st.flops_trsm);
+    if (rc == SSB_CHOLMOD_NOT_POSDEF) {
+        RAISE(Common, SSB_CHOLMOD_NOT_POSDEF, "matrix not positive definite");
+        L->minor = (size_t) minor;
+    } else {
+        L->minor = L->n;
+    }
+    return Common->status >= SSB_CHOLMOD_OK;
+}
+
+static int super_solve_common(ssb_cholmod_factor *L, ssb_cholmod_dense *X, ssb_cholmod_dense *E, ssb_cholmod_common *Common, int which)
+{
+    // checks: cholmod_super_solve.c:59-97
+    if (!Common) return 0;
+    if (Common->itype != SSB_CHOLMOD_LONG || Common->dtype != SSB_CHOLMOD_DOUBLE) { Common->status = SSB_CHOLMOD_INVALID; return 0; }
+    if (!L || !X || !E) { if (Common->status != SSB_CHOLMOD_OUT_OF_MEMORY) RAISE(Common, SSB_CHOLMOD_INVALID, "argument missing"); return 0; }
+    auto bad_xtype = [](int xt, const void *x) { return xt < SSB_CHOLMOD_REAL || xt > SSB_CHOLMOD_COMPLEX || !x; };
+    if (bad_xtype(L->xtype, L->x) || bad_xtype(X->xtype, X->x) || bad_xtype(E->xtype, E->x)) {
+        if (Common->status != SSB_CHOLMOD_OUT_OF_MEMORY) RAISE(Common, SSB_CHOLMOD_INVALID, "invalid xtype"); return 0; }
+    if (L->xtype != X->xtype) { RAISE(Common, SSB_CHOLMOD_INVALID, "L and X must have the same xtype"); return 0; }
+    if (L->xtype != E->xtype) { RAISE(Common, SSB_CHOLMOD_INVALID, "L and E must have the same xtype"); return 0; }
+    if (X->d < X->nrow || L->n != X->nrow) { RAISE(Common, SSB_CHOLMOD_INVALID, "X and L dimensions must match"); return 0; }
+    if (E->nzmax < X->ncol * L->maxesize) { RAISE(Common, SSB_CHOLMOD_INVALID, "workspace E not large enough"); return 0; }
+    if (!L->is_ll || !L->is_super) { RAISE(Common, SSB_CHOLMOD_INVALID, "L not supernodal"); return 0; }
+    Common->status = SSB_CHOLMOD_OK;
+    if (L->n == 0 || X->ncol == 0) return 1;
+    if (L->xtype != SSB_CHOLMOD_REAL) { RAISE(Common, SSB_CHOLMOD_NOT_INSTALLED, "suitesparse_b200: complex supernodal solve is not provided on the GPU path"); return 0; }
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    CacheEntry *e = cache_get_plan(L);
+    if (!e) { RAISE(Common, SSB_CHOLMOD_GPU_PROBLEM, ssb200_last_error()); return 0; }
+    if (!value_fingerprint_ok(e, L)) {
+        // L->x was produced or modified elsewhere: bring it to the device (still the GPU path, just slower)
+        if (ssb200_upload_L(e->plan, (const double *) L->x)) { RAISE(Common, SSB_CHOLMOD_GPU_PROBLEM, ssb200_last_error()); return 0; }
+        take_value_fingerprint(e, L);
+    }
+    const int rc = ssb200_solve(e->plan, which, (double *) X->x, (ssb_long) X->ncol, (ssb_long) X->d);
+    if (rc) { RAISE(Common, rc == SSB_CHOLMOD_INVALID ? SSB_CHOLMOD_INVALID : SSB_CHOLMOD_GPU_PROBLEM, ssb200_last_error()); return 0; }
+    return 1;
+}
+
+extern "C" int cholmod_l_super_lsolve(ssb_cholmod_factor *L, ssb_cholmod_dense *X, ssb_cholmod_dense *E, ssb_cholmod_common *Common)
+{
+    return super_solve_common(L, X, E, Common, 0);
+}
+extern "C" int cholmod_l_super_ltsolve(ssb_cholmod_factor *L, ssb_cholmod_dense *X, ssb_cholmod_dense *E, ssb_cholmod_common *Common)
+{
+    return super_solve_common(L, X, E, Common, 1);
+}
+
+// ---- cholmod_l_gpu_* (GPU/cholmod_gpu.c:71,170,208,255,364): resource queries and teardown -------------------------
+extern "C" int cholmod_l_gpu_memorysize(size_t *total_mem, size_t *available_mem, ssb_cholmod_common *Common)
+{
+    if (total_mem) *total_mem = 0;
+    if (available_mem) *available_mem = 0;
+    if (!Common) return 1;
+    size_t fr = 0, tot = 0;
+    if (cudaMemGetInfo(&fr, &tot) != cudaSuccess) { Common->status = SSB_CHOLMOD_GPU_PROBLEM; return 1; }   // nonzero = problem, as in the reference
+    if (total_mem) *total_mem = tot;
+    if (available_mem) *available_mem = fr;
+    Common->gpuMemorySize = fr;
+    return 0;
+}
+extern "C" int cholmod_l_gpu_probe(ssb_cholmod_common *Common)
+{
+    (void) Common;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return 0;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, 0) != cudaSuccess) return 0;
+    return prop.major >= 10;        // the kernels are sm_100a only
+}
+extern "C" int cholmod_l_gpu_allocate(ssb_cholmod_common *Common) { (void) Common; return 0; }      // plans own their memory; nothing to pre-allocate
+extern "C" int cholmod_l_gpu_deallocate(ssb_cholmod_common *Common)
+{
+    (void) Common;
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    while (!g_cache.empty()) cache_drop(&g_cache.back());
+    return 0;
+}
+extern "C" void cholmod_l_gpu_end(ssb_cholmod_common *Common) { cholmod_l_gpu_deallocate(Common); }
+
+// plan of a cached factor (tests / bench: statistics of the drop-in path)
+extern "C" ssb200_plan *ssb200_plan_of_factor(const ssb_cholmod_factor *L)
+{
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    CacheEntry *e = cache_find(L);
+    return e ? e->plan : nullptr;
+}

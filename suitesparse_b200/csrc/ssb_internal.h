@@ -1,0 +1,110 @@
+// ssb_internal.h — shared between the host plan builder (ssb_plan.cpp) and the CUDA side (ssb_cuda.cu).
+// Vocabulary follows CHOLMOD: supernode s, descendant d, panel, update, Ls (row indices), Lx (values).
+#pragma once
+#include <cstdint>
+#include <vector>
+#include <string>
+
+namespace ssb {
+
+// Blocking of one supernode's dense factorization (potrf of the diagonal block + trsm of the rows below,
+// t_cholmod_super_numeric.c:864,997), done as ONE right-looking blocked Cholesky of the tall nsrow x nscol block:
+//   outer panel NB columns: trailing update with K = NB (every C element is re-read once per NB columns)
+//   inner panel nb columns: unblocked potrf of the nb x nb block, substitution trsm of the rows below, K = nb update
+constexpr int NB_OUTER = 256;
+constexpr int NB_INNER = 64;
+constexpr int TRSM_ROWS = 128;      // rows per trsm tile
+
+// One C -= A * B^T job: A,B are row ranges of the SAME column-major panel (descendant d or a factor panel).
+//   C(i,j) = sum_k P(i,k) P(j,k),  i < nd2, j < nd1, i >= j (lower part only)
+//   target  Lx[c_off + map(i) + map(j)*ldc] -= C(i,j), map = relmap[map_off + .] or identity when map_off < 0
+struct GemmJob {
+    long long a_off;     // offset in Lx of P(0,0)
+    long long c_off;     // offset in Lx of the target block's (0,0)
+    long long map_off;   // offset in relmap, or -1 for the identity map
+    int lda, ldc;
+    int K, nd1, nd2;
+    int tile_start;      // first tile of this job inside its launch
+    int nti, ntj;        // tile rows / tile columns (tile column tj holds tiles ti = tj .. nti-1)
+    int atomic;          // 1: several jobs of the launch may hit the same target entries -> red.add
+    int pad;
+};
+
+// One panel job of the in-supernode factorization.
+struct PanelJob {
+    long long x_off;     // offset in Lx of the nb x nb diagonal block of this step
+    int lda;
+    int w;               // columns of this step (<= NB_INNER)
+    int rows_below;      // rows under the diagonal block (trsm rows)
+    int col0;            // first column of this step inside its supernode (for info)
+    int snode;           // supernode index (for info)
+    int tile_start;      // trsm: first tile of this job inside its launch
+};
+
+// One <=64-column slice of a supernode for the triangular solves: its diagonal block and every row of the supernode
+// below it (rows inside the diagonal part are addressed through Ls as well: Ls[psi+r] = k1+r for r < nscol).
+struct SolveJob {
+    long long x_off;     // offset in Lx of the diagonal block
+    long long ls_off;    // offset in Ls of the first row below the block
+    int lda, w, rows_below;
+    int xcol0;           // first column (= row of X) of the block
+    int tile_start;
+    int pad;
+};
+constexpr int SOLVE_ROWS = 512;     // rows per solve-update tile
+struct SolveStep { long long job0; int njobs; long long tile0; int ntiles; };
+
+enum LaunchKind : int { L_GEMM_BIG = 0, L_GEMM_SMALL = 1, L_POTRF = 2, L_TRSM = 3 };
+
+struct Launch {
+    int kind;
+    int phase;           // 0 = descendant update, 1 = factor (stats only)
+    long long job0;      // first job in the flat job array of that kind
+    int njobs;
+    long long tile0;     // first entry in the flat tile->job array of that kind (gemm, trsm)
+    int ntiles;
+};
+
+struct Update { int d, s; int p0, nd1, nd2; long long map_off; };
+
+struct HostPlan {
+    long long n = 0, nsuper = 0, ssize = 0, xsize = 0;
+    std::vector<int> super;          // nsuper+1
+    std::vector<long long> pi, px;   // nsuper+1
+    std::vector<int> ls;             // ssize (row indices, < 2^31)
+    std::vector<int> supermap;       // n
+    std::vector<int> level;          // etree level of every supernode
+    std::vector<int> parent;
+    int nlevels = 0;
+    std::vector<Update> updates;     // all (d,s) pairs, grouped by level of s
+    long long relmap_size = 0;
+    // flat device-bound arrays
+    std::vector<GemmJob> gemm_jobs;
+    std::vector<int> gemm_tiles;     // tile -> job index relative to the launch's job0
+    std::vector<PanelJob> potrf_jobs;
+    std::vector<PanelJob> trsm_jobs;
+    std::vector<int> trsm_tiles;
+    std::vector<Launch> launches;    // in execution order
+    std::vector<int> level_launch_begin; // nlevels+1
+    // solve schedule: supernodes ordered by level
+    std::vector<int> level_ptr;      // nlevels+1
+    std::vector<int> level_nodes;    // supernodes sorted by level
+    std::vector<SolveJob> solve_jobs;
+    std::vector<int> solve_tiles;
+    std::vector<SolveStep> solve_steps;   // forward order; the backward solve walks them in reverse
+    double flops_update = 0, flops_potrf = 0, flops_trsm = 0;
+    double bytes_update_panel = 0, bytes_update_scatter = 0;
+    std::string error;
+};
+
+// Builds everything above from the symbolic factor.  Returns false (plan.error set) on invalid structure.
+bool build_host_plan(long long n, long long nsuper, const long long *super, const long long *pi, const long long *px,
+                     const long long *s, const int *owner, int rank, HostPlan &plan);
+
+// Job lists for factorizing ONE supernode restricted to its first ncol_limit columns (not-positive-definite repeat,
+// t_cholmod_super_numeric.c:944-967).  Appends launches to `out`.
+void append_factor_jobs(const HostPlan &hp, const std::vector<int> &snodes, int ncol_limit, HostPlan &out);
+
+int gemm_tile_size(int kind);       // 128 for L_GEMM_BIG, 64 for L_GEMM_SMALL
+
+}  // namespace ssb

@@ -1,0 +1,484 @@
+// ssb_kernels.cuh — hand-written sm_100a kernels of the supernodal Cholesky hot path.
+//
+//   gemm_nt_sub_kernel   C -= A*B^T on fp64 tensor cores (mma.sync m8n8k4 = DMMA.8x8x4; tcgen05 has no f64 kind),
+//                        operands staged by a 3-stage cp.async ring, extend-add scatter through the relative map fused
+//                        into the epilogue.  Replaces dsyrk+dgemm+assembly (t_cholmod_super_numeric.c:676-772) and the
+//                        reference GPU path's cublasDsyrk/cublasDgemm/kernelAddUpdate (GPU/t_cholmod_gpu.c:514-620,
+//                        GPU/cholmod_gpu_kernels.cu:39-50); also the trailing updates inside a supernode's own potrf/trsm.
+//   potrf_block_kernel   unblocked Cholesky of one <=64x64 diagonal block in shared memory, LAPACK info contract
+//                        (t_cholmod_super_numeric.c:864-867).
+//   trsm_rows_kernel     rows-below substitution  B <- B * L11^{-T}  (dtrsm R,L,C,N, t_cholmod_super_numeric.c:997-1002).
+//   scatter_A_kernel     supernode assembly of A or A*F (+beta) (t_cholmod_super_numeric.c:353-431)
+//   relmap_kernel        RelativeMap of every update (t_cholmod_super_numeric.c:743-750, cholmod_gpu_kernels.cu:17-37)
+//   lsolve/ltsolve       level-scheduled supernodal triangular solves (t_cholmod_super_solve.c:60-130, 268-332)
+#pragma once
+#include "ssb_internal.h"
+#include <cuda_runtime.h>
+
+namespace ssb {
+
+// ------------------------------------------------------------------------------------------------------------------
+// small device helpers
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc, int src_bytes)
+{
+    unsigned s = (unsigned) __cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(s), "l"(gsrc), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+// D(8x8) += A(8x4, row) * B(4x8, col), fp64 tensor core
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ void red_add_f64(double *addr, double v)
+{
+    asm volatile("red.global.add.f64 [%0], %1;\n" ::"l"(addr), "d"(v) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// C -= A * B^T   (one CTA = one BT x BT tile of one job)
+// ------------------------------------------------------------------------------------------------------------------
+template <int BT> struct GemmCfg;
+template <> struct GemmCfg<128> { static constexpr int WARPS_M = 2, WARPS_N = 4, KB = 16, STAGES = 3; };
+template <> struct GemmCfg<64>  { static constexpr int WARPS_M = 2, WARPS_N = 2, KB = 16, STAGES = 3; };
+
+template <int BT> constexpr int gemm_threads() { return GemmCfg<BT>::WARPS_M * GemmCfg<BT>::WARPS_N * 32; }
+template <int BT> constexpr size_t gemm_smem_bytes()
+{
+    return (size_t) GemmCfg<BT>::STAGES * 2 * GemmCfg<BT>::KB * (BT + 4) * sizeof(double) + 2 * BT * sizeof(int);
+}
+
+template <int BT>
+__global__ void __launch_bounds__(GemmCfg<BT>::WARPS_M *GemmCfg<BT>::WARPS_N * 32)
+gemm_nt_sub_kernel(const GemmJob *__restrict__ jobs, const int *__restrict__ tile_job, double *__restrict__ Lx,
+                   const int *__restrict__ relmap)
+{
+    using Cfg = GemmCfg<BT>;
+    constexpr int NT = Cfg::WARPS_M * Cfg::WARPS_N * 32;
+    constexpr int KB = Cfg::KB, STAGES = Cfg::STAGES;
+    constexpr int WM = BT / Cfg::WARPS_M, WN = BT / Cfg::WARPS_N;
+    constexpr int MT = WM / 8, NTL = WN / 8;
+    constexpr int LD = BT + 4;                      // LD % 16 == 4: conflict-free 8-byte fragment loads
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *smem = reinterpret_cast<double *>(smem_raw);
+    int *rowmap = reinterpret_cast<int *>(smem + (size_t) STAGES * 2 * KB * LD);
+    int *colmap = rowmap + BT;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const GemmJob job = jobs[tile_job[blockIdx.x]];
+    // decode the tile: tile column tj holds tiles ti = tj .. nti-1
+    int rem = (int) blockIdx.x - job.tile_start, tj = 0;
+    while (rem >= job.nti - tj) { rem -= job.nti - tj; tj++; }
+    const int ti = tj + rem;
+    const int rowA0 = ti * BT, rowB0 = tj * BT;
+    const bool diag = (ti == tj);
+    const int K = job.K, nd1 = job.nd1, nd2 = job.nd2;
+    const long long lda = job.lda;
+    const double *__restrict__ P = Lx + job.a_off;
+
+    if (job.map_off >= 0) {
+        const int *rm = relmap + job.map_off;
+        for (int t = tid; t < BT; t += NT) {
+            rowmap[t] = (rowA0 + t < nd2) ? rm[rowA0 + t] : 0;
+            colmap[t] = (rowB0 + t < nd1) ? rm[rowB0 + t] : 0;
+        }
+    }
+
+    const int wm0 = (warp / Cfg::WARPS_N) * WM, wn0 = (warp % Cfg::WARPS_N) * WN;
+    // on a diagonal tile, a warp tile entirely above the diagonal contributes nothing
+    const bool warp_active = !(diag && (wm0 + WM <= wn0));
+
+    double acc[MT][NTL][2];
+#pragma unroll
+    for (int a = 0; a < MT; a++)
+#pragma unroll
+        for (int b = 0; b < NTL; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
+
+    auto load_stage = [&](int stage, int k0) {
+        double *As = smem + (size_t) stage * 2 * KB * LD;
+        double *Bs = As + KB * LD;
+#pragma unroll
+        for (int e = tid; e < BT * KB; e += NT) {
+            const int r = e % BT, k = e / BT;
+            const int gk = k0 + k;
+            {
+                const int gr = rowA0 + r;
+                const bool ok = (gr < nd2) && (gk < K);
+                const double *src = ok ? (P + gr + (long long) gk * lda) : P;
+                cp_async8(As + k * LD + r, src, ok ? 8 : 0);
+            }
+            if (!diag) {
+                const int gr = rowB0 + r;
+                const bool ok = (gr < nd1) && (gk < K);
+                const double *src = ok ? (P + gr + (long long) gk * lda) : P;
+                cp_async8(Bs + k * LD + r, src, ok ? 8 : 0);
+            }
+        }
+    };
+
+    const int nk = (K + KB - 1) / KB;
+#pragma unroll
+    for (int st = 0; st < STAGES - 1; st++) {
+        if (st < nk) load_stage(st, st * KB);
+        cp_async_commit();
+    }
+    for (int kc = 0; kc < nk; kc++) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        // prefetch chunk kc+STAGES-1 into the slot freed at iteration kc-1
+        {
+            const int nxt = kc + STAGES - 1;
+            if (nxt < nk) load_stage(nxt % STAGES, nxt * KB);
+            cp_async_commit();
+        }
+        if (warp_active) {
+            const double *As = smem + (size_t) (kc % STAGES) * 2 * KB * LD;
+            const double *Bs = diag ? As : As + KB * LD;
+#pragma unroll
+            for (int kk = 0; kk < KB; kk += 4) {
+                double a[MT], b[NTL];
+                const double *ap = As + (kk + (lane & 3)) * LD + wm0 + (lane >> 2);
+                const double *bp = Bs + (kk + (lane & 3)) * LD + wn0 + (lane >> 2);
+#pragma unroll
+                for (int m = 0; m < MT; m++) a[m] = ap[m * 8];
+#pragma unroll
+                for (int nn = 0; nn < NTL; nn++) b[nn] = bp[nn * 8];
+#pragma unroll
+                for (int m = 0; m < MT; m++)
+#pragma unroll
+                    for (int nn = 0; nn < NTL; nn++) dmma884(acc[m][nn][0], acc[m][nn][1], a[m], b[nn]);
+            }
+        }
+    }
+    cp_async_wait<0>();
+    __syncthreads();      // rowmap/colmap visible (also when nk == 0)
+
+    if (!warp_active) return;
+    // epilogue: extend-add.  acc[m][nn][e] = C(rowA0+wm0+m*8+lane/4, rowB0+wn0+nn*8+2*(lane%4)+e)
+    double *__restrict__ Cb = Lx + job.c_off;
+    const long long ldc = job.ldc;
+    const bool mapped = job.map_off >= 0;
+    const bool atomic = job.atomic != 0;
+#pragma unroll
+    for (int nn = 0; nn < NTL; nn++) {
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+            const int jl = wn0 + nn * 8 + 2 * (lane & 3) + e;
+            const int j = rowB0 + jl;
+            if (j >= nd1) continue;
+            const long long coff = mapped ? (long long) colmap[jl] * ldc : (long long) j * ldc;
+#pragma unroll
+            for (int m = 0; m < MT; m++) {
+                const int il = wm0 + m * 8 + (lane >> 2);
+                const int i = rowA0 + il;
+                if (i < nd2 && i >= j) {
+                    double *dst = Cb + coff + (mapped ? rowmap[il] : i);
+                    const double v = acc[m][nn][e];
+                    if (atomic) red_add_f64(dst, -v); else *dst -= v;
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// diagonal block Cholesky: one CTA per job, block w x w (w <= 64) in shared memory.
+// info[snode] = min(info, col0 + j + 1) at the first non-positive (or NaN) pivot (LAPACK dpotrf contract).
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int POTRF_THREADS = 256;
+__global__ void __launch_bounds__(POTRF_THREADS) potrf_block_kernel(const PanelJob *__restrict__ jobs, double *__restrict__ Lx,
+                                                                   int *__restrict__ info)
+{
+    constexpr int LDS = NB_INNER + 1;
+    __shared__ double T[NB_INNER * LDS];
+    const PanelJob job = jobs[blockIdx.x];
+    const int w = job.w, tid = threadIdx.x;
+    const long long lda = job.lda;
+    double *__restrict__ A = Lx + job.x_off;
+    for (int e = tid; e < w * w; e += POTRF_THREADS) {
+        const int i = e % w, j = e / w;
+        if (i >= j) T[i * LDS + j] = A[i + j * lda];
+    }
+    __syncthreads();
+    for (int j = 0; j < w; j++) {
+        const double d = T[j * LDS + j];
+        if (!(d > 0.0)) {
+            if (tid == 0) { atomicMin(&info[job.snode], job.col0 + j + 1); }
+            break;                                  // uniform: every thread read the same d
+        }
+        const double r = sqrt(d);
+        __syncthreads();                            // everyone has read T[j][j]
+        if (tid == 0) T[j * LDS + j] = r;
+        for (int i = j + 1 + tid; i < w; i += POTRF_THREADS) T[i * LDS + j] /= r;
+        __syncthreads();
+        // trailing rank-1 update of the lower part: T[i][k] -= T[i][j]*T[k][j], j < k <= i < w
+        const int m = w - j - 1;
+        for (int e = tid; e < m * m; e += POTRF_THREADS) {
+            const int i = j + 1 + e % m, k = j + 1 + e / m;
+            if (i >= k) T[i * LDS + k] -= T[i * LDS + j] * T[k * LDS + j];
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+    for (int e = tid; e < w * w; e += POTRF_THREADS) {
+        const int i = e % w, j = e / w;
+        if (i >= j) A[i + j * lda] = T[i * LDS + j];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// rows below the diagonal block:  B <- B * L11^{-T}.  One CTA = TRSM_ROWS rows, one thread per row, the row kept in
+// registers (NC = compile-time bound on the block width), L11 broadcast from shared memory.
+// ------------------------------------------------------------------------------------------------------------------
+template <int NC>
+__device__ __forceinline__ void trsm_rows_body(const PanelJob &job, int tile, double *__restrict__ Lx, double *Lsm)
+{
+    constexpr int LDS = NB_INNER + 1;
+    const int w = job.w, tid = threadIdx.x;
+    const long long lda = job.lda;
+    const double *__restrict__ L11 = Lx + job.x_off;
+    for (int e = tid; e < w * w; e += TRSM_ROWS) {
+        const int i = e % w, j = e / w;
+        if (i >= j) Lsm[i * LDS + j] = L11[i + j * lda];
+    }
+    __syncthreads();
+    const int r = tile * TRSM_ROWS + tid;
+    if (r >= job.rows_below) return;
+    double *__restrict__ B = Lx + job.x_off + w + r;      // row r below the block, column c at B[c*lda]
+    double x[NC];
+#pragma unroll
+    for (int c = 0; c < NC; c++) x[c] = (c < w) ? B[c * lda] : 0.0;
+#pragma unroll
+    for (int j = 0; j < NC; j++) {
+        if (j < w) {
+            double v = x[j];
+#pragma unroll
+            for (int k = 0; k < j; k++) v -= x[k] * Lsm[j * LDS + k];
+            x[j] = v / Lsm[j * LDS + j];
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < NC; c++) if (c < w) B[c * lda] = x[c];
+}
+
+__global__ void __launch_bounds__(TRSM_ROWS) trsm_rows_kernel(const PanelJob *__restrict__ jobs, const int *__restrict__ tile_job,
+                                                              double *__restrict__ Lx)
+{
+    __shared__ double Lsm[NB_INNER * (NB_INNER + 1)];
+    const PanelJob job = jobs[tile_job[blockIdx.x]];
+    const int tile = (int) blockIdx.x - job.tile_start;
+    if (job.w <= 8) trsm_rows_body<8>(job, tile, Lx, Lsm);
+    else if (job.w <= 16) trsm_rows_body<16>(job, tile, Lx, Lsm);
+    else if (job.w <= 32) trsm_rows_body<32>(job, tile, Lx, Lsm);
+    else trsm_rows_body<64>(job, tile, Lx, Lsm);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// assembly
+// ------------------------------------------------------------------------------------------------------------------
+struct DevSym {                 // device view of the symbolic factor
+    const int *super;           // nsuper+1
+    const long long *pi, *px;   // nsuper+1
+    const int *ls;              // ssize
+    const int *supermap;        // n
+    long long n, nsuper;
+};
+
+struct DevCsc { const long long *p, *i, *nz; const double *x; };
+
+__device__ __forceinline__ int find_row(const int *__restrict__ rows, int nrows, int target)
+{
+    int lo = 0, hi = nrows - 1;
+    while (lo <= hi) {
+        const int mid = (lo + hi) >> 1;
+        const int v = rows[mid];
+        if (v == target) return mid;
+        if (v < target) lo = mid + 1; else hi = mid - 1;
+    }
+    return -1;
+}
+
+// one thread per column k of L: copy A(k:n,k) (stype<0) or (A*F)(k:n,k) (stype==0) into its supernode, add beta.
+// Entries outside the pattern of L are dropped (the reference only avoids the segfault, :366-378).
+// only_snode >= 0 restricts the kernel to the columns of that supernode (not-posdef repeat).
+__global__ void scatter_A_kernel(DevSym sym, int stype, DevCsc A, DevCsc F, double beta, double *__restrict__ Lx,
+                                 long long kfirst, long long kcount, const int *__restrict__ owner_mask)
+{
+    const long long t = blockIdx.x * (long long) blockDim.x + threadIdx.x;
+    if (t >= kcount) return;
+    const long long k = kfirst + t;
+    const int s = sym.supermap[k];
+    if (owner_mask && !owner_mask[s]) return;
+    const int k1 = sym.super[s];
+    const long long psi = sym.pi[s];
+    const int nsrow = (int) (sym.pi[s + 1] - psi);
+    const int *__restrict__ rows = sym.ls + psi;
+    double *__restrict__ col = Lx + sym.px[s] + (k - k1) * (long long) nsrow;
+    if (stype != 0) {
+        long long p = A.p[k];
+        const long long pend = A.nz ? p + A.nz[k] : A.p[k + 1];
+        for (; p < pend; p++) {
+            const long long i = A.i[p];
+            if (i >= k) { const int im = find_row(rows, nsrow, (int) i); if (im >= 0) col[im] = A.x[p]; }
+        }
+    } else {
+        long long pf = F.p[k];
+        const long long pfend = F.nz ? pf + F.nz[k] : F.p[k + 1];
+        for (; pf < pfend; pf++) {
+            const long long j = F.i[pf];
+            const double fjk = F.x[pf];
+            long long p = A.p[j];
+            const long long pend = A.nz ? p + A.nz[j] : A.p[j + 1];
+            for (; p < pend; p++) {
+                const long long i = A.i[p];
+                if (i >= k) { const int im = find_row(rows, nsrow, (int) i); if (im >= 0) col[im] += A.x[p] * fjk; }
+            }
+        }
+    }
+    if (beta != 0.0) col[k - k1] += beta;
+}
+
+struct DevUpdate { long long ls_d, ls_s, map_off; int nsrow_s, nd2; };
+
+// RelativeMap: position of each remaining row of d inside s's row list.  One CTA per update.
+__global__ void relmap_kernel(const DevUpdate *__restrict__ ups, const int *__restrict__ ls, int *__restrict__ relmap)
+{
+    const DevUpdate u = ups[blockIdx.x];
+    const int *__restrict__ rows_s = ls + u.ls_s;
+    for (int i = threadIdx.x; i < u.nd2; i += blockDim.x)
+        relmap[u.map_off + i] = find_row(rows_s, u.nsrow_s, ls[u.ls_d + i]);
+}
+
+__global__ void fill_int_kernel(int *p, long long n, int v)
+{
+    const long long t = blockIdx.x * (long long) blockDim.x + threadIdx.x;
+    if (t < n) p[t] = v;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// triangular solves.  A "solve block" is a <=64-column slice of a supernode: its diagonal block, and every row of the
+// supernode below it (rows of the diagonal part are addressed through Ls too: Ls[psi+r] = k1+r for r < nscol).
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int SOLVE_THREADS = 128;
+
+// forward, step (a): x1 <- L11^{-1} x1 for every right-hand side
+__global__ void __launch_bounds__(SOLVE_THREADS) lsolve_diag_kernel(const SolveJob *__restrict__ jobs, const double *__restrict__ Lx,
+                                                                   double *__restrict__ X, int nrhs, long long ldx)
+{
+    constexpr int LDS = NB_INNER + 1;
+    __shared__ double T[NB_INNER * LDS];
+    __shared__ double xs[NB_INNER];
+    const SolveJob job = jobs[blockIdx.x];
+    const int w = job.w, tid = threadIdx.x;
+    const double *__restrict__ A = Lx + job.x_off;
+    for (int e = tid; e < w * w; e += SOLVE_THREADS) {
+        const int i = e % w, j = e / w;
+        if (i >= j) T[i * LDS + j] = A[i + (long long) j * job.lda];
+    }
+    for (int r = 0; r < nrhs; r++) {
+        double *__restrict__ x = X + r * ldx + job.xcol0;
+        __syncthreads();
+        if (tid < w) xs[tid] = x[tid];
+        __syncthreads();
+        for (int j = 0; j < w; j++) {
+            if (tid == j) xs[j] = xs[j] / T[j * LDS + j];
+            __syncthreads();
+            if (tid > j && tid < w) xs[tid] -= T[tid * LDS + j] * xs[j];
+            __syncthreads();
+        }
+        if (tid < w) x[tid] = xs[tid];
+    }
+}
+
+// forward, step (b): X[rows below] -= L2 * x1.  One CTA = SOLVE_ROWS rows of one job; atomics because several
+// supernodes of a level update the same ancestor rows.
+__global__ void __launch_bounds__(SOLVE_THREADS) lsolve_update_kernel(const SolveJob *__restrict__ jobs, const int *__restrict__ tile_job,
+                                                                     const double *__restrict__ Lx, const int *__restrict__ ls,
+                                                                     double *__restrict__ X, int nrhs, long long ldx)
+{
+    __shared__ double xs[NB_INNER];
+    const SolveJob job = jobs[tile_job[blockIdx.x]];
+    const int tile = (int) blockIdx.x - job.tile_start;
+    const int w = job.w, tid = threadIdx.x;
+    const int r0 = tile * SOLVE_ROWS;
+    const int r1 = min(job.rows_below, r0 + SOLVE_ROWS);
+    const double *__restrict__ L2 = Lx + job.x_off + w;     // row r below the block at L2[r + c*lda]
+    for (int rh = 0; rh < nrhs; rh++) {
+        double *__restrict__ x = X + rh * ldx;
+        __syncthreads();
+        if (tid < w) xs[tid] = x[job.xcol0 + tid];
+        __syncthreads();
+        for (int r = r0 + tid; r < r1; r += SOLVE_THREADS) {
+            double acc = 0.0;
+            const double *__restrict__ row = L2 + r;
+            for (int c = 0; c < w; c++) acc += row[(long long) c * job.lda] * xs[c];
+            red_add_f64(x + ls[job.ls_off + r], -acc);
+        }
+    }
+}
+
+// backward, step (a): x1 -= L2^T * X[rows below].  One CTA = SOLVE_ROWS rows of one job, partial dot products
+// reduced through shared memory, then one atomic per column.
+__global__ void __launch_bounds__(SOLVE_THREADS) ltsolve_update_kernel(const SolveJob *__restrict__ jobs, const int *__restrict__ tile_job,
+                                                                      const double *__restrict__ Lx, const int *__restrict__ ls,
+                                                                      double *__restrict__ X, int nrhs, long long ldx)
+{
+    __shared__ double xr[SOLVE_ROWS];
+    const SolveJob job = jobs[tile_job[blockIdx.x]];
+    const int tile = (int) blockIdx.x - job.tile_start;
+    const int w = job.w, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int r0 = tile * SOLVE_ROWS;
+    const int nr = min(job.rows_below, r0 + SOLVE_ROWS) - r0;
+    const double *__restrict__ L2 = Lx + job.x_off + w + r0;
+    for (int rh = 0; rh < nrhs; rh++) {
+        double *__restrict__ x = X + rh * ldx;
+        __syncthreads();
+        for (int r = tid; r < nr; r += SOLVE_THREADS) xr[r] = x[ls[job.ls_off + r0 + r]];
+        __syncthreads();
+        // warp `warp` handles columns warp, warp+4, ...: lanes stride the rows (coalesced along the column)
+        for (int c = warp; c < w; c += SOLVE_THREADS / 32) {
+            const double *__restrict__ col = L2 + (long long) c * job.lda;
+            double acc = 0.0;
+            for (int r = lane; r < nr; r += 32) acc += col[r] * xr[r];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (lane == 0) red_add_f64(x + job.xcol0 + c, -acc);
+        }
+    }
+}
+
+// backward, step (b): x1 <- L11^{-T} x1
+__global__ void __launch_bounds__(SOLVE_THREADS) ltsolve_diag_kernel(const SolveJob *__restrict__ jobs, const double *__restrict__ Lx,
+                                                                    double *__restrict__ X, int nrhs, long long ldx)
+{
+    constexpr int LDS = NB_INNER + 1;
+    __shared__ double T[NB_INNER * LDS];
+    __shared__ double xs[NB_INNER];
+    const SolveJob job = jobs[blockIdx.x];
+    const int w = job.w, tid = threadIdx.x;
+    const double *__restrict__ A = Lx + job.x_off;
+    for (int e = tid; e < w * w; e += SOLVE_THREADS) {
+        const int i = e % w, j = e / w;
+        if (i >= j) T[i * LDS + j] = A[i + (long long) j * job.lda];
+    }
+    for (int r = 0; r < nrhs; r++) {
+        double *__restrict__ x = X + r * ldx + job.xcol0;
+        __syncthreads();
+        if (tid < w) xs[tid] = x[tid];
+        __syncthreads();
+        for (int j = w - 1; j >= 0; j--) {
+            if (tid == j) xs[j] = xs[j] / T[j * LDS + j];
+            __syncthreads();
+            if (tid < j) xs[tid] -= T[j * LDS + tid] * xs[j];     // L^T(tid,j) = L(j,tid)
+            __syncthreads();
+        }
+        if (tid < w) x[tid] = xs[tid];
+    }
+}
+
+}  // namespace ssb

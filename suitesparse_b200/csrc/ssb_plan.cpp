@@ -1,0 +1,292 @@
+// ssb_plan.cpp — host-side plan builder: everything the reference discovers serially at run time with its
+// Head/Next/Lpos linked lists (t_cholmod_super_numeric.c:442-460,583-611,787-808,1021-1034) is a pure function of
+// the symbolic factor (super/pi/px/s), so it is computed once here and turned into flat, batched GPU work lists:
+//   * every (descendant d, ancestor s) update = a maximal run of d's sub-diagonal rows inside one ancestor
+//     (same walk as cholmod_super_symbolic.c:916-941), with its relative-map slot (t_cholmod_super_numeric.c:746-750)
+//   * the supernodal elimination tree parent(s) = SuperMap[Ls[psi+nscol]] (t_cholmod_super_numeric.c:1025) and its levels:
+//     supernodes of one level are independent, so a level is factorized by a handful of batched launches
+//   * per level: C -= A*B^T tile lists for the descendant updates, then the blocked potrf/trsm/update steps.
+#include "ssb_internal.h"
+#include <algorithm>
+#include <numeric>
+#include <cstring>
+
+namespace ssb {
+
+int gemm_tile_size(int kind) { return kind == L_GEMM_BIG ? 128 : 64; }
+
+namespace {
+
+// Append one launch of gemm jobs (already final except tile_start) of a given kind; builds the tile->job array.
+void emit_gemm_launch(HostPlan &hp, std::vector<GemmJob> &jobs, int kind, int phase)
+{
+    if (jobs.empty()) return;
+    const int T = gemm_tile_size(kind);
+    // heaviest jobs first: CTAs are dispatched in blockIdx order, so this is longest-processing-time-first
+    std::stable_sort(jobs.begin(), jobs.end(), [](const GemmJob &a, const GemmJob &b) {
+        return (double) a.K * a.nd1 * a.nd2 > (double) b.K * b.nd1 * b.nd2;
+    });
+    size_t pos = 0;
+    while (pos < jobs.size()) {
+        // keep every launch's tile count inside int range
+        Launch L{};
+        L.kind = kind; L.phase = phase;
+        L.job0 = (long long) hp.gemm_jobs.size();
+        L.tile0 = (long long) hp.gemm_tiles.size();
+        long long ntiles = 0;
+        int nj = 0;
+        while (pos < jobs.size()) {
+            GemmJob j = jobs[pos];
+            j.nti = (j.nd2 + T - 1) / T;
+            j.ntj = (j.nd1 + T - 1) / T;
+            long long t = 0;
+            for (int tj = 0; tj < j.ntj; tj++) t += j.nti - tj;
+            if (ntiles + t > 1500000000LL && nj > 0) break;
+            j.tile_start = (int) ntiles;
+            hp.gemm_jobs.push_back(j);
+            for (long long q = 0; q < t; q++) hp.gemm_tiles.push_back(nj);
+            ntiles += t; nj++; pos++;
+        }
+        L.njobs = nj; L.ntiles = (int) ntiles;
+        hp.launches.push_back(L);
+    }
+    jobs.clear();
+}
+
+void emit_update_launches(HostPlan &hp, std::vector<GemmJob> &small, std::vector<GemmJob> &big, int phase)
+{
+    emit_gemm_launch(hp, big, L_GEMM_BIG, phase);
+    emit_gemm_launch(hp, small, L_GEMM_SMALL, phase);
+}
+
+inline void route_gemm(const GemmJob &j, std::vector<GemmJob> &small, std::vector<GemmJob> &big)
+{
+    if (j.nd2 <= 64) small.push_back(j); else big.push_back(j);
+}
+
+}  // namespace
+
+// Blocked factorization steps for a set of mutually independent supernodes (one etree level, or one repeated
+// supernode with ncol_limit >= 0).  Appends to out.{potrf_jobs,trsm_jobs,trsm_tiles,gemm_jobs,gemm_tiles,launches}.
+void append_factor_jobs(const HostPlan &hp, const std::vector<int> &snodes, int ncol_limit, HostPlan &out)
+{
+    int maxcol = 0;
+    for (int s : snodes) {
+        int nscol = hp.super[s + 1] - hp.super[s];
+        if (ncol_limit >= 0) nscol = std::min(nscol, ncol_limit);
+        maxcol = std::max(maxcol, nscol);
+    }
+    std::vector<GemmJob> gs, gb;
+    for (int J0 = 0; J0 < maxcol; J0 += NB_OUTER) {
+        for (int j0 = J0; j0 < std::min(J0 + NB_OUTER, maxcol); j0 += NB_INNER) {
+            Launch LP{}; LP.kind = L_POTRF; LP.phase = 1; LP.job0 = (long long) out.potrf_jobs.size();
+            Launch LT{}; LT.kind = L_TRSM; LT.phase = 1; LT.job0 = (long long) out.trsm_jobs.size();
+            LT.tile0 = (long long) out.trsm_tiles.size();
+            long long ttiles = 0;
+            for (int s : snodes) {
+                int nscol = hp.super[s + 1] - hp.super[s];
+                if (ncol_limit >= 0) nscol = std::min(nscol, ncol_limit);
+                if (nscol <= j0) continue;
+                const int nsrow = (int) (hp.pi[s + 1] - hp.pi[s]);
+                const int w = std::min(NB_INNER, nscol - j0);
+                PanelJob pj{};
+                pj.x_off = hp.px[s] + j0 + (long long) j0 * nsrow;
+                pj.lda = nsrow; pj.w = w; pj.rows_below = nsrow - j0 - w; pj.col0 = j0; pj.snode = s; pj.tile_start = 0;
+                out.potrf_jobs.push_back(pj);
+                LP.njobs++;
+                if (pj.rows_below > 0) {
+                    pj.tile_start = (int) ttiles;
+                    int nt = (pj.rows_below + TRSM_ROWS - 1) / TRSM_ROWS;
+                    for (int q = 0; q < nt; q++) out.trsm_tiles.push_back(LT.njobs);
+                    ttiles += nt;
+                    out.trsm_jobs.push_back(pj);
+                    LT.njobs++;
+                    // inner trailing update: remaining columns of the outer panel
+                    const int outer_end = std::min(J0 + NB_OUTER, nscol);
+                    const int ct = outer_end - (j0 + w);
+                    if (ct > 0) {
+                        GemmJob g{};
+                        g.a_off = hp.px[s] + (j0 + w) + (long long) j0 * nsrow;
+                        g.c_off = hp.px[s] + (j0 + w) + (long long) (j0 + w) * nsrow;
+                        g.map_off = -1; g.lda = nsrow; g.ldc = nsrow; g.K = w; g.nd1 = ct; g.nd2 = nsrow - j0 - w; g.atomic = 0;
+                        route_gemm(g, gs, gb);
+                    }
+                }
+            }
+            if (LP.njobs) out.launches.push_back(LP);
+            LT.ntiles = (int) ttiles;
+            if (LT.njobs) out.launches.push_back(LT);
+            emit_update_launches(out, gs, gb, 1);
+        }
+        // outer trailing update with the whole NB_OUTER-wide panel
+        for (int s : snodes) {
+            int nscol = hp.super[s + 1] - hp.super[s];
+            if (ncol_limit >= 0) nscol = std::min(nscol, ncol_limit);
+            if (nscol <= J0) continue;
+            const int nsrow = (int) (hp.pi[s + 1] - hp.pi[s]);
+            const int W = std::min(NB_OUTER, nscol - J0);
+            const int ct = nscol - (J0 + W);
+            if (ct <= 0) continue;
+            GemmJob g{};
+            g.a_off = hp.px[s] + (J0 + W) + (long long) J0 * nsrow;
+            g.c_off = hp.px[s] + (J0 + W) + (long long) (J0 + W) * nsrow;
+            g.map_off = -1; g.lda = nsrow; g.ldc = nsrow; g.K = W; g.nd1 = ct; g.nd2 = nsrow - J0 - W; g.atomic = 0;
+            route_gemm(g, gs, gb);
+        }
+        emit_update_launches(out, gs, gb, 1);
+    }
+}
+
+bool build_host_plan(long long n, long long nsuper, const long long *super, const long long *pi, const long long *px,
+                     const long long *s, const int *owner, int rank, HostPlan &hp)
+{
+    hp = HostPlan();
+    if (n < 0 || nsuper < 0 || (nsuper > 0 && (!super || !pi || !px || !s))) { hp.error = "null symbolic arrays"; return false; }
+    if (n >= (1LL << 31) - 1 || nsuper >= (1LL << 31) - 1) { hp.error = "n too large for 32-bit device row indices"; return false; }
+    hp.n = n; hp.nsuper = nsuper;
+    hp.super.resize(nsuper + 1); hp.pi.resize(nsuper + 1); hp.px.resize(nsuper + 1);
+    for (long long t = 0; t <= nsuper; t++) { hp.super[t] = (int) super[t]; hp.pi[t] = pi[t]; hp.px[t] = px[t]; }
+    if (nsuper == 0) { hp.level_ptr.assign(1, 0); hp.level_launch_begin.assign(1, 0); return true; }
+    if (hp.super[0] != 0 || super[nsuper] != n || pi[0] != 0) { hp.error = "super/pi do not start at 0 or end at n"; return false; }
+    hp.ssize = pi[nsuper]; hp.xsize = px[nsuper];
+    hp.ls.resize(hp.ssize);
+    hp.supermap.assign(n, -1);
+    for (long long t = 0; t < nsuper; t++) {
+        const long long nscol = super[t + 1] - super[t], nsrow = pi[t + 1] - pi[t];
+        if (nscol <= 0 || nsrow < nscol || nsrow >= (1LL << 31) - 1 || px[t + 1] - px[t] < nscol * nsrow) { hp.error = "inconsistent supernode sizes"; return false; }
+        for (long long k = super[t]; k < super[t + 1]; k++) hp.supermap[k] = (int) t;
+        long long prev = -1;
+        for (long long p = pi[t]; p < pi[t + 1]; p++) {
+            const long long r = s[p];
+            if (r < 0 || r >= n || r <= prev) { hp.error = "row indices of a supernode must be sorted, unique and in range"; return false; }
+            if (p - pi[t] < nscol && r != super[t] + (p - pi[t])) { hp.error = "leading rows of a supernode must be its own columns"; return false; }
+            prev = r; hp.ls[p] = (int) r;
+        }
+    }
+    // ---- updates, etree parent, levels --------------------------------------------------------------------
+    hp.parent.assign(nsuper, -1);
+    hp.level.assign(nsuper, 0);
+    std::vector<Update> ups;
+    for (int d = 0; d < (int) nsuper; d++) {
+        const int ndcol = hp.super[d + 1] - hp.super[d];
+        const long long pdi = hp.pi[d], pdend = hp.pi[d + 1];
+        long long p = pdi + ndcol;
+        while (p < pdend) {
+            const int sa = hp.supermap[hp.ls[p]];
+            if (sa <= d) { hp.error = "row index below a supernode's own columns"; return false; }
+            long long q = p;
+            while (q < pdend && hp.supermap[hp.ls[q]] == sa) q++;
+            if (hp.parent[d] < 0) hp.parent[d] = sa;
+            Update u{d, sa, (int) (p - pdi), (int) (q - p), (int) (pdend - p), 0};
+            ups.push_back(u);
+            p = q;
+        }
+    }
+    for (int t = 0; t < (int) nsuper; t++)
+        if (hp.parent[t] >= 0) hp.level[hp.parent[t]] = std::max(hp.level[hp.parent[t]], hp.level[t] + 1);
+    hp.nlevels = 1 + *std::max_element(hp.level.begin(), hp.level.end());
+    // supernodes by level (counting sort keeps index order inside a level)
+    hp.level_ptr.assign(hp.nlevels + 1, 0);
+    for (int t = 0; t < (int) nsuper; t++) hp.level_ptr[hp.level[t] + 1]++;
+    for (int l = 0; l < hp.nlevels; l++) hp.level_ptr[l + 1] += hp.level_ptr[l];
+    hp.level_nodes.resize(nsuper);
+    { std::vector<int> fill(hp.level_ptr.begin(), hp.level_ptr.end() - 1);
+      for (int t = 0; t < (int) nsuper; t++) hp.level_nodes[fill[hp.level[t]]++] = t; }
+    // updates grouped by the level of their target
+    std::stable_sort(ups.begin(), ups.end(), [&](const Update &a, const Update &b) { return hp.level[a.s] < hp.level[b.s]; });
+    long long moff = 0;
+    for (auto &u : ups) { u.map_off = moff; moff += u.nd2; }
+    hp.relmap_size = moff;
+    hp.updates.swap(ups);
+    // ---- per level launches ----------------------------------------------------------------------------------
+    hp.level_launch_begin.assign(hp.nlevels + 1, 0);
+    size_t upos = 0;
+    std::vector<GemmJob> gs, gb;
+    std::vector<int> nodes;
+    for (int l = 0; l < hp.nlevels; l++) {
+        hp.level_launch_begin[l] = (int) hp.launches.size();
+        // which targets receive more than one update in this level -> atomics needed (different CTAs, same entries)
+        size_t ubeg = upos;
+        while (upos < hp.updates.size() && hp.level[hp.updates[upos].s] == l) upos++;
+        for (size_t t = ubeg; t < upos; t++) {
+            const Update &u = hp.updates[t];
+            if (owner && owner[u.s] != rank) continue;
+            const int ndcol = hp.super[u.d + 1] - hp.super[u.d];
+            const int ndrow = (int) (hp.pi[u.d + 1] - hp.pi[u.d]);
+            const int nsrow = (int) (hp.pi[u.s + 1] - hp.pi[u.s]);
+            GemmJob g{};
+            g.a_off = hp.px[u.d] + u.p0;
+            g.c_off = hp.px[u.s];
+            g.map_off = u.map_off; g.lda = ndrow; g.ldc = nsrow; g.K = ndcol; g.nd1 = u.nd1; g.nd2 = u.nd2; g.atomic = 1;
+            route_gemm(g, gs, gb);
+            const double tri = (double) u.nd1 * u.nd2 - 0.5 * (double) u.nd1 * (u.nd1 - 1);
+            hp.flops_update += 2.0 * ndcol * tri;
+            hp.bytes_update_panel += 8.0 * (double) u.nd2 * ndcol;
+            hp.bytes_update_scatter += 16.0 * tri;
+        }
+        emit_update_launches(hp, gs, gb, 0);
+        nodes.clear();
+        for (int t = hp.level_ptr[l]; t < hp.level_ptr[l + 1]; t++) {
+            const int sn = hp.level_nodes[t];
+            if (owner && owner[sn] != rank) continue;
+            nodes.push_back(sn);
+            const double nscol = hp.super[sn + 1] - hp.super[sn], nsrow = (double) (hp.pi[sn + 1] - hp.pi[sn]);
+            hp.flops_potrf += nscol * nscol * nscol / 3.0;
+            hp.flops_trsm += nscol * nscol * (nsrow - nscol);
+        }
+        if (!nodes.empty()) append_factor_jobs(hp, nodes, -1, hp);
+    }
+    hp.level_launch_begin[hp.nlevels] = (int) hp.launches.size();
+    // ---- solve schedule: per level, per 64-column block index ------------------------------------------------
+    for (int l = 0; l < hp.nlevels; l++) {
+        int maxcol = 0;
+        for (int t = hp.level_ptr[l]; t < hp.level_ptr[l + 1]; t++) {
+            const int sn = hp.level_nodes[t];
+            if (owner && owner[sn] != rank) continue;
+            maxcol = std::max(maxcol, hp.super[sn + 1] - hp.super[sn]);
+        }
+        for (int j0 = 0; j0 < maxcol; j0 += NB_INNER) {
+            SolveStep st{(long long) hp.solve_jobs.size(), 0, (long long) hp.solve_tiles.size(), 0};
+            for (int t = hp.level_ptr[l]; t < hp.level_ptr[l + 1]; t++) {
+                const int sn = hp.level_nodes[t];
+                if (owner && owner[sn] != rank) continue;
+                const int nscol = hp.super[sn + 1] - hp.super[sn];
+                if (nscol <= j0) continue;
+                const int nsrow = (int) (hp.pi[sn + 1] - hp.pi[sn]);
+                SolveJob sj{};
+                sj.w = std::min(NB_INNER, nscol - j0);
+                sj.x_off = hp.px[sn] + j0 + (long long) j0 * nsrow;
+                sj.ls_off = hp.pi[sn] + j0 + sj.w;
+                sj.lda = nsrow; sj.rows_below = nsrow - j0 - sj.w; sj.xcol0 = hp.super[sn] + j0;
+                sj.tile_start = st.ntiles;
+                const int nt = (sj.rows_below + SOLVE_ROWS - 1) / SOLVE_ROWS;
+                for (int q = 0; q < nt; q++) hp.solve_tiles.push_back(st.njobs);
+                st.ntiles += nt;
+                hp.solve_jobs.push_back(sj);
+                st.njobs++;
+            }
+            if (st.njobs) hp.solve_steps.push_back(st);
+        }
+    }
+    return true;
+}
+
+}  // namespace ssb
+
+// Host-only view of the plan (no GPU needed): sizes of the schedule, for tests and for DESIGN.md's tables.
+//  out[0]=nlevels out[1]=nupdates out[2]=relmap_size out[3]=nlaunches out[4]=gemm jobs out[5]=gemm tiles
+//  out[6]=potrf jobs out[7]=trsm jobs out[8]=trsm tiles out[9]=solve steps out[10]=solve jobs
+//  out[11]=flops_update out[12]=flops_potrf out[13]=flops_trsm out[14]=bytes_update_panel out[15]=bytes_update_scatter
+extern "C" int ssb200_plan_summary(long long n, long long nsuper, const long long *super, const long long *pi, const long long *px,
+                                   const long long *s, double *out, int *level_of_supernode)
+{
+    ssb::HostPlan hp;
+    if (!ssb::build_host_plan(n, nsuper, super, pi, px, s, nullptr, 0, hp)) return -4;
+    out[0] = hp.nlevels; out[1] = (double) hp.updates.size(); out[2] = (double) hp.relmap_size; out[3] = (double) hp.launches.size();
+    out[4] = (double) hp.gemm_jobs.size(); out[5] = (double) hp.gemm_tiles.size(); out[6] = (double) hp.potrf_jobs.size();
+    out[7] = (double) hp.trsm_jobs.size(); out[8] = (double) hp.trsm_tiles.size(); out[9] = (double) hp.solve_steps.size();
+    out[10] = (double) hp.solve_jobs.size(); out[11] = hp.flops_update; out[12] = hp.flops_potrf; out[13] = hp.flops_trsm;
+    out[14] = hp.bytes_update_panel; out[15] = hp.bytes_update_scatter;
+    if (level_of_supernode) for (long long t = 0; t < nsuper; t++) level_of_supernode[t] = hp.level[t];
+    return 0;
+}

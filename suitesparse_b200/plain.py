@@ -1,0 +1,148 @@
+"""ctypes binding of the PLAIN layer of include/suitesparse_b200.h (ssb200_*): raw arrays in, raw arrays out.
+The library is required — there is no CPU fallback; a missing .so or a missing GPU raises."""
+from __future__ import annotations
+import ctypes as C
+import numpy as np
+from .cholmod_host import load_b200
+
+c_long = C.c_int64
+
+
+class Stats(C.Structure):
+    _fields_ = [("nsuper", c_long), ("nlevels", c_long), ("nupdates", c_long),
+                ("kernel_launches", c_long), ("kernel_launches_total", c_long),
+                ("flops_update", C.c_double), ("flops_potrf", C.c_double), ("flops_trsm", C.c_double),
+                ("ms_total", C.c_double), ("ms_assemble", C.c_double), ("ms_update", C.c_double),
+                ("ms_factor", C.c_double), ("ms_d2h", C.c_double), ("ms_h2d", C.c_double),
+                ("bytes_update_panel", C.c_double), ("bytes_update_scatter", C.c_double),
+                ("device_bytes", c_long)]
+
+    def asdict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+def _lib():
+    L = load_b200()
+    if not getattr(L, "_ssb_typed", False):
+        L.ssb200_plan_create.restype = C.c_void_p
+        L.ssb200_plan_create.argtypes = [c_long, c_long, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.ssb200_plan_destroy.argtypes = [C.c_void_p]
+        L.ssb200_factorize.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, c_long,
+                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                       C.c_void_p, C.POINTER(c_long)]
+        L.ssb200_upload_A.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, c_long,
+                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ssb200_factorize_resident.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(c_long)]
+        L.ssb200_download_L.argtypes = [C.c_void_p, C.c_void_p]
+        L.ssb200_upload_L.argtypes = [C.c_void_p, C.c_void_p]
+        L.ssb200_solve.argtypes = [C.c_void_p, C.c_int, C.c_void_p, c_long, c_long]
+        L.ssb200_solve_resident.argtypes = [C.c_void_p, C.c_int, C.c_void_p, c_long, c_long]
+        L.ssb200_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
+        L.ssb200_last_error.restype = C.c_char_p
+        L.ssb200_version.restype = C.c_char_p
+        L.ssb200_device_Lx.restype = C.c_void_p
+        L.ssb200_device_Lx.argtypes = [C.c_void_p]
+        L.ssb200_xsize.restype = c_long
+        L.ssb200_xsize.argtypes = [C.c_void_p]
+        L.ssb200_debug_relmap.restype = c_long
+        L.ssb200_debug_relmap.argtypes = [C.c_void_p, C.c_void_p, c_long]
+        L.ssb200_plan_of_factor.restype = C.c_void_p
+        L.ssb200_plan_of_factor.argtypes = [C.c_void_p]
+        L._ssb_typed = True
+    return L
+
+
+def _i64(a):
+    return np.ascontiguousarray(a, dtype=np.int64)
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class SsbError(RuntimeError):
+    pass
+
+
+class Plan:
+    """Device plan + device-resident factor for one symbolic supernodal structure (super/pi/px/s)."""
+
+    def __init__(self, n, super_, pi, px, s, device: int = -1, handle=None):
+        self.lib = _lib()
+        self.n = int(n)
+        self.owned = handle is None
+        if handle is None:
+            self.super, self.pi, self.px, self.s = _i64(super_), _i64(pi), _i64(px), _i64(s)
+            self.nsuper = self.super.size - 1
+            handle = self.lib.ssb200_plan_create(self.n, self.nsuper, _ptr(self.super), _ptr(self.pi), _ptr(self.px),
+                                                 _ptr(self.s), device)
+            if not handle:
+                raise SsbError(self.lib.ssb200_last_error().decode())
+        self.h = C.c_void_p(handle)
+        self.xsize = int(self.lib.ssb200_xsize(self.h))
+
+    def _check(self, rc):
+        if rc < 0:
+            raise SsbError(f"status {rc}: {self.lib.ssb200_last_error().decode()}")
+        return rc
+
+    def close(self):
+        if self.h and self.owned:
+            self.lib.ssb200_plan_destroy(self.h)
+        self.h = None
+
+    def upload_A(self, A_lower, F=None):
+        Ap, Ai, Ax = _i64(A_lower.indptr), _i64(A_lower.indices), np.ascontiguousarray(A_lower.data, dtype=np.float64)
+        self._keepA = (Ap, Ai, Ax)
+        if F is None:
+            return self._check(self.lib.ssb200_upload_A(self.h, -1, _ptr(Ap), _ptr(Ai), None, _ptr(Ax), A_lower.shape[1],
+                                                        None, None, None, None))
+        Fp, Fi, Fx = _i64(F.indptr), _i64(F.indices), np.ascontiguousarray(F.data, dtype=np.float64)
+        return self._check(self.lib.ssb200_upload_A(self.h, 0, _ptr(Ap), _ptr(Ai), None, _ptr(Ax), A_lower.shape[1],
+                                                    _ptr(Fp), _ptr(Fi), None, _ptr(Fx)))
+
+    def factorize_resident(self, beta: float = 0.0, quick_return: bool = False):
+        b = (C.c_double * 2)(beta, 0.0)
+        minor = c_long(0)
+        st = self._check(self.lib.ssb200_factorize_resident(self.h, b, 1 if quick_return else 0, C.byref(minor)))
+        return st, minor.value
+
+    def download_L(self, out: np.ndarray | None = None) -> np.ndarray:
+        if out is None:
+            out = np.empty(self.xsize, dtype=np.float64)
+        self._check(self.lib.ssb200_download_L(self.h, _ptr(out)))
+        return out
+
+    def factorize(self, A_lower, beta: float = 0.0, quick_return: bool = False, F=None):
+        """One call = upload A, factorize on the device, download L.  Returns (status, minor, Lx)."""
+        self.upload_A(A_lower, F)
+        st, minor = self.factorize_resident(beta, quick_return)
+        return st, minor, self.download_L()
+
+    def solve(self, X: np.ndarray, which: int = 2) -> np.ndarray:
+        X = np.array(X, dtype=np.float64, order="F", copy=True)
+        X2 = X.reshape(X.shape[0], -1, order="F")
+        self._check(self.lib.ssb200_solve(self.h, which, _ptr(X2), X2.shape[1], X2.shape[0]))
+        return X
+
+    def solve_resident(self, dX_ptr: int, nrhs: int, ldx: int, which: int = 2):
+        self._check(self.lib.ssb200_solve_resident(self.h, which, C.c_void_p(dX_ptr), nrhs, ldx))
+
+    def stats(self) -> dict:
+        st = Stats()
+        self.lib.ssb200_get_stats(self.h, C.byref(st))
+        return st.asdict()
+
+    def relmap(self) -> np.ndarray:
+        nrel = self.lib.ssb200_debug_relmap(self.h, None, 0)
+        out = np.empty(max(nrel, 1), dtype=np.int32)
+        self.lib.ssb200_debug_relmap(self.h, _ptr(out), nrel)
+        return out[:nrel]
+
+
+def plan_of_factor(Lp) -> Plan | None:
+    """The plan the drop-in layer cached for a cholmod_factor (statistics of the interposed path)."""
+    h = _lib().ssb200_plan_of_factor(Lp)
+    if not h:
+        return None
+    return Plan(Lp.contents.n, None, None, None, None, handle=h)
