@@ -1,0 +1,308 @@
+#!/usr/bin/env python
+"""bench.py — supernodal Cholesky factorize GFLOP/s (fp64) on B200, plus solve GB/s (BASELINE.json's metric).
+
+  python bench.py --gpus N --steps K --warmup W          # our arm (CUDA path through the C ABI)
+  python bench.py --impl reference --steps K --warmup W  # the reference's own CPU+BLAS path on the host cores
+
+A "step" is one numeric factorization (cholmod_l_super_numeric) of the workload matrix with a symbolic factor that
+already exists (the refactorization loop of a Newton / time-stepping code: analyze once, factorize many times).
+  value   factorize GFLOP/s = Common->fl / t, A and the plan resident in HBM, timed with CUDA events on the plan's stream
+  e2e     the same metric through the drop-in C-ABI call cholmod_l_super_numeric(S, NULL, beta, L, Common) with HOST
+          buffers: S is uploaded and L->x (xsize doubles) is copied back inside the timed region, every step
+  solve   forward+backward triangular solve GB/s = 16*xsize / t  (extra keys)
+  roofline  the dominant kernel (gemm_nt_sub_kernel<128>, DMMA) against a cuBLAS DGEMM peak measured in this run
+  cpu_baseline  the reference library (oracle/_ref) timed on the host cores on a bounded sample
+Workload: BASELINE.json configs[1], the 3-D 7-point Laplacian 128^3 (n = 2 097 152, L = 29 GB), geometric nested
+dissection (MESHND) passed as the user permutation.  The other configs are parity-test cases (tests/).
+Multi-GPU (N > 1): the elimination-tree shard is not implemented in this round; every rank factorizes its own replica
+("replicas only", scaling = weak) and the value is the sum over ranks.
+"""
+from __future__ import annotations
+import argparse, ctypes as C, json, os, subprocess, sys, threading, time
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--kind", default=os.environ.get("SSB200_BENCH_KIND", "lap7"))
+    ap.add_argument("--N", type=int, default=int(os.environ.get("SSB200_BENCH_N", "128")))
+    ap.add_argument("--cpu-sample-N", type=int, default=0, help="mesh size of the CPU sample (0 = choose from the step count)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def build_problem(ch, kind, N):
+    """A (upper CSC), ND permutation, symbolic factor, S = tril(P A P') as cholmod_factorize_p builds it."""
+    from suitesparse_b200 import gen
+    A, perm = gen.make_problem(kind, N)
+    S = ch.sparse(A, +1)
+    t0 = time.time()
+    Lp = ch.analyze(S, perm)
+    t_an = time.time() - t0
+    S2 = ch.lower_permuted(S, Lp)
+    return A, perm, S, Lp, S2, t_an
+
+
+def cpu_sample_size(steps, warmup, budget_s=150.0):
+    # measured factorize seconds of the reference CPU path on 8 host threads (BASELINE.md §2 and this repo's runs)
+    est = [(32, 0.3), (48, 1.6), (64, 7.0), (80, 28.0), (96, 75.0)]
+    per = budget_s / max(1, steps + warmup)
+    best = 32
+    for n, t in est:
+        if t <= per:
+            best = n
+    return best
+
+
+def time_reference_steps(kind, N, steps, warmup):
+    """The reference's own cholmod_l_super_numeric (CPU, BLAS threads = all host cores) on lap7 N^3."""
+    from suitesparse_b200.cholmod_host import Cholmod
+    ch = Cholmod(gpu=False)
+    A, perm, S, Lp, S2, t_an = build_problem(ch, kind, N)
+    fl = ch.cm.fl
+    f = ch.hot("cholmod_l_super_numeric")
+    beta = (C.c_double * 2)(0.0, 0.0)
+    for _ in range(warmup):
+        f(S2, None, beta, Lp, C.byref(ch.cm))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        ok = f(S2, None, beta, Lp, C.byref(ch.cm))
+    dt = (time.perf_counter() - t0) / max(1, steps)
+    assert ok and ch.cm.status == 0
+    xsize = Lp.contents.xsize
+    # solve sample
+    b = np.ones(A.shape[0])
+    ts = time.perf_counter(); x = ch.solve(Lp, b); ts = time.perf_counter() - ts
+    import scipy.sparse as sp
+    Af = A + sp.triu(A, 1).T
+    resid = float(np.linalg.norm(Af @ x - b) / np.linalg.norm(b))
+    ch.free_sparse(S2); ch.free_factor(Lp)
+    return dict(gflops=fl / dt / 1e9, sec=dt, fl=fl, xsize=xsize, solve_gbs=16.0 * xsize / ts / 1e9, resid=resid, n=A.shape[0])
+
+
+class ClockSampler:
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index; self.samples = []; self.proc = None
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.gpu)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True); self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            parts = [p.strip() for p in s.split(",")]
+            if len(parts) < 8:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm_sorted = sorted(sm)
+        # "under load": the upper half of the samples (idle gaps between steps pull the clock down)
+        med = sm_sorted[len(sm_sorted) // 2] if sm_sorted else None
+        return {"sm_mhz": med, "sm_max_mhz": (max(mx) if mx else None), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measure_fp64_peak(torch, dev):
+    """cuBLAS DGEMM ceiling on this GPU (MEASURED_PEAKS.json holds only bf16 and HBM)."""
+    n = 8192
+    a = torch.randn(n, n, dtype=torch.float64, device=dev); b = torch.randn(n, n, dtype=torch.float64, device=dev)
+    torch.matmul(a, b); torch.cuda.synchronize(dev)
+    best = 1e9
+    for _ in range(5):
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(); torch.matmul(a, b); e1.record(); torch.cuda.synchronize(dev)
+        best = min(best, e0.elapsed_time(e1))
+    del a, b
+    torch.cuda.empty_cache()
+    return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    workload = f"{args.kind} {args.N}^3, geometric ND (MESHND) as UserPerm, supernodal LL', refactorization step"
+
+    # -------------------------------------------------------------------------------------------------- reference arm
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        Ns = args.cpu_sample_N or cpu_sample_size(args.steps, args.warmup)
+        r = time_reference_steps(args.kind, Ns, args.steps, args.warmup)
+        cores = os.cpu_count()
+        sample = f"{args.kind} {Ns}^3 (n={r['n']}, fl={r['fl']:.3e}); the full {args.N}^3 step takes ~180 s on 8 cores"
+        out = {"impl": "reference", "metric": "supernodal Cholesky factorize GFLOP/s (fp64)", "value": round(r["gflops"], 2), "unit": "GFLOP/s",
+               "n_gpus": 0, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(r["sec"] * 1e3, 2), "higher_is_better": True,
+               "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+               "config": {"workload": workload, "sample": sample},
+               "cpu_baseline": {"value": round(r["gflops"], 2), "unit": "GFLOP/s", "cores": cores, "kind": "reference", "sample": sample,
+                                "blas": "OpenBLAS (scipy-bundled), threads = all host cores", "solve_GBps": round(r["solve_gbs"], 2), "resid": r["resid"]},
+               "e2e": {"value": round(r["gflops"], 2), "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(out), flush=True)
+        return
+
+    # -------------------------------------------------------------------------------------------------------- our arm
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback")
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    os.environ["SSB200_DEVICE"] = str(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    from suitesparse_b200.cholmod_host import Cholmod
+    from suitesparse_b200 import plain
+
+    ch = Cholmod(gpu=True)
+    A, perm, S, Lp, S2, t_an = build_problem(ch, args.kind, args.N)
+    n = A.shape[0]; fl = ch.cm.fl; lnz = ch.cm.lnz
+    Lc = Lp.contents
+    xsize = Lc.xsize; nsuper = Lc.nsuper
+    f_numeric = ch.hot("cholmod_l_super_numeric")
+    beta = (C.c_double * 2)(0.0, 0.0)
+
+    # ---- e2e: drop-in call with host buffers (first call allocates L->x, builds + caches the plan, pins L->x)
+    t0 = time.perf_counter()
+    ok = f_numeric(S2, None, beta, Lp, C.byref(ch.cm))
+    t_first = time.perf_counter() - t0
+    if not ok or ch.cm.status != 0:
+        raise SystemExit(f"factorize failed: status {ch.cm.status}")
+    pl = plain.plan_of_factor(Lp)
+    sampler = ClockSampler(local); sampler.start()
+    e2e_warm = 1
+    for _ in range(e2e_warm):
+        f_numeric(S2, None, beta, Lp, C.byref(ch.cm))
+    if dist: dist.barrier()
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    launches_e2e = 0
+    for _ in range(args.steps):
+        f_numeric(S2, None, beta, Lp, C.byref(ch.cm))
+        launches_e2e += ch.cm.gpuNumKernelLaunches
+    torch.cuda.synchronize(dev)
+    t_e2e = (time.perf_counter() - t0) / args.steps
+    st_e2e = pl.stats()
+
+    # ---- value: resident factorization (A already uploaded by the calls above), CUDA-event time from the plan
+    for _ in range(args.warmup):
+        pl.factorize_resident()
+    if dist: dist.barrier()
+    torch.cuda.synchronize(dev)
+    ms_steps = []; kind_ms = np.zeros(4); kind_fl = np.zeros(4); kind_n = np.zeros(4); launches = 0
+    tw0 = time.perf_counter()
+    for _ in range(args.steps):
+        st, minor = pl.factorize_resident()
+        s_ = pl.stats()
+        ms_steps.append(s_["ms_total"]); kind_ms += np.array(s_["ms_kind"]); kind_fl += np.array(s_["flops_kind"]); kind_n += np.array(s_["launches_kind"])
+        launches += s_["kernel_launches"]
+    torch.cuda.synchronize(dev)
+    wall_res = (time.perf_counter() - tw0) / args.steps
+    if dist: dist.barrier()
+    ms_step = float(np.mean(ms_steps))
+
+    # ---- solve: resident forward+backward, nrhs = 1
+    b = np.ones(n)
+    dX = torch.ones(n, dtype=torch.float64, device=dev)
+    for _ in range(2):
+        pl.solve_resident(dX.data_ptr(), 1, n, which=2)
+    solve_ms = []
+    for _ in range(max(3, args.steps)):
+        dX.fill_(1.0)
+        pl.solve_resident(dX.data_ptr(), 1, n, which=2)
+        solve_ms.append(pl.stats()["ms_total"])
+    solve_launches = pl.stats()["kernel_launches"]
+    solve_ms_v = float(np.median(solve_ms))
+    clocks = sampler.stop()
+    # e2e solve through cholmod_l_solve (host B, host X; P and P' applied by the host library)
+    ts = time.perf_counter(); x = ch.solve(Lp, b); t_solve_e2e = time.perf_counter() - ts
+    import scipy.sparse as sp
+    Af = A + sp.triu(A, 1).T
+    resid = float(np.linalg.norm(Af @ x - b) / np.linalg.norm(b))
+
+    # ---- reduce over ranks (max time), aggregate
+    t_dev = ms_step * 1e-3; t_host = t_e2e
+    if dist:
+        tt = torch.tensor([t_dev, t_host], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_dev, t_host = tt.tolist()
+    value = world * fl / t_dev / 1e9
+    e2e_v = world * fl / t_host / 1e9
+
+    if rank == 0:
+        peak_tf = measure_fp64_peak(torch, dev)
+        gi = 0   # gemm_nt_sub_kernel<128>
+        ach = (kind_fl[gi] / (kind_ms[gi] * 1e-3) / 1e12) if kind_ms[gi] > 0 else 0.0
+        names = ["gemm_nt_sub_kernel<128>", "gemm_nt_sub_kernel<64>", "potrf_block_kernel", "trsm_rows_kernel"]
+        share = {names[k]: round(float(kind_ms[k] / max(kind_ms.sum(), 1e-9)), 4) for k in range(4)}
+        a_bytes = int(S2.contents.nzmax) * 16 + (n + 1) * 8
+        out = {"metric": "supernodal Cholesky factorize GFLOP/s (fp64)", "value": round(value, 1), "unit": "GFLOP/s", "n_gpus": world,
+               "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(t_dev * 1e3, 2), "higher_is_better": True,
+               "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+               "config": {"workload": workload, "n": n, "nnz_tril_A": int(S2.contents.nzmax), "fl": fl, "lnz": lnz, "nsuper": int(nsuper), "xsize": int(xsize),
+                          "levels": st_e2e["nlevels"], "updates": st_e2e["nupdates"], "l2": "inputs_exceed_l2 (L is %.1f GB)" % (xsize * 8 / 1e9),
+                          "parallelism": "1 GPU" if world == 1 else f"replicas only x{world} (etree shard not implemented this round)",
+                          "analyze_s_host": round(t_an, 2), "first_call_s": round(t_first, 2)},
+               "e2e": {"value": round(e2e_v, 1), "unit": "GFLOP/s", "h2d_bytes_per_step": a_bytes, "d2h_bytes_per_step": int(xsize) * 8,
+                       "ms_per_step": round(t_host * 1e3, 2), "call": "cholmod_l_super_numeric(S,NULL,beta,L,Common) via the interposed C ABI, host buffers, L->x page-locked once",
+                       "ms_h2d": round(st_e2e["ms_h2d"], 2), "ms_d2h": round(st_e2e["ms_d2h"], 2)},
+               "gpu_launches": int(launches),
+               "clocks": clocks,
+               "roofline": {"kernel": names[gi], "bound": "tensor", "achieved": round(ach, 2), "peak": round(peak_tf, 2), "unit": "TFLOP/s",
+                            "frac": round(ach / peak_tf, 4) if peak_tf else None, "traffic": None,
+                            "peak_source": "cuBLAS DGEMM 8192^3 (torch.matmul fp64) measured in this run; MEASURED_PEAKS.json has no fp64 entry",
+                            "kernel_time_share": share, "launches_per_step": [int(v / args.steps) for v in kind_n],
+                            "whole_step_frac_of_peak": round(fl / t_dev / 1e12 / peak_tf, 4) if peak_tf else None},
+               "solve": {"value": round(16.0 * xsize / (solve_ms_v * 1e-3) / 1e9, 1), "unit": "GB/s", "ms": round(solve_ms_v, 3), "launches": int(solve_launches),
+                         "hbm_peak_GBps": json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(REPO, "MEASURED_PEAKS.json")) else 6650.0,
+                         "e2e_cholmod_l_solve_ms": round(t_solve_e2e * 1e3, 2), "resid_2norm_rel": resid},
+               "wall_ms_per_resident_step": round(wall_res * 1e3, 2)}
+        out["solve"]["frac_of_hbm"] = round(out["solve"]["value"] / out["solve"]["hbm_peak_GBps"], 4)
+        if not args.no_cpu_baseline and world == 1:
+            Ns = args.cpu_sample_N or 64
+            # separate process: the interposed symbols of this process must not be bound there
+            try:
+                p = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "2", "--warmup", "1", "--cpu-sample-N", str(Ns),
+                                    "--kind", args.kind, "--N", str(args.N)], capture_output=True, text=True, timeout=600)
+                ref = json.loads(p.stdout.strip().splitlines()[-1])
+                out["cpu_baseline"] = ref["cpu_baseline"]
+            except Exception as ex:          # noqa
+                out["cpu_baseline"] = {"value": None, "unit": "GFLOP/s", "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {ex}"}
+        print(json.dumps(out), flush=True)
+    ch.free_sparse(S2)
+    if dist:
+        dist.barrier(); dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -370,13 +370,12 @@ extern "C" int ssb200_factorize_resident(ssb200_plan *p, const double beta[2], i
     cudaEventRecord(get_event(p, ev++), p->stream);                               // 1: assembled
     const char *stop = getenv("SSB200_DEBUG_STOP_LEVEL");                          // debugging aid: stop after this many levels
     const int stop_level = stop ? atoi(stop) : INT_MAX;
-    // phase boundaries are timed with events: (phase, event index) pairs
+    // every launch is bracketed by events on the plan's stream: (launch index, event index) pairs
     std::vector<std::pair<int, size_t>> marks;
-    int cur_phase = -1;
     for (int l = 0; l < hp.nlevels && l < stop_level; l++) {
         for (int t = hp.level_launch_begin[l]; t < hp.level_launch_begin[l + 1]; t++) {
             const Launch &L = hp.launches[t];
-            if (L.phase != cur_phase) { cudaEventRecord(get_event(p, ev), p->stream); marks.push_back({L.phase, ev}); ev++; cur_phase = L.phase; }
+            cudaEventRecord(get_event(p, ev), p->stream); marks.push_back({t, ev}); ev++;
             if (run_launch(p, L, p->jobs)) return SSB_CHOLMOD_GPU_PROBLEM;
         }
     }
@@ -388,9 +387,12 @@ extern "C" int ssb200_factorize_resident(ssb200_plan *p, const double beta[2], i
     float ms = 0;
     cudaEventElapsedTime(&ms, p->events[0], p->events[1]); p->stats.ms_assemble = ms;
     p->stats.ms_update = p->stats.ms_factor = 0;
+    for (int k = 0; k < 4; k++) { p->stats.ms_kind[k] = 0; p->stats.flops_kind[k] = 0; p->stats.launches_kind[k] = 0; }
     for (size_t t = 0; t + 1 < marks.size(); t++) {
         cudaEventElapsedTime(&ms, p->events[marks[t].second], p->events[marks[t + 1].second]);
-        if (marks[t].first == 0) p->stats.ms_update += ms; else p->stats.ms_factor += ms;
+        const Launch &L = hp.launches[marks[t].first];
+        if (L.phase == 0) p->stats.ms_update += ms; else p->stats.ms_factor += ms;
+        p->stats.ms_kind[L.kind] += ms; p->stats.flops_kind[L.kind] += L.flops; p->stats.launches_kind[L.kind]++;
     }
     int status = 0;
     int sfail = -1;
@@ -552,6 +554,7 @@ struct CacheEntry {
     unsigned long long sym_hash = 0;
     std::vector<long long> sample_idx; std::vector<double> sample_val;   // fingerprint of the numeric values last written to L->x
     const void *xptr = nullptr;
+    void *pinned_ptr = nullptr;            // L->x range registered with cudaHostRegister (fast D2H into the caller's buffer)
 };
 static std::mutex g_cache_mu;
 static std::vector<CacheEntry> g_cache;
@@ -581,7 +584,22 @@ static CacheEntry *cache_find(const ssb_cholmod_factor *L)
     return nullptr;
 }
 
-static void cache_drop(CacheEntry *e) { plan_free(e->plan); g_cache.erase(g_cache.begin() + (e - g_cache.data())); }
+static void unpin(CacheEntry *e) { if (e->pinned_ptr) { cudaHostUnregister(e->pinned_ptr); e->pinned_ptr = nullptr; } }
+static void cache_drop(CacheEntry *e) { unpin(e); plan_free(e->plan); g_cache.erase(g_cache.begin() + (e - g_cache.data())); }
+
+// Page-lock the caller's L->x so the factor streams back at PCIe speed.  Best effort: a failure only costs bandwidth.
+// SSB200_PIN_HOST=0 disables it.  The registration is dropped when the plan is evicted, when L->x moves, or by
+// cholmod_l_gpu_deallocate(); call that before freeing a factor whose memory must be returned to the OS immediately.
+static void pin_host_x(CacheEntry *e, const ssb_cholmod_factor *L)
+{
+    static int enabled = -1;
+    if (enabled < 0) { const char *v = getenv("SSB200_PIN_HOST"); enabled = (v && atoi(v) == 0) ? 0 : 1; }
+    if (!enabled || e->pinned_ptr == L->x) return;
+    unpin(e);
+    if (L->xsize < (1u << 16)) return;                   // not worth it for small factors
+    cudaError_t err = cudaHostRegister(L->x, L->xsize * sizeof(double), cudaHostRegisterDefault);
+    if (err == cudaSuccess) e->pinned_ptr = L->x; else (void) cudaGetLastError();
+}
 
 // returns the (possibly new) entry for L; nullptr on failure
 static CacheEntry *cache_get_plan(ssb_cholmod_factor *L)
@@ -670,6 +688,7 @@ extern "C" int cholmod_l_super_numeric(ssb_cholmod_sparse *A, ssb_cholmod_sparse
     std::lock_guard<std::mutex> lk(g_cache_mu);
     CacheEntry *e = cache_get_plan(L);
     if (!e) { RAISE(Common, SSB_CHOLMOD_GPU_PROBLEM, ssb200_last_error()); return 0; }
+    pin_host_x(e, L);
     ssb_long minor = (ssb_long) L->n;
     const int rc = ssb200_factorize(e->plan, stype, (const ssb_long *) A->p, (const ssb_long *) A->i, A->packed ? nullptr : (const ssb_long *) A->nz,
                                     (const double *) A->x, (ssb_long) A->ncol,

@@ -63,6 +63,7 @@ struct Launch {
     int njobs;
     long long tile0;     // first entry in the flat tile->job array of that kind (gemm, trsm)
     int ntiles;
+    double flops;        // algorithmic flops of the launch
 };
 
 struct Update { int d, s; int p0, nd1, nd2; long long map_off; };

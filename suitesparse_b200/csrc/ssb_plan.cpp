@@ -43,6 +43,7 @@ void emit_gemm_launch(HostPlan &hp, std::vector<GemmJob> &jobs, int kind, int ph
             for (int tj = 0; tj < j.ntj; tj++) t += j.nti - tj;
             if (ntiles + t > 1500000000LL && nj > 0) break;
             j.tile_start = (int) ntiles;
+            L.flops += 2.0 * j.K * ((double) j.nd1 * j.nd2 - 0.5 * (double) j.nd1 * (j.nd1 - 1));
             hp.gemm_jobs.push_back(j);
             for (long long q = 0; q < t; q++) hp.gemm_tiles.push_back(nj);
             ntiles += t; nj++; pos++;
@@ -93,14 +94,14 @@ void append_factor_jobs(const HostPlan &hp, const std::vector<int> &snodes, int 
                 pj.x_off = hp.px[s] + j0 + (long long) j0 * nsrow;
                 pj.lda = nsrow; pj.w = w; pj.rows_below = nsrow - j0 - w; pj.col0 = j0; pj.snode = s; pj.tile_start = 0;
                 out.potrf_jobs.push_back(pj);
-                LP.njobs++;
+                LP.njobs++; LP.flops += (double) w * w * w / 3.0;
                 if (pj.rows_below > 0) {
                     pj.tile_start = (int) ttiles;
                     int nt = (pj.rows_below + TRSM_ROWS - 1) / TRSM_ROWS;
                     for (int q = 0; q < nt; q++) out.trsm_tiles.push_back(LT.njobs);
                     ttiles += nt;
                     out.trsm_jobs.push_back(pj);
-                    LT.njobs++;
+                    LT.njobs++; LT.flops += (double) w * w * pj.rows_below;
                     // inner trailing update: remaining columns of the outer panel
                     const int outer_end = std::min(J0 + NB_OUTER, nscol);
                     const int ct = outer_end - (j0 + w);

@@ -15,10 +15,14 @@ class Stats(C.Structure):
                 ("ms_total", C.c_double), ("ms_assemble", C.c_double), ("ms_update", C.c_double),
                 ("ms_factor", C.c_double), ("ms_d2h", C.c_double), ("ms_h2d", C.c_double),
                 ("bytes_update_panel", C.c_double), ("bytes_update_scatter", C.c_double),
-                ("device_bytes", c_long)]
+                ("device_bytes", c_long),
+                ("ms_kind", C.c_double * 4), ("flops_kind", C.c_double * 4), ("launches_kind", c_long * 4)]
 
     def asdict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_}
+        d = {k: getattr(self, k) for k, _ in self._fields_}
+        for k in ("ms_kind", "flops_kind", "launches_kind"):
+            d[k] = list(d[k])
+        return d
 
 
 def _lib():
