@@ -1,0 +1,181 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C ABI, against
+  * the golden fixtures generated from the reference build (L->x, minor, status, solution x),
+  * the oracle on seeded/deterministic mesh problems,
+  * size-independent properties at the benchmark's full size (lap7 128^3)."""
+import ctypes as C, os
+import numpy as np
+import pytest
+import scipy.sparse as sp
+from conftest import GOLDEN, load_golden, golden_matrix, persuper_relerr
+
+pytestmark = pytest.mark.gpu
+
+TOL_L = 1e-11          # per-supernode max|L-L_ref|/max|L_ref| (fp64; BLAS/DMMA summation order differs)
+TOL_X = 1e-9
+TOL_RESID = 1e-10      # BASELINE.json north_star: ||Ax-b||/||b|| <= 1e-10 on every config
+
+
+def _plan(g):
+    from suitesparse_b200 import plain
+    return plain.Plan(int(g["n"]), g["super"], g["pi"], g["px"], g["s"])
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_plain_layer_matches_reference_golden(path):
+    g = load_golden(path)
+    S, F = golden_matrix(g)
+    pl = _plan(g)
+    st, minor, Lx = pl.factorize(S, beta=float(g["beta"]), quick_return=bool(g.get("quick", 0)), F=F)
+    assert st == int(g["status"])
+    assert minor == int(g["minor"])                       # integer side: exact
+    assert persuper_relerr(g["px"], Lx, g["Lx"]) < TOL_L
+    assert pl.stats()["kernel_launches"] > 0
+    for s in range(len(g["px"]) - 1):                      # strictly-upper part of diagonal blocks stays exactly zero
+        nscol = int(g["super"][s + 1] - g["super"][s]); nsrow = int(g["pi"][s + 1] - g["pi"][s])
+        blk = Lx[int(g["px"][s]):int(g["px"][s]) + nsrow * nscol].reshape((nsrow, nscol), order="F")
+        assert np.all(np.triu(blk[:nscol, :], 1) == 0.0)
+    if g["x"].size:
+        perm = g["Perm"]
+        y = pl.solve(g["b"][perm], which=2)
+        x = np.empty_like(y); x[perm] = y
+        assert np.abs(x - g["x"]).max() <= TOL_X * max(1.0, np.abs(g["x"]).max())
+        # L and L' separately equal the combined call
+        y1 = pl.solve(pl.solve(g["b"][perm], which=0), which=1)
+        assert np.abs(y1 - y).max() <= 1e-12 * max(1.0, np.abs(y).max())
+    pl.close()
+
+
+def _manual_factor(H, g, keep):
+    """A symbolic supernodal cholmod_factor built from raw arrays (what cholmod_l_analyze would return)."""
+    L = H.Factor()
+    arrs = {k: np.ascontiguousarray(g[k], dtype=np.int64) for k in ("Perm", "super", "pi", "px", "s")}
+    colcount = np.ones(int(g["n"]), dtype=np.int64)
+    keep.extend(list(arrs.values()) + [colcount])
+    L.n = int(g["n"]); L.minor = int(g["n"])
+    L.Perm = arrs["Perm"].ctypes.data; L.ColCount = colcount.ctypes.data
+    L.nsuper = len(g["super"]) - 1; L.ssize = int(g["pi"][-1]); L.xsize = int(g["px"][-1])
+    L.maxcsize = int(g["maxcsize"]); L.maxesize = int(g["maxesize"])
+    L.super = arrs["super"].ctypes.data; L.pi = arrs["pi"].ctypes.data; L.px = arrs["px"].ctypes.data; L.s = arrs["s"].ctypes.data
+    L.ordering = 1; L.is_ll = 1; L.is_super = 1; L.is_monotonic = 1
+    L.itype = H.CHOLMOD_LONG; L.xtype = H.CHOLMOD_PATTERN; L.dtype = 0
+    return L
+
+
+@pytest.mark.parametrize("name", ["bcsstk01_tri", "pts5ldd03_mtx_norelax", "lp_afiro_tri", "plskz362_mtx", "npd_mid", "npd_first", "3singular"])
+def test_dropin_symbols_on_golden(name):
+    """cholmod_l_super_numeric / _lsolve / _ltsolve called exactly as cholmod_factorize_p and cholmod_solve2 call them."""
+    from suitesparse_b200 import cholmod_host as H
+    g = load_golden([p for p in GOLDEN if os.path.basename(p) == name + ".npz"][0])
+    ch = H.Cholmod(gpu=True)
+    keep = []
+    L = _manual_factor(H, g, keep)
+    S, F = golden_matrix(g)
+    Ss = ch.sparse(S, -1 if F is None else 0)
+    Fs = ch.sparse(F, 0) if F is not None else None
+    beta = (C.c_double * 2)(float(g["beta"]), 0.0)
+    ch.cm.quick_return_if_not_posdef = int(g.get("quick", 0))
+    ok = ch.hot("cholmod_l_super_numeric")(C.byref(Ss), C.byref(Fs) if Fs is not None else None, beta, C.byref(L), C.byref(ch.cm))
+    assert ok == 1
+    assert ch.cm.status == int(g["status"])               # CHOLMOD_OK or CHOLMOD_NOT_POSDEF, returned TRUE in both cases
+    assert L.minor == int(g["minor"]) and L.xtype == H.CHOLMOD_REAL and L.is_ll == 1
+    Lx = H._np_view(L.x, L.xsize, np.float64)
+    assert persuper_relerr(g["px"], Lx, g["Lx"]) < TOL_L
+    assert ch.cm.gpuNumKernelLaunches > 0
+    if g["x"].size:
+        n = int(g["n"]); perm = g["Perm"]
+        Y = np.asfortranarray(g["b"][perm].reshape(n, 1)); E = np.zeros(max(1, int(g["maxesize"])))
+        Yd = ch.dense(Y); Ed = ch.dense(E)
+        assert ch.hot("cholmod_l_super_lsolve")(C.byref(L), C.byref(Yd), C.byref(Ed), C.byref(ch.cm)) == 1
+        assert ch.hot("cholmod_l_super_ltsolve")(C.byref(L), C.byref(Yd), C.byref(Ed), C.byref(ch.cm)) == 1
+        x = np.empty(n); x[perm] = Y[:, 0]
+        assert np.abs(x - g["x"]).max() <= TOL_X * max(1.0, np.abs(g["x"]).max())
+    # refactorization with the now-numeric L reuses L->x and the cached plan
+    ok = ch.hot("cholmod_l_super_numeric")(C.byref(Ss), C.byref(Fs) if Fs is not None else None, beta, C.byref(L), C.byref(ch.cm))
+    assert ok == 1 and ch.cm.status == int(g["status"])
+    ch.lib.cholmod_l_change_factor(H.CHOLMOD_PATTERN, 1, 1, 1, 1, C.byref(L), C.byref(ch.cm))    # frees L->x
+
+
+@pytest.mark.parametrize("kind,N,nrelax", [("lap7", 9, None), ("lap7", 20, None), ("lap27", 14, None), ("elas", 7, None),
+                                           ("lap7", 12, (0, 0, 0)), ("lap7", 40, None)])
+def test_full_driver_path_vs_oracle(kind, N, nrelax):
+    """cholmod_l_analyze -> cholmod_l_factorize -> cholmod_l_solve through the host library with our symbols interposed."""
+    from suitesparse_b200 import gen, cholmod_host as H
+    from oracle import oracle
+    ch = H.Cholmod(gpu=True)
+    A, p = gen.make_problem(kind, N)
+    S = ch.sparse(A, +1)
+    L = ch.analyze(S, p, nrelax=nrelax, zrelax=(0.0, 0.0, 0.0) if nrelax else None)
+    assert ch.factorize(S, L) == 1 and ch.cm.status == 0
+    assert ch.cm.gpuNumKernelLaunches > 0 and ch.cm.cpu_syrk_calls == 0         # the CPU BLAS path did not run
+    f = ch.factor_arrays(L)
+    n = f["n"]
+    assert f["minor"] == n
+    assert ch.lib.cholmod_l_check_factor(L, C.byref(ch.cm)) == 1                # reference's structural validator
+    S2 = ch.lower_permuted(S, L); s2 = S2.contents
+    Ap = H._np_view(s2.p, n + 1, np.int64); Ai = H._np_view(s2.i, int(Ap[n]), np.int64); Ax = H._np_view(s2.x, int(Ap[n]), np.float64)
+    st, minor, Lo = oracle.factorize(n, f["super"], f["pi"], f["px"], f["s"], sp.csc_matrix((Ax, Ai, Ap), shape=(n, n)))
+    assert st == 0
+    assert persuper_relerr(f["px"], f["x"], Lo) < TOL_L
+    rng = np.random.default_rng(42)                                             # seed 42 as Tcov/cm.c:1245
+    B = rng.standard_normal((n, 3))
+    X = ch.solve(L, B)
+    Af = A + sp.triu(A, 1).T
+    assert np.linalg.norm(Af @ X - B) / np.linalg.norm(B) < TOL_RESID
+    ch.free_sparse(S2); ch.free_factor(L)
+
+
+def test_unsymmetric_AAt_path():
+    """stype == 0: factorize A*A' + beta*I (the A*F assembly branch, t_cholmod_super_numeric.c:386-417)."""
+    from suitesparse_b200 import cholmod_host as H
+    rng = np.random.default_rng(42)
+    m, k = 60, 90
+    A = sp.random(m, k, density=0.08, random_state=rng, format="csc") + sp.eye(m, k, format="csc")
+    A = A.tocsc(); A.sort_indices()
+    ch = H.Cholmod(gpu=True)
+    S = ch.sparse(A, 0)
+    ch.cm.supernodal = H.CHOLMOD_SUPERNODAL
+    L = ch.lib.cholmod_l_analyze(C.byref(S), C.byref(ch.cm))
+    assert ch.factorize(S, L, beta=1e-3) == 1 and ch.cm.status == 0 and ch.cm.gpuNumKernelLaunches > 0
+    b = rng.standard_normal(m)
+    x = ch.solve(L, b)
+    M = (A @ A.T + 1e-3 * sp.eye(m)).toarray()
+    assert np.linalg.norm(M @ x - b) / np.linalg.norm(b) < TOL_RESID
+    ch.free_factor(L)
+
+
+def test_full_size_properties_lap7_128():
+    """BASELINE.json configs[1] at full size: properties that do not need a second factor of 29 GB."""
+    from suitesparse_b200 import gen, cholmod_host as H, plain
+    ch = H.Cholmod(gpu=True)
+    A, p = gen.make_problem("lap7", 128)
+    S = ch.sparse(A, +1)
+    L = ch.analyze(S, p)
+    # symbolic numbers pinned by the reference: MATLAB_Tools/MESHND/meshnd_quality_out.txt:731-734
+    assert abs(ch.cm.lnz / 2.830e9 - 1) < 2e-3 and abs(ch.cm.fl / 2.843e13 - 1) < 2e-3
+    assert ch.factorize(S, L) == 1 and ch.cm.status == 0 and ch.cm.gpuNumKernelLaunches > 0
+    f = ch.factor_arrays(L)
+    n = f["n"]
+    assert f["minor"] == n
+    Lx = f["x"]
+    assert np.isfinite(Lx[:: 1009]).all()
+    # diagonal of L is positive; strict upper part of the root supernode's diagonal block is zero
+    s = f["nsuper"] - 1
+    nscol = int(f["super"][s + 1] - f["super"][s]); nsrow = int(f["pi"][s + 1] - f["pi"][s]); a = int(f["px"][s])
+    blk = Lx[a:a + nsrow * nscol].reshape((nsrow, nscol), order="F")
+    assert (np.diag(blk) > 0).all() and np.all(np.triu(blk[:512, :512], 1) == 0.0)
+    b = np.ones(n)
+    x = ch.solve(L, b)
+    Af = A + sp.triu(A, 1).T
+    assert np.linalg.norm(Af @ x - b) / np.linalg.norm(b) < TOL_RESID
+    # linearity of the solve: solve(2b + c) = 2 solve(b) + solve(c)
+    c = 1.0 + np.arange(n) / n
+    X = ch.solve(L, np.stack([c, 2 * b + c], axis=1))
+    assert np.abs(X[:, 1] - (2 * x + X[:, 0])).max() < 1e-9 * np.abs(X).max()
+    # refactorization is reproducible to rounding (atomic extend-add order may differ)
+    pl = plain.plan_of_factor(L)
+    chk1 = Lx[:: 4099].copy()
+    assert ch.factorize(S, L) == 1
+    assert np.abs(ch.factor_arrays(L)["x"][:: 4099] - chk1).max() < 1e-11 * np.abs(chk1).max()
+    assert pl is not None and pl.stats()["nsuper"] == f["nsuper"]
+    ch.free_factor(L)
+    ch.b200.cholmod_l_gpu_deallocate(C.byref(ch.cm))

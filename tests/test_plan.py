@@ -1,0 +1,67 @@
+"""CPU tests of the host plan builder (ssb_plan.cpp): the precomputed update lists, levels and schedules are checked
+against the oracle's enumeration and against first principles on the golden structures."""
+import ctypes as C, os
+import numpy as np
+import pytest
+from conftest import GOLDEN, load_golden, B200_LIB
+from oracle import oracle
+
+
+def plan_summary(n, super_, pi, px, s):
+    lib = C.CDLL(B200_LIB)
+    out = np.zeros(16); lev = np.zeros(len(super_) - 1, dtype=np.int32)
+    a = [np.ascontiguousarray(v, dtype=np.int64) for v in (super_, pi, px, s)]
+    rc = lib.ssb200_plan_summary(C.c_int64(n), C.c_int64(len(super_) - 1), *[v.ctypes.data_as(C.c_void_p) for v in a],
+                                 out.ctypes.data_as(C.c_void_p), lev.ctypes.data_as(C.c_void_p))
+    return rc, out, lev
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_plan_matches_oracle_enumeration(path):
+    g = load_golden(path)
+    n = int(g["n"])
+    rc, out, lev = plan_summary(n, g["super"], g["pi"], g["px"], g["s"])
+    assert rc == 0
+    up = oracle.enumerate_updates(n, g["super"], g["pi"], g["s"])
+    assert int(out[1]) == len(up["d"])
+    assert int(out[2]) == int(up["ndrow2"].sum())
+    # levels: every update's descendant lies strictly below its target; some supernode sits at every level
+    assert np.all(lev[up["d"]] < lev[up["s"]])
+    assert set(lev.tolist()) == set(range(int(out[0])))
+    # dense flop counts from first principles
+    nscol = np.diff(g["super"]).astype(np.float64); nsrow = np.diff(g["pi"]).astype(np.float64)
+    assert np.isclose(out[12], (nscol ** 3 / 3).sum())
+    assert np.isclose(out[13], (nscol ** 2 * (nsrow - nscol)).sum())
+    ndcol = nscol[up["d"]]
+    tri = up["ndrow1"] * up["ndrow2"] - 0.5 * up["ndrow1"] * (up["ndrow1"] - 1)
+    assert np.isclose(out[11], (2 * ndcol * tri).sum())
+    # one potrf job per 64-column block, one solve job per block
+    blocks = np.ceil(nscol / 64).sum()
+    assert int(out[6]) == int(blocks) and int(out[10]) == int(blocks)
+
+
+def test_plan_rejects_bad_structure():
+    g = load_golden([p for p in GOLDEN if "bcsstk01_tri.npz" in p][0])
+    s_bad = g["s"].copy(); s_bad[-1] = s_bad[-2]           # unsorted / duplicate row index
+    rc, _, _ = plan_summary(int(g["n"]), g["super"], g["pi"], g["px"], s_bad)
+    assert rc == -4
+    sup_bad = g["super"].copy(); sup_bad[-1] += 1
+    rc, _, _ = plan_summary(int(g["n"]), sup_bad, g["pi"], g["px"], g["s"])
+    assert rc == -4
+
+
+def test_generators():
+    from suitesparse_b200 import gen
+    A = gen.laplacian(5, 7)
+    assert A.shape == (125, 125) and A.nnz == 125 + 3 * 5 * 5 * 4       # diagonal + one upper entry per mesh edge
+    p = gen.meshnd_perm(5, 5, 5)
+    assert sorted(p.tolist()) == list(range(125))
+    # the last 25 ordered nodes are the middle plane k=2 (separator last, meshnd.m:96-100)
+    assert set(p[-25:].tolist()) == set((np.arange(25) + 25 * 2).tolist())
+    A27 = gen.laplacian(4, 27)
+    full = A27 + __import__("scipy.sparse").sparse.triu(A27, 1).T
+    assert np.allclose(full.diagonal(), 26.0) and abs(full.sum(axis=1).min()) >= 0
+    E = gen.elasticity(4)
+    assert E.shape == (192, 192)
+    fullE = (E + __import__("scipy.sparse").sparse.triu(E, 1).T).toarray()
+    assert np.linalg.eigvalsh(fullE).min() > 0
