@@ -40,6 +40,8 @@ struct ssb200_plan {
     HostPlan hp;
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;      // device-to-host streaming of finished supernodes
+    cudaEvent_t copy_gate = nullptr, copy_done = nullptr;
     int *d_super = nullptr, *d_ls = nullptr, *d_supermap = nullptr, *d_relmap = nullptr, *d_info = nullptr;
     long long *d_pi = nullptr, *d_px = nullptr;
     double *d_Lx = nullptr;
@@ -52,8 +54,11 @@ struct ssb200_plan {
     int stype = -1;
     double *d_X = nullptr; size_t capX = 0;
     bool factor_on_device = false;
+    // the whole solve sequence is replayed as one CUDA graph (thousands of tiny dependent kernels)
+    cudaGraphExec_t solve_graph = nullptr; double *sg_X = nullptr; long long sg_nrhs = 0, sg_ldx = 0; int sg_which = -1;
     std::vector<cudaEvent_t> events;
     ssb200_stats stats{};
+    std::vector<float> launch_ms;          // device time of every launch of the last factorize (debug / tuning)
     size_t device_bytes = 0;
 };
 
@@ -74,11 +79,9 @@ static DevSym dev_sym(const ssb200_plan *p)
 
 static int configure_kernels_once()
 {
-    static std::once_flag once; static cudaError_t err = cudaSuccess;
     // attributes are per device context; set them every time a plan is created (cheap)
     cudaError_t e1 = cudaFuncSetAttribute(gemm_nt_sub_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) gemm_smem_bytes<128>());
     cudaError_t e2 = cudaFuncSetAttribute(gemm_nt_sub_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) gemm_smem_bytes<64>());
-    (void) once; (void) err;
     if (e1 != cudaSuccess || e2 != cudaSuccess) { set_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : e2)); return SSB_CHOLMOD_GPU_PROBLEM; }
     return 0;
 }
@@ -96,8 +99,12 @@ static void plan_free(ssb200_plan *p)
                     p->d_X};
     for (void *q : ptrs) if (q) cudaFree(q);
     free_cscbuf(p->bufA); free_cscbuf(p->bufF);
+    if (p->solve_graph) cudaGraphExecDestroy(p->solve_graph);
     if (p->h_info) cudaFreeHost(p->h_info);
     for (auto e : p->events) cudaEventDestroy(e);
+    if (p->copy_gate) cudaEventDestroy(p->copy_gate);
+    if (p->copy_done) cudaEventDestroy(p->copy_done);
+    if (p->copy_stream) cudaStreamDestroy(p->copy_stream);
     if (p->stream) cudaStreamDestroy(p->stream);
     delete p;
 }
@@ -127,6 +134,7 @@ static int plan_build_device(ssb200_plan *p)
     if (dev_alloc_copy(p, &p->d_px, hp.px)) return SSB_CHOLMOD_GPU_PROBLEM;
     if (dev_alloc_copy(p, &p->d_ls, hp.ls)) return SSB_CHOLMOD_GPU_PROBLEM;
     if (dev_alloc_copy(p, &p->d_supermap, hp.supermap)) return SSB_CHOLMOD_GPU_PROBLEM;
+    if (const char *fa = getenv("SSB200_FORCE_ATOMIC")) { if (atoi(fa)) for (auto &g : hp.gemm_jobs) g.atomic = 1; }
     if (upload_jobs(p, hp, p->jobs)) return SSB_CHOLMOD_GPU_PROBLEM;
     if (dev_alloc_copy(p, &p->d_solve_jobs, hp.solve_jobs)) return SSB_CHOLMOD_GPU_PROBLEM;
     if (dev_alloc_copy(p, &p->d_solve_tiles, hp.solve_tiles)) return SSB_CHOLMOD_GPU_PROBLEM;
@@ -179,7 +187,8 @@ static ssb200_plan *plan_create_impl(ssb_long n, ssb_long nsuper, const ssb_long
                          owner, rank, p->hp)) {
         set_error("invalid symbolic factor: " + p->hp.error); delete p; return nullptr;
     }
-    if (cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("cudaStreamCreate failed"); delete p; return nullptr; }
+    if (cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&p->copy_gate, cudaEventDisableTiming) != cudaSuccess || cudaEventCreate(&p->copy_done) != cudaSuccess) { set_error("cudaStreamCreate failed"); delete p; return nullptr; }
     if (plan_build_device(p) != 0) { plan_free(p); return nullptr; }
     return p;
 }
@@ -347,7 +356,16 @@ static int handle_not_posdef(ssb200_plan *p, int sfail, int info, double beta0, 
     return 0;
 }
 
-extern "C" int ssb200_factorize_resident(ssb200_plan *p, const double beta[2], int quick_return_if_not_posdef, ssb_long *minor_out)
+// Is this host pointer page-locked (cudaHostAlloc / cudaHostRegister)?  Only then can finished supernodes stream to
+// the host asynchronously while the factorization continues.
+static bool host_is_pinned(const void *ptr)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, ptr) != cudaSuccess) { (void) cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+}
+
+static int factorize_impl(ssb200_plan *p, const double beta[2], int quick_return_if_not_posdef, ssb_long *minor_out, double *Lx_host)
 {
     if (!p) { set_error("null plan"); return SSB_CHOLMOD_INVALID; }
     if (!p->haveA) { set_error("no matrix uploaded"); return SSB_CHOLMOD_INVALID; }
@@ -372,11 +390,24 @@ extern "C" int ssb200_factorize_resident(ssb200_plan *p, const double beta[2], i
     const int stop_level = stop ? atoi(stop) : INT_MAX;
     // every launch is bracketed by events on the plan's stream: (launch index, event index) pairs
     std::vector<std::pair<int, size_t>> marks;
+    static int stream_d2h = -1;
+    if (stream_d2h < 0) { const char *v = getenv("SSB200_STREAM_D2H"); stream_d2h = (v && atoi(v) == 0) ? 0 : 1; }
+    const bool streaming = Lx_host && stream_d2h && stop_level == INT_MAX && host_is_pinned(Lx_host);
+    size_t ctask = 0;
     for (int l = 0; l < hp.nlevels && l < stop_level; l++) {
         for (int t = hp.level_launch_begin[l]; t < hp.level_launch_begin[l + 1]; t++) {
             const Launch &L = hp.launches[t];
             cudaEventRecord(get_event(p, ev), p->stream); marks.push_back({t, ev}); ev++;
             if (run_launch(p, L, p->jobs)) return SSB_CHOLMOD_GPU_PROBLEM;
+            if (streaming && ctask < hp.copy_tasks.size() && hp.copy_tasks[ctask].after_launch == t) {
+                // these ranges of Lx are final: copy them out behind the compute stream
+                CU_TRY(cudaEventRecord(p->copy_gate, p->stream));
+                CU_TRY(cudaStreamWaitEvent(p->copy_stream, p->copy_gate, 0));
+                for (; ctask < hp.copy_tasks.size() && hp.copy_tasks[ctask].after_launch == t; ctask++) {
+                    const CopyTask &ct = hp.copy_tasks[ctask];
+                    CU_TRY(cudaMemcpyAsync(Lx_host + ct.off, p->d_Lx + ct.off, (size_t) ct.cnt * sizeof(double), cudaMemcpyDeviceToHost, p->copy_stream));
+                }
+            }
         }
     }
     cudaEventRecord(get_event(p, ev), p->stream); marks.push_back({-1, ev}); ev++;
@@ -388,9 +419,11 @@ extern "C" int ssb200_factorize_resident(ssb200_plan *p, const double beta[2], i
     cudaEventElapsedTime(&ms, p->events[0], p->events[1]); p->stats.ms_assemble = ms;
     p->stats.ms_update = p->stats.ms_factor = 0;
     for (int k = 0; k < 4; k++) { p->stats.ms_kind[k] = 0; p->stats.flops_kind[k] = 0; p->stats.launches_kind[k] = 0; }
+    p->launch_ms.assign(hp.launches.size(), 0.f);
     for (size_t t = 0; t + 1 < marks.size(); t++) {
         cudaEventElapsedTime(&ms, p->events[marks[t].second], p->events[marks[t + 1].second]);
         const Launch &L = hp.launches[marks[t].first];
+        p->launch_ms[marks[t].first] = ms;
         if (L.phase == 0) p->stats.ms_update += ms; else p->stats.ms_factor += ms;
         p->stats.ms_kind[L.kind] += ms; p->stats.flops_kind[L.kind] += L.flops; p->stats.launches_kind[L.kind]++;
     }
@@ -408,7 +441,24 @@ extern "C" int ssb200_factorize_resident(ssb200_plan *p, const double beta[2], i
     cudaEventElapsedTime(&ms, p->events[0], p->events[ev]); p->stats.ms_total = ms;
     p->stats.kernel_launches_total += p->stats.kernel_launches;
     p->factor_on_device = true;
+    if (Lx_host) {
+        if (streaming && status == 0) {
+            // only the tail of the copy stream is still exposed
+            CU_TRY(cudaEventRecord(p->copy_done, p->copy_stream));
+            CU_TRY(cudaStreamSynchronize(p->copy_stream));
+            cudaEventElapsedTime(&ms, p->events[ev], p->copy_done); p->stats.ms_d2h = ms > 0 ? ms : 0;
+        } else {
+            CU_TRY(cudaStreamSynchronize(p->copy_stream));
+            int r2 = ssb200_download_L(p, Lx_host);        // not positive definite (rare) or pageable host memory: one plain copy
+            if (r2) return r2;
+        }
+    }
     return status;
+}
+
+extern "C" int ssb200_factorize_resident(ssb200_plan *p, const double beta[2], int quick_return_if_not_posdef, ssb_long *minor_out)
+{
+    return factorize_impl(p, beta, quick_return_if_not_posdef, minor_out, nullptr);
 }
 
 extern "C" int ssb200_download_L(ssb200_plan *p, double *Lx_host)
@@ -442,10 +492,7 @@ extern "C" int ssb200_factorize(ssb200_plan *p, int stype, const ssb_long *Ap, c
 {
     int rc = ssb200_upload_A(p, stype, Ap, Ai, Anz, Ax, ncolA, Fp, Fi, Fnz, Fx);
     if (rc) return rc;
-    rc = ssb200_factorize_resident(p, beta, quick_return_if_not_posdef, minor_out);
-    if (rc < 0) return rc;
-    if (Lx_host) { int r2 = ssb200_download_L(p, Lx_host); if (r2) return r2; }
-    return rc;
+    return factorize_impl(p, beta, quick_return_if_not_posdef, minor_out, Lx_host);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -461,29 +508,49 @@ extern "C" int ssb200_solve_resident(ssb200_plan *p, int which, double *dX, ssb_
     if (p->hp.n == 0 || nrhs == 0) return 0;
     const HostPlan &hp = p->hp;
     cudaEvent_t e0 = get_event(p, 0), e1 = get_event(p, 1);
-    cudaEventRecord(e0, p->stream);
     const int nsteps = (int) hp.solve_steps.size();
-    if (which == 0 || which == 2) {
-        for (int t = 0; t < nsteps; t++) {
-            const SolveStep &st = hp.solve_steps[t];
-            lsolve_diag_kernel<<<st.njobs, SOLVE_THREADS, 0, p->stream>>>(p->d_solve_jobs + st.job0, p->d_Lx, dX, (int) nrhs, ldx);
-            p->stats.kernel_launches++;
-            if (st.ntiles > 0) {
-                lsolve_update_kernel<<<st.ntiles, SOLVE_THREADS, 0, p->stream>>>(p->d_solve_jobs + st.job0, p->d_solve_tiles + st.tile0, p->d_Lx, p->d_ls, dX, (int) nrhs, ldx);
-                p->stats.kernel_launches++;
+    static int use_graph = -1;
+    if (use_graph < 0) { const char *v = getenv("SSB200_SOLVE_GRAPH"); use_graph = (v && atoi(v) == 0) ? 0 : 1; }
+    const bool cached = use_graph && p->solve_graph && p->sg_X == dX && p->sg_nrhs == nrhs && p->sg_ldx == ldx && p->sg_which == which;
+    if (!cached) {
+        if (use_graph) {
+            if (p->solve_graph) { cudaGraphExecDestroy(p->solve_graph); p->solve_graph = nullptr; }
+            CU_TRY(cudaStreamBeginCapture(p->stream, cudaStreamCaptureModeThreadLocal));
+        } else cudaEventRecord(e0, p->stream);
+        if (which == 0 || which == 2) {
+            for (int t = 0; t < nsteps; t++) {
+                const SolveStep &st = hp.solve_steps[t];
+                lsolve_diag_kernel<<<st.njobs, SOLVE_THREADS, 0, p->stream>>>(p->d_solve_jobs + st.job0, p->d_Lx, dX, (int) nrhs, ldx);
+                if (st.ntiles > 0)
+                    lsolve_update_kernel<<<st.ntiles, SOLVE_THREADS, 0, p->stream>>>(p->d_solve_jobs + st.job0, p->d_solve_tiles + st.tile0, p->d_Lx, p->d_ls, dX, (int) nrhs, ldx);
             }
+        }
+        if (which == 1 || which == 2) {
+            for (int t = nsteps - 1; t >= 0; t--) {
+                const SolveStep &st = hp.solve_steps[t];
+                if (st.ntiles > 0)
+                    ltsolve_update_kernel<<<st.ntiles, SOLVE_THREADS, 0, p->stream>>>(p->d_solve_jobs + st.job0, p->d_solve_tiles + st.tile0, p->d_Lx, p->d_ls, dX, (int) nrhs, ldx);
+                ltsolve_diag_kernel<<<st.njobs, SOLVE_THREADS, 0, p->stream>>>(p->d_solve_jobs + st.job0, p->d_Lx, dX, (int) nrhs, ldx);
+            }
+        }
+        if (use_graph) {
+            cudaGraph_t g = nullptr;
+            CU_TRY(cudaStreamEndCapture(p->stream, &g));
+            cudaError_t ie = cudaGraphInstantiate(&p->solve_graph, g, 0);
+            cudaGraphDestroy(g);
+            if (ie != cudaSuccess) { p->solve_graph = nullptr; set_error(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ie)); return SSB_CHOLMOD_GPU_PROBLEM; }
+            p->sg_X = dX; p->sg_nrhs = nrhs; p->sg_ldx = ldx; p->sg_which = which;
         }
     }
-    if (which == 1 || which == 2) {
-        for (int t = nsteps - 1; t >= 0; t--) {
-            const SolveStep &st = hp.solve_steps[t];
-            if (st.ntiles > 0) {
-                ltsolve_update_kernel<<<st.ntiles, SOLVE_THREADS, 0, p->stream>>>(p->d_solve_jobs + st.job0, p->d_solve_tiles + st.tile0, p->d_Lx, p->d_ls, dX, (int) nrhs, ldx);
-                p->stats.kernel_launches++;
-            }
-            ltsolve_diag_kernel<<<st.njobs, SOLVE_THREADS, 0, p->stream>>>(p->d_solve_jobs + st.job0, p->d_Lx, dX, (int) nrhs, ldx);
-            p->stats.kernel_launches++;
-        }
+    // launches of one solve: a diag kernel per step and an update kernel per step that has rows below, per direction
+    {
+        long long per_dir = 0;
+        for (const SolveStep &st : hp.solve_steps) per_dir += 1 + (st.ntiles > 0 ? 1 : 0);
+        p->stats.kernel_launches = per_dir * (which == 2 ? 2 : 1);
+    }
+    if (use_graph) {
+        cudaEventRecord(e0, p->stream);
+        CU_TRY(cudaGraphLaunch(p->solve_graph, p->stream));
     }
     cudaEventRecord(e1, p->stream);
     CU_TRY(cudaGetLastError());
@@ -517,6 +584,22 @@ extern "C" int ssb200_get_stats(const ssb200_plan *p, ssb200_stats *out)
     if (!p || !out) return SSB_CHOLMOD_INVALID;
     *out = p->stats; out->device_bytes = (ssb_long) p->device_bytes;
     return 0;
+}
+
+// tuning aid: per launch of the last factorize: kind, phase, ntiles, njobs, flops, ms, and K of its first (heaviest) job
+extern "C" ssb_long ssb200_debug_launches(ssb200_plan *p, double *out, ssb_long cap)
+{
+    if (!p) return -1;
+    const ssb_long nl = (ssb_long) p->hp.launches.size();
+    if (!out || cap < nl * 7) return nl;
+    for (ssb_long t = 0; t < nl; t++) {
+        const Launch &L = p->hp.launches[t];
+        double K = 0;
+        if (L.kind == L_GEMM_BIG || L.kind == L_GEMM_SMALL) K = p->hp.gemm_jobs[L.job0].K;
+        out[7 * t + 0] = L.kind; out[7 * t + 1] = L.phase; out[7 * t + 2] = L.ntiles; out[7 * t + 3] = L.njobs;
+        out[7 * t + 4] = L.flops; out[7 * t + 5] = t < (ssb_long) p->launch_ms.size() ? p->launch_ms[t] : 0; out[7 * t + 6] = K;
+    }
+    return nl;
 }
 
 // debugging aid for tests: copy the relative maps back (size = sum of ndrow2 over updates)

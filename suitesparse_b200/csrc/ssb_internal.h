@@ -51,7 +51,7 @@ struct SolveJob {
     int tile_start;
     int pad;
 };
-constexpr int SOLVE_ROWS = 512;     // rows per solve-update tile
+constexpr int SOLVE_ROWS = 128;     // rows per solve-update tile
 struct SolveStep { long long job0; int njobs; long long tile0; int ntiles; };
 
 enum LaunchKind : int { L_GEMM_BIG = 0, L_GEMM_SMALL = 1, L_POTRF = 2, L_TRSM = 3 };
@@ -65,6 +65,10 @@ struct Launch {
     int ntiles;
     double flops;        // algorithmic flops of the launch
 };
+
+// Device-to-host streaming of the factor: the Lx range [off, off+cnt) is final once launch `after_launch` has run.
+struct CopyTask { int after_launch; long long off, cnt; };
+constexpr int COPY_FLUSH_LEVEL = 8;  // supernodes up to this etree level are copied in merged ranges after that level
 
 struct Update { int d, s; int p0, nd1, nd2; long long map_off; };
 
@@ -87,6 +91,7 @@ struct HostPlan {
     std::vector<int> trsm_tiles;
     std::vector<Launch> launches;    // in execution order
     std::vector<int> level_launch_begin; // nlevels+1
+    std::vector<CopyTask> copy_tasks;    // sorted by after_launch
     // solve schedule: supernodes ordered by level
     std::vector<int> level_ptr;      // nlevels+1
     std::vector<int> level_nodes;    // supernodes sorted by level
@@ -104,7 +109,7 @@ bool build_host_plan(long long n, long long nsuper, const long long *super, cons
 
 // Job lists for factorizing ONE supernode restricted to its first ncol_limit columns (not-positive-definite repeat,
 // t_cholmod_super_numeric.c:944-967).  Appends launches to `out`.
-void append_factor_jobs(const HostPlan &hp, const std::vector<int> &snodes, int ncol_limit, HostPlan &out);
+void append_factor_jobs(const HostPlan &hp, const std::vector<int> &snodes, int ncol_limit, HostPlan &out, bool panel_copies = false);
 
 int gemm_tile_size(int kind);       // 128 for L_GEMM_BIG, 64 for L_GEMM_SMALL
 

@@ -72,8 +72,16 @@ gemm_nt_sub_kernel(const GemmJob *__restrict__ jobs, const int *__restrict__ til
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const GemmJob job = jobs[tile_job[blockIdx.x]];
     // decode the tile: tile column tj holds tiles ti = tj .. nti-1
-    int rem = (int) blockIdx.x - job.tile_start, tj = 0;
-    while (rem >= job.nti - tj) { rem -= job.nti - tj; tj++; }
+    // tiles before column tj: tj*nti - tj*(tj-1)/2  ->  invert with a float estimate, then fix up
+    int rem = (int) blockIdx.x - job.tile_start, tj;
+    {
+        const float b = 2.0f * job.nti + 1.0f;
+        tj = (int) ((b - sqrtf(fmaxf(b * b - 8.0f * (float) rem, 0.0f))) * 0.5f);
+        tj = max(0, min(tj, job.ntj - 1));
+        while (tj > 0 && rem < tj * job.nti - (tj * (tj - 1)) / 2) tj--;
+        while (tj + 1 < job.ntj && rem >= (tj + 1) * job.nti - ((tj + 1) * tj) / 2) tj++;
+        rem -= tj * job.nti - (tj * (tj - 1)) / 2;
+    }
     const int ti = tj + rem;
     const int rowA0 = ti * BT, rowB0 = tj * BT;
     const bool diag = (ti == tj);
@@ -164,6 +172,13 @@ gemm_nt_sub_kernel(const GemmJob *__restrict__ jobs, const int *__restrict__ til
     const long long ldc = job.ldc;
     const bool mapped = job.map_off >= 0;
     const bool atomic = job.atomic != 0;
+    // row offsets of this thread's MT rows (identity or relative map), -1 = outside the job
+    int roff[MT];
+#pragma unroll
+    for (int m = 0; m < MT; m++) {
+        const int il = wm0 + m * 8 + (lane >> 2);
+        roff[m] = (rowA0 + il < nd2) ? (mapped ? rowmap[il] : rowA0 + il) : -1;
+    }
 #pragma unroll
     for (int nn = 0; nn < NTL; nn++) {
 #pragma unroll
@@ -171,15 +186,25 @@ gemm_nt_sub_kernel(const GemmJob *__restrict__ jobs, const int *__restrict__ til
             const int jl = wn0 + nn * 8 + 2 * (lane & 3) + e;
             const int j = rowB0 + jl;
             if (j >= nd1) continue;
-            const long long coff = mapped ? (long long) colmap[jl] * ldc : (long long) j * ldc;
+            double *__restrict__ colp = Cb + (mapped ? (long long) colmap[jl] * ldc : (long long) j * ldc);
+            if (atomic) {
 #pragma unroll
-            for (int m = 0; m < MT; m++) {
-                const int il = wm0 + m * 8 + (lane >> 2);
-                const int i = rowA0 + il;
-                if (i < nd2 && i >= j) {
-                    double *dst = Cb + coff + (mapped ? rowmap[il] : i);
-                    const double v = acc[m][nn][e];
-                    if (atomic) red_add_f64(dst, -v); else *dst -= v;
+                for (int m = 0; m < MT; m++) {
+                    const int i = rowA0 + wm0 + m * 8 + (lane >> 2);
+                    if (roff[m] >= 0 && i >= j) red_add_f64(colp + roff[m], -acc[m][nn][e]);
+                }
+            } else {
+                // exclusive owner of the target entries: batch the loads so their latencies overlap
+                double old[MT];
+#pragma unroll
+                for (int m = 0; m < MT; m++) {
+                    const int i = rowA0 + wm0 + m * 8 + (lane >> 2);
+                    old[m] = (roff[m] >= 0 && i >= j) ? __ldcg(colp + roff[m]) : 0.0;
+                }
+#pragma unroll
+                for (int m = 0; m < MT; m++) {
+                    const int i = rowA0 + wm0 + m * 8 + (lane >> 2);
+                    if (roff[m] >= 0 && i >= j) __stcg(colp + roff[m], old[m] - acc[m][nn][e]);
                 }
             }
         }
@@ -191,43 +216,59 @@ gemm_nt_sub_kernel(const GemmJob *__restrict__ jobs, const int *__restrict__ til
 // info[snode] = min(info, col0 + j + 1) at the first non-positive (or NaN) pivot (LAPACK dpotrf contract).
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int POTRF_THREADS = 256;
+// 256 threads = 16 x 16; thread (ti,tk) keeps the 4x4 strided sub-block T(ti+16a, tk+16b) in registers for the whole
+// factorization.  Per column j: the owners of column j publish it to shared memory (double-buffered), one barrier,
+// then every thread applies the rank-1 update to its registers.  L's column j goes straight to global memory.
 __global__ void __launch_bounds__(POTRF_THREADS) potrf_block_kernel(const PanelJob *__restrict__ jobs, double *__restrict__ Lx,
                                                                    int *__restrict__ info)
 {
-    constexpr int LDS = NB_INNER + 1;
-    __shared__ double T[NB_INNER * LDS];
+    __shared__ double colbuf[2][NB_INNER];
     const PanelJob job = jobs[blockIdx.x];
     const int w = job.w, tid = threadIdx.x;
+    const int ti = tid & 15, tk = tid >> 4;
     const long long lda = job.lda;
     double *__restrict__ A = Lx + job.x_off;
-    for (int e = tid; e < w * w; e += POTRF_THREADS) {
-        const int i = e % w, j = e / w;
-        if (i >= j) T[i * LDS + j] = A[i + j * lda];
-    }
-    __syncthreads();
+    double t[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            const int i = ti + 16 * a, k = tk + 16 * b;
+            t[a][b] = (i < w && k < w && i >= k) ? A[i + k * lda] : 0.0;
+        }
     for (int j = 0; j < w; j++) {
-        const double d = T[j * LDS + j];
-        if (!(d > 0.0)) {
-            if (tid == 0) { atomicMin(&info[job.snode], job.col0 + j + 1); }
-            break;                                  // uniform: every thread read the same d
-        }
-        const double r = sqrt(d);
-        __syncthreads();                            // everyone has read T[j][j]
-        if (tid == 0) T[j * LDS + j] = r;
-        for (int i = j + 1 + tid; i < w; i += POTRF_THREADS) T[i * LDS + j] /= r;
-        __syncthreads();
-        // trailing rank-1 update of the lower part: T[i][k] -= T[i][j]*T[k][j], j < k <= i < w
-        const int m = w - j - 1;
-        for (int e = tid; e < m * m; e += POTRF_THREADS) {
-            const int i = j + 1 + e % m, k = j + 1 + e / m;
-            if (i >= k) T[i * LDS + k] -= T[i * LDS + j] * T[k * LDS + j];
+        double *cb = colbuf[j & 1];
+        // owners of column j (tk == j%16, b == j/16) publish their rows
+        if (tk == (j & 15)) {
+            const int b = j >> 4;
+#pragma unroll
+            for (int a = 0; a < 4; a++) {
+                double v = 0.0;
+#pragma unroll
+                for (int bb = 0; bb < 4; bb++) if (bb == b) v = t[a][bb];
+                cb[ti + 16 * a] = v;
+            }
         }
         __syncthreads();
-    }
-    __syncthreads();
-    for (int e = tid; e < w * w; e += POTRF_THREADS) {
-        const int i = e % w, j = e / w;
-        if (i >= j) A[i + j * lda] = T[i * LDS + j];
+        const double d = cb[j];
+        if (!(d > 0.0)) {                           // uniform: every thread reads the same d
+            if (tid == 0) atomicMin(&info[job.snode], job.col0 + j + 1);
+            break;
+        }
+        const double r = sqrt(d), rinv = 1.0 / r, dinv = 1.0 / d;
+        if (tid < w - j) { const int i = j + tid; A[i + j * lda] = (tid == 0) ? r : cb[i] * rinv; }   // w <= 64 < 256 threads
+        double ci[4], ck[4];
+#pragma unroll
+        for (int a = 0; a < 4; a++) ci[a] = cb[ti + 16 * a];
+#pragma unroll
+        for (int b = 0; b < 4; b++) ck[b] = cb[tk + 16 * b] * dinv;
+#pragma unroll
+        for (int a = 0; a < 4; a++)
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                const int i = ti + 16 * a, k = tk + 16 * b;
+                if (k > j && i >= k) t[a][b] -= ci[a] * ck[b];
+            }
     }
 }
 
@@ -242,9 +283,9 @@ __device__ __forceinline__ void trsm_rows_body(const PanelJob &job, int tile, do
     const int w = job.w, tid = threadIdx.x;
     const long long lda = job.lda;
     const double *__restrict__ L11 = Lx + job.x_off;
-    for (int e = tid; e < w * w; e += TRSM_ROWS) {
-        const int i = e % w, j = e / w;
-        if (i >= j) Lsm[i * LDS + j] = L11[i + j * lda];
+    for (int e = tid; e < NC * NC; e += TRSM_ROWS) {
+        const int i = e % NC, j = e / NC;              // NC is a power of two: shifts
+        Lsm[i * LDS + j] = (i < w && j < w && i >= j) ? L11[i + j * lda] : 0.0;
     }
     __syncthreads();
     const int r = tile * TRSM_ROWS + tid;
@@ -253,13 +294,14 @@ __device__ __forceinline__ void trsm_rows_body(const PanelJob &job, int tile, do
     double x[NC];
 #pragma unroll
     for (int c = 0; c < NC; c++) x[c] = (c < w) ? B[c * lda] : 0.0;
+    // right-looking substitution: after x[j] is final, it is eliminated from every later column (independent FMAs)
 #pragma unroll
     for (int j = 0; j < NC; j++) {
         if (j < w) {
-            double v = x[j];
+            const double xj = x[j] / Lsm[j * LDS + j];
+            x[j] = xj;
 #pragma unroll
-            for (int k = 0; k < j; k++) v -= x[k] * Lsm[j * LDS + k];
-            x[j] = v / Lsm[j * LDS + j];
+            for (int k = j + 1; k < NC; k++) x[k] -= xj * Lsm[k * LDS + j];       // rows k >= w of Lsm are zero
         }
     }
 #pragma unroll
@@ -395,8 +437,8 @@ __global__ void __launch_bounds__(SOLVE_THREADS) lsolve_diag_kernel(const SolveJ
     }
 }
 
-// forward, step (b): X[rows below] -= L2 * x1.  One CTA = SOLVE_ROWS rows of one job; atomics because several
-// supernodes of a level update the same ancestor rows.
+// forward, step (b): X[rows below] -= L2 * x1.  One CTA = SOLVE_ROWS rows of one job, one thread per row (coalesced
+// along every column), 8 loads in flight per thread; atomics because several supernodes of a level hit the same rows.
 __global__ void __launch_bounds__(SOLVE_THREADS) lsolve_update_kernel(const SolveJob *__restrict__ jobs, const int *__restrict__ tile_job,
                                                                      const double *__restrict__ Lx, const int *__restrict__ ls,
                                                                      double *__restrict__ X, int nrhs, long long ldx)
@@ -405,25 +447,33 @@ __global__ void __launch_bounds__(SOLVE_THREADS) lsolve_update_kernel(const Solv
     const SolveJob job = jobs[tile_job[blockIdx.x]];
     const int tile = (int) blockIdx.x - job.tile_start;
     const int w = job.w, tid = threadIdx.x;
-    const int r0 = tile * SOLVE_ROWS;
-    const int r1 = min(job.rows_below, r0 + SOLVE_ROWS);
-    const double *__restrict__ L2 = Lx + job.x_off + w;     // row r below the block at L2[r + c*lda]
+    const int r = tile * SOLVE_ROWS + tid;
+    const bool live = r < job.rows_below;
+    const long long lda = job.lda;
+    const double *__restrict__ row = Lx + job.x_off + w + (live ? r : 0);     // row r below the block at row[c*lda]
+    const int xrow = live ? ls[job.ls_off + r] : 0;
     for (int rh = 0; rh < nrhs; rh++) {
         double *__restrict__ x = X + rh * ldx;
         __syncthreads();
         if (tid < w) xs[tid] = x[job.xcol0 + tid];
         __syncthreads();
-        for (int r = r0 + tid; r < r1; r += SOLVE_THREADS) {
-            double acc = 0.0;
-            const double *__restrict__ row = L2 + r;
-            for (int c = 0; c < w; c++) acc += row[(long long) c * job.lda] * xs[c];
-            red_add_f64(x + ls[job.ls_off + r], -acc);
+        if (!live) continue;
+        double acc = 0.0;
+        int c = 0;
+        for (; c + 8 <= w; c += 8) {
+            double v[8];
+#pragma unroll
+            for (int q = 0; q < 8; q++) v[q] = __ldcs(row + (long long) (c + q) * lda);
+#pragma unroll
+            for (int q = 0; q < 8; q++) acc += v[q] * xs[c + q];
         }
+        for (; c < w; c++) acc += __ldcs(row + (long long) c * lda) * xs[c];
+        red_add_f64(x + xrow, -acc);
     }
 }
 
-// backward, step (a): x1 -= L2^T * X[rows below].  One CTA = SOLVE_ROWS rows of one job, partial dot products
-// reduced through shared memory, then one atomic per column.
+// backward, step (a): x1 -= L2^T * X[rows below].  One CTA = SOLVE_ROWS rows of one job; a warp takes 4 columns at a
+// time (16 loads in flight per lane), reduces with shuffles and issues one atomic per column.
 __global__ void __launch_bounds__(SOLVE_THREADS) ltsolve_update_kernel(const SolveJob *__restrict__ jobs, const int *__restrict__ tile_job,
                                                                       const double *__restrict__ Lx, const int *__restrict__ ls,
                                                                       double *__restrict__ X, int nrhs, long long ldx)
@@ -434,20 +484,33 @@ __global__ void __launch_bounds__(SOLVE_THREADS) ltsolve_update_kernel(const Sol
     const int w = job.w, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int r0 = tile * SOLVE_ROWS;
     const int nr = min(job.rows_below, r0 + SOLVE_ROWS) - r0;
+    const long long lda = job.lda;
     const double *__restrict__ L2 = Lx + job.x_off + w + r0;
+    constexpr int NW = SOLVE_THREADS / 32, RPL = SOLVE_ROWS / 32;
     for (int rh = 0; rh < nrhs; rh++) {
         double *__restrict__ x = X + rh * ldx;
         __syncthreads();
-        for (int r = tid; r < nr; r += SOLVE_THREADS) xr[r] = x[ls[job.ls_off + r0 + r]];
+        for (int r = tid; r < SOLVE_ROWS; r += SOLVE_THREADS) xr[r] = (r < nr) ? x[ls[job.ls_off + r0 + r]] : 0.0;
         __syncthreads();
-        // warp `warp` handles columns warp, warp+4, ...: lanes stride the rows (coalesced along the column)
-        for (int c = warp; c < w; c += SOLVE_THREADS / 32) {
-            const double *__restrict__ col = L2 + (long long) c * job.lda;
-            double acc = 0.0;
-            for (int r = lane; r < nr; r += 32) acc += col[r] * xr[r];
+        for (int c0 = warp * 4; c0 < w; c0 += NW * 4) {
+            double acc[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-            if (lane == 0) red_add_f64(x + job.xcol0 + c, -acc);
+            for (int q = 0; q < 4; q++) {
+                if (c0 + q < w) {
+                    const double *__restrict__ col = L2 + (long long) (c0 + q) * lda;
+#pragma unroll
+                    for (int t = 0; t < RPL; t++) {
+                        const int r = lane + 32 * t;
+                        if (r < nr) acc[q] += __ldcs(col + r) * xr[r];
+                    }
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
+                if (lane == 0 && c0 + q < w) red_add_f64(x + job.xcol0 + c0 + q, -acc[q]);
+            }
         }
     }
 }

@@ -69,7 +69,7 @@ inline void route_gemm(const GemmJob &j, std::vector<GemmJob> &small, std::vecto
 
 // Blocked factorization steps for a set of mutually independent supernodes (one etree level, or one repeated
 // supernode with ncol_limit >= 0).  Appends to out.{potrf_jobs,trsm_jobs,trsm_tiles,gemm_jobs,gemm_tiles,launches}.
-void append_factor_jobs(const HostPlan &hp, const std::vector<int> &snodes, int ncol_limit, HostPlan &out)
+void append_factor_jobs(const HostPlan &hp, const std::vector<int> &snodes, int ncol_limit, HostPlan &out, bool panel_copies)
 {
     int maxcol = 0;
     for (int s : snodes) {
@@ -109,7 +109,7 @@ void append_factor_jobs(const HostPlan &hp, const std::vector<int> &snodes, int 
                         GemmJob g{};
                         g.a_off = hp.px[s] + (j0 + w) + (long long) j0 * nsrow;
                         g.c_off = hp.px[s] + (j0 + w) + (long long) (j0 + w) * nsrow;
-                        g.map_off = -1; g.lda = nsrow; g.ldc = nsrow; g.K = w; g.nd1 = ct; g.nd2 = nsrow - j0 - w; g.atomic = 0;
+                        g.map_off = -1; g.lda = nsrow; g.ldc = nsrow; g.K = w; g.nd1 = ct; g.nd2 = nsrow - j0 - w; g.atomic = 1;
                         route_gemm(g, gs, gb);
                     }
                 }
@@ -118,6 +118,18 @@ void append_factor_jobs(const HostPlan &hp, const std::vector<int> &snodes, int 
             LT.ntiles = (int) ttiles;
             if (LT.njobs) out.launches.push_back(LT);
             emit_update_launches(out, gs, gb, 1);
+        }
+        // columns [J0, J0+W) of every active supernode are final now: they can stream to the host while the trailing
+        // update runs
+        if (panel_copies && !out.launches.empty()) {
+            const int after = (int) out.launches.size() - 1;
+            for (int s : snodes) {
+                const int nscol = hp.super[s + 1] - hp.super[s];
+                if (nscol <= J0) continue;
+                const long long nsrow = hp.pi[s + 1] - hp.pi[s];
+                const int W = std::min(NB_OUTER, nscol - J0);
+                out.copy_tasks.push_back(CopyTask{after, hp.px[s] + (long long) J0 * nsrow, (long long) W * nsrow});
+            }
         }
         // outer trailing update with the whole NB_OUTER-wide panel
         for (int s : snodes) {
@@ -131,7 +143,7 @@ void append_factor_jobs(const HostPlan &hp, const std::vector<int> &snodes, int 
             GemmJob g{};
             g.a_off = hp.px[s] + (J0 + W) + (long long) J0 * nsrow;
             g.c_off = hp.px[s] + (J0 + W) + (long long) (J0 + W) * nsrow;
-            g.map_off = -1; g.lda = nsrow; g.ldc = nsrow; g.K = W; g.nd1 = ct; g.nd2 = nsrow - J0 - W; g.atomic = 0;
+            g.map_off = -1; g.lda = nsrow; g.ldc = nsrow; g.K = W; g.nd1 = ct; g.nd2 = nsrow - J0 - W; g.atomic = 1;
             route_gemm(g, gs, gb);
         }
         emit_update_launches(out, gs, gb, 1);
@@ -235,7 +247,24 @@ bool build_host_plan(long long n, long long nsuper, const long long *super, cons
             hp.flops_potrf += nscol * nscol * nscol / 3.0;
             hp.flops_trsm += nscol * nscol * (nsrow - nscol);
         }
-        if (!nodes.empty()) append_factor_jobs(hp, nodes, -1, hp);
+        const int flush = std::min(COPY_FLUSH_LEVEL, hp.nlevels - 1);
+        if (!nodes.empty()) append_factor_jobs(hp, nodes, -1, hp, /*panel_copies=*/l > flush);
+        if (l == flush && !hp.launches.empty()) {
+            // every supernode of level <= flush is final: merge consecutive indices into contiguous Lx ranges
+            const int after = (int) hp.launches.size() - 1;
+            long long run_off = -1, run_end = -1;
+            for (int t = 0; t < (int) nsuper; t++) {
+                const bool mine = hp.level[t] <= flush && (!owner || owner[t] == rank);
+                if (mine) {
+                    if (run_off < 0) run_off = hp.px[t];
+                    run_end = hp.px[t + 1];
+                }
+                if ((!mine || t == (int) nsuper - 1) && run_off >= 0) {
+                    hp.copy_tasks.push_back(CopyTask{after, run_off, run_end - run_off});
+                    run_off = -1;
+                }
+            }
+        }
     }
     hp.level_launch_begin[hp.nlevels] = (int) hp.launches.size();
     // ---- solve schedule: per level, per 64-column block index ------------------------------------------------
