@@ -80,8 +80,10 @@ static DevSym dev_sym(const ssb200_plan *p)
 static int configure_kernels_once()
 {
     // attributes are per device context; set them every time a plan is created (cheap)
-    cudaError_t e1 = cudaFuncSetAttribute(gemm_nt_sub_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) gemm_smem_bytes<128>());
-    cudaError_t e2 = cudaFuncSetAttribute(gemm_nt_sub_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) gemm_smem_bytes<64>());
+    cudaError_t e1 = cudaFuncSetAttribute(gemm_nt_sub_kernel<128, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) gemm_smem_bytes<128, 16>());
+    cudaError_t e2 = cudaFuncSetAttribute(gemm_nt_sub_kernel<64, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) gemm_smem_bytes<64, 16>());
+    cudaError_t e3 = cudaFuncSetAttribute(gemm_nt_sub_kernel<128, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) gemm_smem_bytes<128, 32>());
+    if (e3 != cudaSuccess) e1 = e3;
     if (e1 != cudaSuccess || e2 != cudaSuccess) { set_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : e2)); return SSB_CHOLMOD_GPU_PROBLEM; }
     return 0;
 }
@@ -268,11 +270,17 @@ extern "C" int ssb200_upload_A(ssb200_plan *p, int stype, const ssb_long *Ap, co
 static int run_launch(ssb200_plan *p, const Launch &L, const DevJobs &dj)
 {
     switch (L.kind) {
-    case L_GEMM_BIG:
-        gemm_nt_sub_kernel<128><<<L.ntiles, gemm_threads<128>(), gemm_smem_bytes<128>(), p->stream>>>(dj.gemm_jobs + L.job0, dj.gemm_tiles + L.tile0, p->d_Lx, p->d_relmap);
+    case L_GEMM_BIG: {
+        static int kb32 = -1;
+        if (kb32 < 0) { const char *v = getenv("SSB200_KB32"); kb32 = (v && atoi(v)) ? 1 : 0; }
+        if (kb32)
+            gemm_nt_sub_kernel<128, 32><<<L.ntiles, gemm_threads<128>(), gemm_smem_bytes<128, 32>(), p->stream>>>(dj.gemm_jobs + L.job0, dj.gemm_tiles + L.tile0, p->d_Lx, p->d_relmap);
+        else
+            gemm_nt_sub_kernel<128, 16><<<L.ntiles, gemm_threads<128>(), gemm_smem_bytes<128, 16>(), p->stream>>>(dj.gemm_jobs + L.job0, dj.gemm_tiles + L.tile0, p->d_Lx, p->d_relmap);
         break;
+    }
     case L_GEMM_SMALL:
-        gemm_nt_sub_kernel<64><<<L.ntiles, gemm_threads<64>(), gemm_smem_bytes<64>(), p->stream>>>(dj.gemm_jobs + L.job0, dj.gemm_tiles + L.tile0, p->d_Lx, p->d_relmap);
+        gemm_nt_sub_kernel<64, 16><<<L.ntiles, gemm_threads<64>(), gemm_smem_bytes<64, 16>(), p->stream>>>(dj.gemm_jobs + L.job0, dj.gemm_tiles + L.tile0, p->d_Lx, p->d_relmap);
         break;
     case L_POTRF:
         potrf_block_kernel<<<L.njobs, POTRF_THREADS, 0, p->stream>>>(dj.potrf_jobs + L.job0, p->d_Lx, p->d_info);

@@ -14,6 +14,7 @@
 #pragma once
 #include "ssb_internal.h"
 #include <cuda_runtime.h>
+#include <type_traits>
 
 namespace ssb {
 
@@ -31,8 +32,9 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 // D(8x8) += A(8x4, row) * B(4x8, col), fp64 tensor core
 __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b)
 {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+    // not volatile: the scheduler may interleave the staging code of the next chunk between the DMMAs
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+        : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
 __device__ __forceinline__ void red_add_f64(double *addr, double v)
@@ -44,23 +46,23 @@ __device__ __forceinline__ void red_add_f64(double *addr, double v)
 // C -= A * B^T   (one CTA = one BT x BT tile of one job)
 // ------------------------------------------------------------------------------------------------------------------
 template <int BT> struct GemmCfg;
-template <> struct GemmCfg<128> { static constexpr int WARPS_M = 2, WARPS_N = 4, KB = 16, STAGES = 3; };
-template <> struct GemmCfg<64>  { static constexpr int WARPS_M = 2, WARPS_N = 2, KB = 16, STAGES = 3; };
+template <> struct GemmCfg<128> { static constexpr int WARPS_M = 2, WARPS_N = 4, STAGES = 3; };
+template <> struct GemmCfg<64>  { static constexpr int WARPS_M = 2, WARPS_N = 2, STAGES = 3; };
 
 template <int BT> constexpr int gemm_threads() { return GemmCfg<BT>::WARPS_M * GemmCfg<BT>::WARPS_N * 32; }
-template <int BT> constexpr size_t gemm_smem_bytes()
+template <int BT, int KB> constexpr size_t gemm_smem_bytes()
 {
-    return (size_t) GemmCfg<BT>::STAGES * 2 * GemmCfg<BT>::KB * (BT + 4) * sizeof(double) + 2 * BT * sizeof(int);
+    return (size_t) GemmCfg<BT>::STAGES * 2 * KB * (BT + 4) * sizeof(double) + 2 * BT * sizeof(int);
 }
 
-template <int BT>
+template <int BT, int KB>
 __global__ void __launch_bounds__(GemmCfg<BT>::WARPS_M *GemmCfg<BT>::WARPS_N * 32)
 gemm_nt_sub_kernel(const GemmJob *__restrict__ jobs, const int *__restrict__ tile_job, double *__restrict__ Lx,
                    const int *__restrict__ relmap)
 {
     using Cfg = GemmCfg<BT>;
     constexpr int NT = Cfg::WARPS_M * Cfg::WARPS_N * 32;
-    constexpr int KB = Cfg::KB, STAGES = Cfg::STAGES;
+    constexpr int STAGES = Cfg::STAGES;
     constexpr int WM = BT / Cfg::WARPS_M, WN = BT / Cfg::WARPS_N;
     constexpr int MT = WM / 8, NTL = WN / 8;
     constexpr int LD = BT + 4;                      // LD % 16 == 4: conflict-free 8-byte fragment loads
@@ -107,62 +109,81 @@ gemm_nt_sub_kernel(const GemmJob *__restrict__ jobs, const int *__restrict__ til
 #pragma unroll
         for (int b = 0; b < NTL; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
 
-    auto load_stage = [&](int stage, int k0) {
-        double *As = smem + (size_t) stage * 2 * KB * LD;
+    // Every thread stages the same (row, k mod KPT) pattern in every chunk: row lr = tid % BT of the A tile and of the
+    // B tile, columns k = kq + KPT*i.  The source pointers simply advance by KB columns per chunk; only the last chunk
+    // needs the k < K test.  The staging of chunk c+STAGES-1 is cut into KB/4 slices issued between the k-steps of
+    // chunk c, so its address arithmetic fills the issue slots between DMMAs instead of stalling the tensor pipe.
+    constexpr int KPT = NT / BT;                    // k-columns covered by one pass of the CTA
+    constexpr int NLD = KB / KPT;                   // cp.async per operand per thread per chunk
+    constexpr int KSTEPS = KB / 4;
+    constexpr int LPS = (NLD + KSTEPS - 1) / KSTEPS; // cp.async per operand per thread per k-step slice
+    const int lr = tid % BT, kq = tid / BT;
+    const bool okA = rowA0 + lr < nd2, okB = (!diag) && (rowB0 + lr < nd1);
+    const int szA = okA ? 8 : 0, szB = okB ? 8 : 0;
+    const long long kstep = (long long) KPT * lda;
+    const double *gA = P + (okA ? rowA0 + lr : 0) + (long long) kq * lda;     // advance as chunks are staged
+    const double *gB = P + (okB ? rowB0 + lr : 0) + (long long) kq * lda;
+    const int soff = kq * LD + lr;
+    const int nk = (K + KB - 1) / KB;
+    int ld_kcol = kq, ld_stage = 0;                 // first k-column this thread stages in the next chunk; its ring slot
+    // slice `sl` (0..KSTEPS-1) of the staging of the next chunk.  Branch-free: columns at or beyond K (the tail of the
+    // last chunk, or chunks past the end) are zero-filled with a zero-size copy from a valid dummy address.
+    auto stage_slice = [&](int sl) {
+        double *As = smem + (size_t) ld_stage * 2 * KB * LD + soff;
         double *Bs = As + KB * LD;
 #pragma unroll
-        for (int e = tid; e < BT * KB; e += NT) {
-            const int r = e % BT, k = e / BT;
-            const int gk = k0 + k;
-            {
-                const int gr = rowA0 + r;
-                const bool ok = (gr < nd2) && (gk < K);
-                const double *src = ok ? (P + gr + (long long) gk * lda) : P;
-                cp_async8(As + k * LD + r, src, ok ? 8 : 0);
-            }
-            if (!diag) {
-                const int gr = rowB0 + r;
-                const bool ok = (gr < nd1) && (gk < K);
-                const double *src = ok ? (P + gr + (long long) gk * lda) : P;
-                cp_async8(Bs + k * LD + r, src, ok ? 8 : 0);
+        for (int q = 0; q < LPS; q++) {
+            const int i = sl * LPS + q;
+            if (i < NLD) {                          // compile-time
+                const bool kin = ld_kcol + KPT * i < K;
+                cp_async8(As + i * KPT * LD, kin ? gA : P, kin ? szA : 0);
+                cp_async8(Bs + i * KPT * LD, kin ? gB : P, kin ? szB : 0);
+                gA += kstep; gB += kstep;
             }
         }
     };
+    auto stage_advance = [&]() { ld_kcol += KB; ld_stage = (ld_stage + 1 == STAGES) ? 0 : ld_stage + 1; };
 
-    const int nk = (K + KB - 1) / KB;
 #pragma unroll
     for (int st = 0; st < STAGES - 1; st++) {
-        if (st < nk) load_stage(st, st * KB);
+#pragma unroll
+        for (int sl = 0; sl < KSTEPS; sl++) stage_slice(sl);
+        stage_advance();
         cp_async_commit();
     }
-    for (int kc = 0; kc < nk; kc++) {
-        cp_async_wait<STAGES - 2>();
-        __syncthreads();
-        // prefetch chunk kc+STAGES-1 into the slot freed at iteration kc-1
-        {
-            const int nxt = kc + STAGES - 1;
-            if (nxt < nk) load_stage(nxt % STAGES, nxt * KB);
-            cp_async_commit();
-        }
-        if (warp_active) {
-            const double *As = smem + (size_t) (kc % STAGES) * 2 * KB * LD;
+    // The loop exists twice (warps that own output, and the idle warps of a diagonal tile that only stage and sync) so
+    // that the k-step body is one straight-line block.
+    auto mainloop = [&](auto ACTIVE) {
+        constexpr bool act = decltype(ACTIVE)::value;
+        int cs = 0;                                 // ring slot of the chunk being consumed
+        for (int kc = 0; kc < nk; kc++) {
+            cp_async_wait<STAGES - 2>();
+            __syncthreads();                        // chunk kc landed for everyone; slot (kc-1)%STAGES is free again
+            const double *As = smem + (size_t) cs * 2 * KB * LD;
             const double *Bs = diag ? As : As + KB * LD;
+            const double *ap = As + (lane & 3) * LD + wm0 + (lane >> 2);
+            const double *bp = Bs + (lane & 3) * LD + wn0 + (lane >> 2);
 #pragma unroll
-            for (int kk = 0; kk < KB; kk += 4) {
-                double a[MT], b[NTL];
-                const double *ap = As + (kk + (lane & 3)) * LD + wm0 + (lane >> 2);
-                const double *bp = Bs + (kk + (lane & 3)) * LD + wn0 + (lane >> 2);
+            for (int ks = 0; ks < KSTEPS; ks++) {
+                if constexpr (act) {
+                    double a[MT], b[NTL];
 #pragma unroll
-                for (int m = 0; m < MT; m++) a[m] = ap[m * 8];
+                    for (int m = 0; m < MT; m++) a[m] = ap[ks * 4 * LD + m * 8];
 #pragma unroll
-                for (int nn = 0; nn < NTL; nn++) b[nn] = bp[nn * 8];
+                    for (int nn = 0; nn < NTL; nn++) b[nn] = bp[ks * 4 * LD + nn * 8];
 #pragma unroll
-                for (int m = 0; m < MT; m++)
+                    for (int m = 0; m < MT; m++)
 #pragma unroll
-                    for (int nn = 0; nn < NTL; nn++) dmma884(acc[m][nn][0], acc[m][nn][1], a[m], b[nn]);
+                        for (int nn = 0; nn < NTL; nn++) dmma884(acc[m][nn][0], acc[m][nn][1], a[m], b[nn]);
+                }
+                stage_slice(ks);                    // part of chunk kc+STAGES-1 goes into the slot freed by chunk kc-1
             }
+            stage_advance();
+            cp_async_commit();
+            cs = (cs + 1 == STAGES) ? 0 : cs + 1;
         }
-    }
+    };
+    if (warp_active) mainloop(std::true_type{}); else mainloop(std::false_type{});
     cp_async_wait<0>();
     __syncthreads();      // rowmap/colmap visible (also when nk == 0)
 
