@@ -230,10 +230,11 @@ typedef struct ssb200_stats {
     double   ms_total, ms_assemble, ms_update, ms_factor, ms_d2h, ms_h2d; /* device time (CUDA events), last call */
     double   bytes_update_panel, bytes_update_scatter;  /* algorithmic bytes of the update kernel */
     ssb_long device_bytes;                    /* HBM held by the plan */
-    /* per kernel of the last factorize: [0] gemm_nt_sub<128>, [1] gemm_nt_sub<64>, [2] potrf_block, [3] trsm_rows */
-    double   ms_kind[4];                      /* device time (CUDA events on the plan's stream) */
-    double   flops_kind[4];                   /* algorithmic flops executed by that kernel */
-    ssb_long launches_kind[4];
+    /* per kernel of the last factorize: [0] gemm_nt_sub<128>, [1] gemm_nt_sub<64>, [2] potrf_block, [3] trsm_rows,
+       [4] trsm_tc, [5] unused */
+    double   ms_kind[6];                      /* device time (CUDA events on the plan's stream) */
+    double   flops_kind[6];                   /* algorithmic flops executed by that kernel */
+    ssb_long launches_kind[6];
 } ssb200_stats;
 int ssb200_get_stats(const ssb200_plan *plan, ssb200_stats *out);
 

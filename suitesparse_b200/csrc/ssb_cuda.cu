@@ -45,6 +45,7 @@ struct ssb200_plan {
     int *d_super = nullptr, *d_ls = nullptr, *d_supermap = nullptr, *d_relmap = nullptr, *d_info = nullptr;
     long long *d_pi = nullptr, *d_px = nullptr;
     double *d_Lx = nullptr;
+    double *d_winv = nullptr; long long winv_slots = 0;   // inverses of the wide diagonal blocks of the running step
     DevJobs jobs;
     SolveJob *d_solve_jobs = nullptr; int *d_solve_tiles = nullptr;
     int *h_info = nullptr;                 // pinned
@@ -84,6 +85,8 @@ static int configure_kernels_once()
     cudaError_t e2 = cudaFuncSetAttribute(gemm_nt_sub_kernel<64, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) gemm_smem_bytes<64, 16>());
     cudaError_t e3 = cudaFuncSetAttribute(gemm_nt_sub_kernel<128, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) gemm_smem_bytes<128, 32>());
     if (e3 != cudaSuccess) e1 = e3;
+    cudaError_t e4 = cudaFuncSetAttribute(trsm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) trsm_tc_smem_bytes());
+    if (e4 != cudaSuccess) e1 = e4;
     if (e1 != cudaSuccess || e2 != cudaSuccess) { set_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : e2)); return SSB_CHOLMOD_GPU_PROBLEM; }
     return 0;
 }
@@ -96,7 +99,7 @@ static void plan_free(ssb200_plan *p)
 {
     if (!p) return;
     cudaSetDevice(p->device);
-    void *ptrs[] = {p->d_super, p->d_ls, p->d_supermap, p->d_relmap, p->d_info, p->d_pi, p->d_px, p->d_Lx, p->jobs.gemm_jobs,
+    void *ptrs[] = {p->d_super, p->d_ls, p->d_supermap, p->d_relmap, p->d_info, p->d_pi, p->d_px, p->d_Lx, p->d_winv, p->jobs.gemm_jobs,
                     p->jobs.gemm_tiles, p->jobs.potrf_jobs, p->jobs.trsm_jobs, p->jobs.trsm_tiles, p->d_solve_jobs, p->d_solve_tiles,
                     p->d_X};
     for (void *q : ptrs) if (q) cudaFree(q);
@@ -142,6 +145,9 @@ static int plan_build_device(ssb200_plan *p)
     if (dev_alloc_copy(p, &p->d_solve_tiles, hp.solve_tiles)) return SSB_CHOLMOD_GPU_PROBLEM;
     const size_t xbytes = std::max<long long>(hp.xsize, 1) * sizeof(double);
     CU_TRY(cudaMalloc((void **) &p->d_Lx, xbytes)); p->device_bytes += xbytes;
+    p->winv_slots = std::max(1, hp.max_winv_slots);
+    const size_t wbytes = (size_t) p->winv_slots * NB_INNER * NB_INNER * sizeof(double);
+    CU_TRY(cudaMalloc((void **) &p->d_winv, wbytes)); p->device_bytes += wbytes;
     const size_t ibytes = std::max<long long>(hp.nsuper, 1) * sizeof(int);
     CU_TRY(cudaMalloc((void **) &p->d_info, ibytes)); p->device_bytes += ibytes;
     CU_TRY(cudaMallocHost((void **) &p->h_info, ibytes));
@@ -283,10 +289,13 @@ static int run_launch(ssb200_plan *p, const Launch &L, const DevJobs &dj)
         gemm_nt_sub_kernel<64, 16><<<L.ntiles, gemm_threads<64>(), gemm_smem_bytes<64, 16>(), p->stream>>>(dj.gemm_jobs + L.job0, dj.gemm_tiles + L.tile0, p->d_Lx, p->d_relmap);
         break;
     case L_POTRF:
-        potrf_block_kernel<<<L.njobs, POTRF_THREADS, 0, p->stream>>>(dj.potrf_jobs + L.job0, p->d_Lx, p->d_info);
+        potrf_block_kernel<<<L.njobs, POTRF_THREADS, 0, p->stream>>>(dj.potrf_jobs + L.job0, p->d_Lx, p->d_info, p->d_winv);
         break;
     case L_TRSM:
         trsm_rows_kernel<<<L.ntiles, TRSM_ROWS, 0, p->stream>>>(dj.trsm_jobs + L.job0, dj.trsm_tiles + L.tile0, p->d_Lx);
+        break;
+    case L_TRSM_TC:
+        trsm_tc_kernel<<<L.ntiles, TRSM_ROWS, trsm_tc_smem_bytes(), p->stream>>>(dj.trsm_jobs + L.job0, dj.trsm_tiles + L.tile0, p->d_Lx, p->d_winv);
         break;
     default: set_error("bad launch kind"); return SSB_CHOLMOD_GPU_PROBLEM;
     }
@@ -352,6 +361,7 @@ static int handle_not_posdef(ssb200_plan *p, int sfail, int info, double beta0, 
     }
     std::vector<int> one{sfail};
     append_factor_jobs(hp, one, ncol_new, tmp);
+    if (tmp.max_winv_slots > p->winv_slots) { set_error("internal: winv workspace too small"); return SSB_CHOLMOD_GPU_PROBLEM; }
     DevJobs dj;
     size_t saved = p->device_bytes;
     if (upload_jobs(p, tmp, dj)) return SSB_CHOLMOD_GPU_PROBLEM;
@@ -426,7 +436,7 @@ static int factorize_impl(ssb200_plan *p, const double beta[2], int quick_return
     float ms = 0;
     cudaEventElapsedTime(&ms, p->events[0], p->events[1]); p->stats.ms_assemble = ms;
     p->stats.ms_update = p->stats.ms_factor = 0;
-    for (int k = 0; k < 4; k++) { p->stats.ms_kind[k] = 0; p->stats.flops_kind[k] = 0; p->stats.launches_kind[k] = 0; }
+    for (int k = 0; k < 6; k++) { p->stats.ms_kind[k] = 0; p->stats.flops_kind[k] = 0; p->stats.launches_kind[k] = 0; }
     p->launch_ms.assign(hp.launches.size(), 0.f);
     for (size_t t = 0; t + 1 < marks.size(); t++) {
         cudaEventElapsedTime(&ms, p->events[marks[t].second], p->events[marks[t + 1].second]);
@@ -646,6 +656,7 @@ struct CacheEntry {
     std::vector<long long> sample_idx; std::vector<double> sample_val;   // fingerprint of the numeric values last written to L->x
     const void *xptr = nullptr;
     void *pinned_ptr = nullptr;            // L->x range registered with cudaHostRegister (fast D2H into the caller's buffer)
+    size_t pinned_bytes = 0;
 };
 static std::mutex g_cache_mu;
 static std::vector<CacheEntry> g_cache;
@@ -675,21 +686,56 @@ static CacheEntry *cache_find(const ssb_cholmod_factor *L)
     return nullptr;
 }
 
-static void unpin(CacheEntry *e) { if (e->pinned_ptr) { cudaHostUnregister(e->pinned_ptr); e->pinned_ptr = nullptr; } }
+static void unpin(CacheEntry *e) { if (e->pinned_ptr) { if (cudaHostUnregister(e->pinned_ptr) != cudaSuccess) (void) cudaGetLastError(); e->pinned_ptr = nullptr; e->pinned_bytes = 0; } }
 static void cache_drop(CacheEntry *e) { unpin(e); plan_free(e->plan); g_cache.erase(g_cache.begin() + (e - g_cache.data())); }
 
 // Page-lock the caller's L->x so the factor streams back at PCIe speed.  Best effort: a failure only costs bandwidth.
 // SSB200_PIN_HOST=0 disables it.  The registration is dropped when the plan is evicted, when L->x moves, or by
-// cholmod_l_gpu_deallocate(); call that before freeing a factor whose memory must be returned to the OS immediately.
+// cholmod_l_gpu_deallocate().
+// A registration can go STALE: if the application frees the factor and the allocator later hands out the same
+// virtual range again, CUDA would still DMA into the old physical pages.  Every call therefore probes the mapping with
+// three 8-byte device-to-host copies (first, middle, last element) and re-registers when the CPU does not see them.
+static bool pin_probe(CacheEntry *e, const ssb_cholmod_factor *L)
+{
+    ssb200_plan *p = e->plan;
+    volatile double *x = (volatile double *) L->x;
+    const size_t idx[3] = {0, L->xsize / 2, L->xsize - 1};
+    static const double magic = 0x1.b200b200b200bp+77;
+    if (cudaMemcpyAsync(p->d_winv, &magic, sizeof(double), cudaMemcpyHostToDevice, p->stream) != cudaSuccess) { (void) cudaGetLastError(); return false; }
+    for (size_t t : idx) x[t] = 0.0;
+    for (size_t t : idx)
+        if (cudaMemcpyAsync((void *) &x[t], p->d_winv, sizeof(double), cudaMemcpyDeviceToHost, p->stream) != cudaSuccess) { (void) cudaGetLastError(); return false; }
+    if (cudaStreamSynchronize(p->stream) != cudaSuccess) { (void) cudaGetLastError(); return false; }
+    for (size_t t : idx) { const double v = x[t]; if (memcmp(&v, &magic, sizeof(double)) != 0) return false; }
+    return true;
+}
+
 static void pin_host_x(CacheEntry *e, const ssb_cholmod_factor *L)
 {
     static int enabled = -1;
     if (enabled < 0) { const char *v = getenv("SSB200_PIN_HOST"); enabled = (v && atoi(v) == 0) ? 0 : 1; }
-    if (!enabled || e->pinned_ptr == L->x) return;
-    unpin(e);
+    if (!enabled) return;
+    const size_t bytes = L->xsize * sizeof(double);
+    if (e->pinned_ptr == L->x && e->pinned_bytes == bytes) {
+        if (pin_probe(e, L)) return;
+        unpin(e);                                       // stale: the pages behind this range were replaced
+    } else unpin(e);
     if (L->xsize < (1u << 16)) return;                   // not worth it for small factors
-    cudaError_t err = cudaHostRegister(L->x, L->xsize * sizeof(double), cudaHostRegisterDefault);
-    if (err == cudaSuccess) e->pinned_ptr = L->x; else (void) cudaGetLastError();
+    cudaError_t err = cudaHostRegister(L->x, bytes, cudaHostRegisterDefault);
+    if (err != cudaSuccess) {
+        (void) cudaGetLastError();
+        // a stale registration of another (freed) factor may overlap this range: drop those and retry once
+        bool dropped = false;
+        for (auto &o : g_cache) {
+            if (&o == e || !o.pinned_ptr) continue;
+            const char *a0 = (const char *) o.pinned_ptr, *a1 = a0 + o.pinned_bytes, *b0 = (const char *) L->x, *b1 = b0 + bytes;
+            if (a0 < b1 && b0 < a1) { unpin(&o); dropped = true; }
+        }
+        if (dropped) err = cudaHostRegister(L->x, bytes, cudaHostRegisterDefault);
+        if (err != cudaSuccess) { (void) cudaGetLastError(); return; }
+    }
+    e->pinned_ptr = L->x; e->pinned_bytes = bytes;
+    if (!pin_probe(e, L)) unpin(e);
 }
 
 // returns the (possibly new) entry for L; nullptr on failure

@@ -39,6 +39,8 @@ struct PanelJob {
     int col0;            // first column of this step inside its supernode (for info)
     int snode;           // supernode index (for info)
     int tile_start;      // trsm: first tile of this job inside its launch
+    int winv_slot;       // >= 0: potrf also writes the inverse of the diagonal block to winv[slot]; trsm_tc reads it
+    int pad;
 };
 
 // One <=64-column slice of a supernode for the triangular solves: its diagonal block and every row of the supernode
@@ -54,7 +56,8 @@ struct SolveJob {
 constexpr int SOLVE_ROWS = 128;     // rows per solve-update tile
 struct SolveStep { long long job0; int njobs; long long tile0; int ntiles; };
 
-enum LaunchKind : int { L_GEMM_BIG = 0, L_GEMM_SMALL = 1, L_POTRF = 2, L_TRSM = 3 };
+enum LaunchKind : int { L_GEMM_BIG = 0, L_GEMM_SMALL = 1, L_POTRF = 2, L_TRSM = 3, L_TRSM_TC = 4, L_NKINDS = 5 };
+constexpr int TRSM_TC_MIN_W = 33;   // panels wider than 32 columns use the tensor-core trsm (inverse of the diagonal block)
 
 struct Launch {
     int kind;
@@ -89,6 +92,7 @@ struct HostPlan {
     std::vector<PanelJob> potrf_jobs;
     std::vector<PanelJob> trsm_jobs;
     std::vector<int> trsm_tiles;
+    int max_winv_slots = 0;          // inverse-diagonal-block workspace slots needed by the widest launch
     std::vector<Launch> launches;    // in execution order
     std::vector<int> level_launch_begin; // nlevels+1
     std::vector<CopyTask> copy_tasks;    // sorted by after_launch

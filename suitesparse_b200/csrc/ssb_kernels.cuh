@@ -241,25 +241,28 @@ constexpr int POTRF_THREADS = 256;
 // factorization.  Per column j: the owners of column j publish it to shared memory (double-buffered), one barrier,
 // then every thread applies the rank-1 update to its registers.  L's column j goes straight to global memory.
 __global__ void __launch_bounds__(POTRF_THREADS) potrf_block_kernel(const PanelJob *__restrict__ jobs, double *__restrict__ Lx,
-                                                                   int *__restrict__ info)
+                                                                   int *__restrict__ info, double *__restrict__ winv)
 {
     __shared__ double colbuf[2][NB_INNER];
+    __shared__ double rowbuf[2][NB_INNER];
     const PanelJob job = jobs[blockIdx.x];
     const int w = job.w, tid = threadIdx.x;
     const int ti = tid & 15, tk = tid >> 4;
     const long long lda = job.lda;
+    const bool want_inv = job.winv_slot >= 0;       // also build W = L^{-1} (forward substitution on the identity)
     double *__restrict__ A = Lx + job.x_off;
-    double t[4][4];
+    double t[4][4], y[4][4];
 #pragma unroll
     for (int a = 0; a < 4; a++)
 #pragma unroll
         for (int b = 0; b < 4; b++) {
             const int i = ti + 16 * a, k = tk + 16 * b;
             t[a][b] = (i < w && k < w && i >= k) ? A[i + k * lda] : 0.0;
+            y[a][b] = (i == k) ? 1.0 : 0.0;
         }
     for (int j = 0; j < w; j++) {
-        double *cb = colbuf[j & 1];
-        // owners of column j (tk == j%16, b == j/16) publish their rows
+        double *cb = colbuf[j & 1], *rb = rowbuf[j & 1];
+        // owners of column j of T (tk == j%16, b == j/16) publish their rows; owners of row j of Y publish it
         if (tk == (j & 15)) {
             const int b = j >> 4;
 #pragma unroll
@@ -270,13 +273,23 @@ __global__ void __launch_bounds__(POTRF_THREADS) potrf_block_kernel(const PanelJ
                 cb[ti + 16 * a] = v;
             }
         }
+        if (want_inv && ti == (j & 15)) {
+            const int a = j >> 4;
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                double v = 0.0;
+#pragma unroll
+                for (int aa = 0; aa < 4; aa++) if (aa == a) v = y[aa][b];
+                rb[tk + 16 * b] = v;
+            }
+        }
         __syncthreads();
         const double d = cb[j];
         if (!(d > 0.0)) {                           // uniform: every thread reads the same d
             if (tid == 0) atomicMin(&info[job.snode], job.col0 + j + 1);
             break;
         }
-        const double r = sqrt(d), rinv = 1.0 / r, dinv = 1.0 / d;
+        const double rinv = rsqrt(d), r = d * rinv, dinv = rinv * rinv;
         if (tid < w - j) { const int i = j + tid; A[i + j * lda] = (tid == 0) ? r : cb[i] * rinv; }   // w <= 64 < 256 threads
         double ci[4], ck[4];
 #pragma unroll
@@ -290,6 +303,27 @@ __global__ void __launch_bounds__(POTRF_THREADS) potrf_block_kernel(const PanelJ
                 const int i = ti + 16 * a, k = tk + 16 * b;
                 if (k > j && i >= k) t[a][b] -= ci[a] * ck[b];
             }
+        if (want_inv) {
+            // Y(j,:) /= L(j,j);  Y(i,:) -= L(i,j) * Y(j,:) for i > j      (L(i,j) = T(i,j) / r)
+            double yr[4];
+#pragma unroll
+            for (int b = 0; b < 4; b++) yr[b] = rb[tk + 16 * b] * rinv;
+#pragma unroll
+            for (int a = 0; a < 4; a++)
+#pragma unroll
+                for (int b = 0; b < 4; b++) {
+                    const int i = ti + 16 * a;
+                    if (i == j) y[a][b] = yr[b];
+                    else if (i > j) y[a][b] -= (ci[a] * rinv) * yr[b];
+                }
+        }
+    }
+    if (want_inv) {
+        double *__restrict__ W = winv + (long long) job.winv_slot * (NB_INNER * NB_INNER);
+#pragma unroll
+        for (int a = 0; a < 4; a++)
+#pragma unroll
+            for (int b = 0; b < 4; b++) W[(ti + 16 * a) + NB_INNER * (tk + 16 * b)] = y[a][b];
     }
 }
 
@@ -339,6 +373,76 @@ __global__ void __launch_bounds__(TRSM_ROWS) trsm_rows_kernel(const PanelJob *__
     else if (job.w <= 16) trsm_rows_body<16>(job, tile, Lx, Lsm);
     else if (job.w <= 32) trsm_rows_body<32>(job, tile, Lx, Lsm);
     else trsm_rows_body<64>(job, tile, Lx, Lsm);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// rows below a WIDE diagonal block on the tensor cores:  B <- B * W^T with W = L11^{-1} from potrf_block_kernel.
+// One CTA = 128 rows x (<= 64) columns, all of K (= w <= 64) resident in shared memory, 4 warps x (32 x 64) DMMA tiles.
+// In place: a CTA reads only its own rows (all columns) before it writes them.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int TRSM_TC_LDA = TRSM_ROWS + 4, TRSM_TC_LDW = NB_INNER + 4;
+constexpr size_t trsm_tc_smem_bytes() { return (size_t) NB_INNER * (TRSM_TC_LDA + TRSM_TC_LDW) * sizeof(double); }
+
+__global__ void __launch_bounds__(TRSM_ROWS) trsm_tc_kernel(const PanelJob *__restrict__ jobs, const int *__restrict__ tile_job,
+                                                            double *__restrict__ Lx, const double *__restrict__ winv)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *As = reinterpret_cast<double *>(smem_raw);          // As[k][r], k-major
+    double *Ws = As + NB_INNER * TRSM_TC_LDA;                   // Ws[k][j] = W(j,k)
+    const PanelJob job = jobs[tile_job[blockIdx.x]];
+    const int tile = (int) blockIdx.x - job.tile_start;
+    const int w = job.w, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long lda = job.lda;
+    const int r0 = tile * TRSM_ROWS;
+    const int rows = min(TRSM_ROWS, job.rows_below - r0);
+    double *__restrict__ B = Lx + job.x_off + w + r0;           // row r, column k at B[r + k*lda]
+    const double *__restrict__ W = winv + (long long) job.winv_slot * (NB_INNER * NB_INNER);
+    {
+        const bool okr = tid < rows;
+        const double *src = B + (okr ? tid : 0);
+        for (int k = 0; k < NB_INNER; k++) {
+            const bool ok = okr && k < w;
+            cp_async8(As + k * TRSM_TC_LDA + tid, ok ? src + (long long) k * lda : B, ok ? 8 : 0);
+        }
+        for (int e = tid; e < NB_INNER * NB_INNER; e += TRSM_ROWS) {
+            const int j = e % NB_INNER, k = e / NB_INNER;
+            cp_async8(Ws + k * TRSM_TC_LDW + j, W + e, 8);
+        }
+        cp_async_commit();
+    }
+    double acc[4][8][2];
+#pragma unroll
+    for (int m = 0; m < 4; m++)
+#pragma unroll
+        for (int nn = 0; nn < 8; nn++) acc[m][nn][0] = acc[m][nn][1] = 0.0;
+    cp_async_wait<0>();
+    __syncthreads();
+    const double *ap = As + (lane & 3) * TRSM_TC_LDA + warp * 32 + (lane >> 2);
+    const double *bp = Ws + (lane & 3) * TRSM_TC_LDW + (lane >> 2);
+    const int nks = (w + 3) >> 2;
+    for (int ks = 0; ks < nks; ks++) {
+        double a[4], b[8];
+#pragma unroll
+        for (int m = 0; m < 4; m++) a[m] = ap[ks * 4 * TRSM_TC_LDA + m * 8];
+#pragma unroll
+        for (int nn = 0; nn < 8; nn++) b[nn] = bp[ks * 4 * TRSM_TC_LDW + nn * 8];
+#pragma unroll
+        for (int m = 0; m < 4; m++)
+#pragma unroll
+            for (int nn = 0; nn < 8; nn++) dmma884(acc[m][nn][0], acc[m][nn][1], a[m], b[nn]);
+    }
+#pragma unroll
+    for (int nn = 0; nn < 8; nn++)
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+            const int j = nn * 8 + 2 * (lane & 3) + e;
+            if (j >= w) continue;
+#pragma unroll
+            for (int m = 0; m < 4; m++) {
+                const int r = warp * 32 + m * 8 + (lane >> 2);
+                if (r < rows) B[r + (long long) j * lda] = acc[m][nn][e];
+            }
+        }
 }
 
 // ------------------------------------------------------------------------------------------------------------------

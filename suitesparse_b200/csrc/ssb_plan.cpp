@@ -81,9 +81,10 @@ void append_factor_jobs(const HostPlan &hp, const std::vector<int> &snodes, int 
     for (int J0 = 0; J0 < maxcol; J0 += NB_OUTER) {
         for (int j0 = J0; j0 < std::min(J0 + NB_OUTER, maxcol); j0 += NB_INNER) {
             Launch LP{}; LP.kind = L_POTRF; LP.phase = 1; LP.job0 = (long long) out.potrf_jobs.size();
-            Launch LT{}; LT.kind = L_TRSM; LT.phase = 1; LT.job0 = (long long) out.trsm_jobs.size();
-            LT.tile0 = (long long) out.trsm_tiles.size();
-            long long ttiles = 0;
+            // rows-below jobs: narrow panels go to the substitution kernel, wide ones to the tensor-core kernel.  Both job
+            // lists live in trsm_jobs (substitution jobs of this step first), each with its own tile->job array.
+            std::vector<PanelJob> sub_jobs, tc_jobs;
+            int nslots = 0;
             for (int s : snodes) {
                 int nscol = hp.super[s + 1] - hp.super[s];
                 if (ncol_limit >= 0) nscol = std::min(nscol, ncol_limit);
@@ -93,15 +94,11 @@ void append_factor_jobs(const HostPlan &hp, const std::vector<int> &snodes, int 
                 PanelJob pj{};
                 pj.x_off = hp.px[s] + j0 + (long long) j0 * nsrow;
                 pj.lda = nsrow; pj.w = w; pj.rows_below = nsrow - j0 - w; pj.col0 = j0; pj.snode = s; pj.tile_start = 0;
+                pj.winv_slot = (pj.rows_below > 0 && w >= TRSM_TC_MIN_W) ? nslots++ : -1;
                 out.potrf_jobs.push_back(pj);
                 LP.njobs++; LP.flops += (double) w * w * w / 3.0;
                 if (pj.rows_below > 0) {
-                    pj.tile_start = (int) ttiles;
-                    int nt = (pj.rows_below + TRSM_ROWS - 1) / TRSM_ROWS;
-                    for (int q = 0; q < nt; q++) out.trsm_tiles.push_back(LT.njobs);
-                    ttiles += nt;
-                    out.trsm_jobs.push_back(pj);
-                    LT.njobs++; LT.flops += (double) w * w * pj.rows_below;
+                    (pj.winv_slot >= 0 ? tc_jobs : sub_jobs).push_back(pj);
                     // inner trailing update: remaining columns of the outer panel
                     const int outer_end = std::min(J0 + NB_OUTER, nscol);
                     const int ct = outer_end - (j0 + w);
@@ -114,9 +111,27 @@ void append_factor_jobs(const HostPlan &hp, const std::vector<int> &snodes, int 
                     }
                 }
             }
+            out.max_winv_slots = std::max(out.max_winv_slots, nslots);
+            auto emit_trsm = [&](std::vector<PanelJob> &jobs, int kind) {
+                Launch LT{}; LT.kind = kind; LT.phase = 1; LT.job0 = (long long) out.trsm_jobs.size();
+                LT.tile0 = (long long) out.trsm_tiles.size();
+                long long ttiles = 0;
+                for (PanelJob &pj : jobs) {
+                    pj.tile_start = (int) ttiles;
+                    const int nt = (pj.rows_below + TRSM_ROWS - 1) / TRSM_ROWS;
+                    for (int q = 0; q < nt; q++) out.trsm_tiles.push_back(LT.njobs);
+                    ttiles += nt;
+                    out.trsm_jobs.push_back(pj);
+                    LT.njobs++; LT.flops += (double) pj.w * pj.w * pj.rows_below;
+                }
+                LT.ntiles = (int) ttiles;
+                return LT;
+            };
+            Launch LT = emit_trsm(sub_jobs, L_TRSM);
+            Launch LT2 = emit_trsm(tc_jobs, L_TRSM_TC);
             if (LP.njobs) out.launches.push_back(LP);
-            LT.ntiles = (int) ttiles;
             if (LT.njobs) out.launches.push_back(LT);
+            if (LT2.njobs) out.launches.push_back(LT2);
             emit_update_launches(out, gs, gb, 1);
         }
         // columns [J0, J0+W) of every active supernode are final now: they can stream to the host while the trailing
