@@ -187,9 +187,25 @@ ssb200_plan *ssb200_plan_create(ssb_long n, ssb_long nsuper, const ssb_long *sup
                                 const ssb_long *px, const ssb_long *s, int device);
 void ssb200_plan_destroy(ssb200_plan *plan);
 
-/* Restrict the plan to a shard: supernode j is factorized by this plan iff owner[j]==rank
- * (owner==NULL: all).  Used for the elimination-tree subtree split across GPUs. */
-int ssb200_plan_set_owner(ssb200_plan *plan, const int32_t *owner, int rank);
+/* Elimination-tree shard over nranks GPUs, one process per GPU.  The plan builder cuts the supernodal
+ * etree into independent subtrees (LPT-balanced by dense flops) owned by one rank each; the wide supernodes above the cut
+ * are shared panel-cyclically (256-column panels).  Every rank keeps the whole Lx array; a finished subtree / panel is
+ * replicated by ONE broadcast of a contiguous Lx range, issued by the caller (torch.distributed / NCCL) between steps:
+ *     ssb200_upload_A(); ssb200_dist_begin();
+ *     for k < ssb200_dist_num_steps(): ssb200_dist_run_step(k); ssb200_dist_step_info(k,&src,&off,&cnt); if (src>=0) broadcast(Lx+off, cnt, src);
+ *     ssb200_dist_end(&bad);  minor = min over ranks of bad;  if (minor < n) ssb200_dist_zero_from(minor);
+ * All kernels and the broadcasts must share one stream: ssb200_set_stream(plan, cudaStream_t). */
+ssb200_plan *ssb200_plan_create_dist(ssb_long n, ssb_long nsuper, const ssb_long *super, const ssb_long *pi,
+                                     const ssb_long *px, const ssb_long *s, int device, int nranks, int rank);
+int      ssb200_set_stream(ssb200_plan *plan, void *cuda_stream);      /* NULL: back to the plan's own stream */
+ssb_long ssb200_dist_num_steps(const ssb200_plan *plan);
+int      ssb200_dist_step_info(const ssb200_plan *plan, ssb_long k, int *src, ssb_long *off, ssb_long *cnt);
+int      ssb200_dist_begin(ssb200_plan *plan, const double beta[2]);
+int      ssb200_dist_run_step(ssb200_plan *plan, ssb_long k);
+int      ssb200_dist_end(ssb200_plan *plan, ssb_long *first_bad_column);
+int      ssb200_dist_zero_from(ssb200_plan *plan, ssb_long column);
+int      ssb200_dist_flops(const ssb200_plan *plan, double *mine, double *total);
+int      ssb200_plan_set_owner(ssb200_plan *plan, const int32_t *owner, int rank);   /* superseded by ssb200_plan_create_dist */
 
 /* Numeric factorization.  A (and F for stype==0) are HOST CSC arrays with 64-bit indices:
  * Ap[n+1], Ai, Ax and optional Anz (unpacked).  stype<0 symmetric-lower input, stype==0 A*F.

@@ -39,7 +39,9 @@ static void free_cscbuf(CscBuf *b) { if (!b) return; if (b->p) cudaFree(b->p); i
 struct ssb200_plan {
     HostPlan hp;
     int device = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;           // launches go here (the plan's own stream, or the caller's: ssb200_set_stream)
+    cudaStream_t own_stream = nullptr;
+    int *d_owner = nullptr;                  // sharded plans: owner rank per supernode (-1 = panel-cyclic)
     cudaStream_t copy_stream = nullptr;      // device-to-host streaming of finished supernodes
     cudaEvent_t copy_gate = nullptr, copy_done = nullptr;
     int *d_super = nullptr, *d_ls = nullptr, *d_supermap = nullptr, *d_relmap = nullptr, *d_info = nullptr;
@@ -99,7 +101,7 @@ static void plan_free(ssb200_plan *p)
 {
     if (!p) return;
     cudaSetDevice(p->device);
-    void *ptrs[] = {p->d_super, p->d_ls, p->d_supermap, p->d_relmap, p->d_info, p->d_pi, p->d_px, p->d_Lx, p->d_winv, p->jobs.gemm_jobs,
+    void *ptrs[] = {p->d_owner, p->d_super, p->d_ls, p->d_supermap, p->d_relmap, p->d_info, p->d_pi, p->d_px, p->d_Lx, p->d_winv, p->jobs.gemm_jobs,
                     p->jobs.gemm_tiles, p->jobs.potrf_jobs, p->jobs.trsm_jobs, p->jobs.trsm_tiles, p->d_solve_jobs, p->d_solve_tiles,
                     p->d_X};
     for (void *q : ptrs) if (q) cudaFree(q);
@@ -110,7 +112,7 @@ static void plan_free(ssb200_plan *p)
     if (p->copy_gate) cudaEventDestroy(p->copy_gate);
     if (p->copy_done) cudaEventDestroy(p->copy_done);
     if (p->copy_stream) cudaStreamDestroy(p->copy_stream);
-    if (p->stream) cudaStreamDestroy(p->stream);
+    if (p->own_stream) cudaStreamDestroy(p->own_stream);
     delete p;
 }
 
@@ -139,6 +141,7 @@ static int plan_build_device(ssb200_plan *p)
     if (dev_alloc_copy(p, &p->d_px, hp.px)) return SSB_CHOLMOD_GPU_PROBLEM;
     if (dev_alloc_copy(p, &p->d_ls, hp.ls)) return SSB_CHOLMOD_GPU_PROBLEM;
     if (dev_alloc_copy(p, &p->d_supermap, hp.supermap)) return SSB_CHOLMOD_GPU_PROBLEM;
+    if (hp.nranks > 1) if (dev_alloc_copy(p, &p->d_owner, hp.owner)) return SSB_CHOLMOD_GPU_PROBLEM;
     if (const char *fa = getenv("SSB200_FORCE_ATOMIC")) { if (atoi(fa)) for (auto &g : hp.gemm_jobs) g.atomic = 1; }
     if (upload_jobs(p, hp, p->jobs)) return SSB_CHOLMOD_GPU_PROBLEM;
     if (dev_alloc_copy(p, &p->d_solve_jobs, hp.solve_jobs)) return SSB_CHOLMOD_GPU_PROBLEM;
@@ -182,7 +185,7 @@ static int plan_build_device(ssb200_plan *p)
 }
 
 static ssb200_plan *plan_create_impl(ssb_long n, ssb_long nsuper, const ssb_long *super, const ssb_long *pi, const ssb_long *px,
-                                     const ssb_long *s, int device, const int *owner, int rank)
+                                     const ssb_long *s, int device, int nranks, int rank)
 {
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_error("no CUDA device: the hot path has no CPU fallback"); return nullptr; }
@@ -192,11 +195,12 @@ static ssb200_plan *plan_create_impl(ssb_long n, ssb_long nsuper, const ssb_long
     ssb200_plan *p = new ssb200_plan();
     p->device = device; p->bufA = new CscBuf(); p->bufF = new CscBuf();
     if (!build_host_plan(n, nsuper, (const long long *) super, (const long long *) pi, (const long long *) px, (const long long *) s,
-                         owner, rank, p->hp)) {
+                         nranks, rank, p->hp)) {
         set_error("invalid symbolic factor: " + p->hp.error); delete p; return nullptr;
     }
-    if (cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+    if (cudaStreamCreateWithFlags(&p->own_stream, cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&p->copy_gate, cudaEventDisableTiming) != cudaSuccess || cudaEventCreate(&p->copy_done) != cudaSuccess) { set_error("cudaStreamCreate failed"); delete p; return nullptr; }
+    p->stream = p->own_stream;
     if (plan_build_device(p) != 0) { plan_free(p); return nullptr; }
     return p;
 }
@@ -204,15 +208,106 @@ static ssb200_plan *plan_create_impl(ssb_long n, ssb_long nsuper, const ssb_long
 extern "C" ssb200_plan *ssb200_plan_create(ssb_long n, ssb_long nsuper, const ssb_long *super, const ssb_long *pi, const ssb_long *px,
                                            const ssb_long *s, int device)
 {
-    return plan_create_impl(n, nsuper, super, pi, px, s, device, nullptr, 0);
+    return plan_create_impl(n, nsuper, super, pi, px, s, device, 1, 0);
 }
 
 extern "C" void ssb200_plan_destroy(ssb200_plan *plan) { plan_free(plan); }
 
+// ---- sharded factorization: one process per GPU, the caller (suitesparse_b200/dist.py) moves the finished Lx ranges
+// between the ranks with torch.distributed / NCCL broadcasts on the same stream ---------------------------------------
+extern "C" ssb200_plan *ssb200_plan_create_dist(ssb_long n, ssb_long nsuper, const ssb_long *super, const ssb_long *pi, const ssb_long *px,
+                                                const ssb_long *s, int device, int nranks, int rank)
+{
+    if (nranks < 1 || rank < 0 || rank >= nranks) { set_error("bad rank / nranks"); return nullptr; }
+    return plan_create_impl(n, nsuper, super, pi, px, s, device, nranks, rank);
+}
+
+extern "C" int ssb200_set_stream(ssb200_plan *p, void *stream)
+{
+    if (!p) return SSB_CHOLMOD_INVALID;
+    p->stream = stream ? (cudaStream_t) stream : p->own_stream;
+    return 0;
+}
+
+extern "C" ssb_long ssb200_dist_num_steps(const ssb200_plan *p) { return p ? (ssb_long) p->hp.steps.size() : 0; }
+
+// step k: *src = broadcasting rank (-1: none), [*off, *off+*cnt) = the Lx range that is final on src after the step's launches
+extern "C" int ssb200_dist_step_info(const ssb200_plan *p, ssb_long k, int *src, ssb_long *off, ssb_long *cnt)
+{
+    if (!p || k < 0 || k >= (ssb_long) p->hp.steps.size()) return SSB_CHOLMOD_INVALID;
+    const DistStep &st = p->hp.steps[k];
+    *src = st.bcast_src; *off = st.off; *cnt = st.cnt;
+    return 0;
+}
+
+static int scatter_A(ssb200_plan *p, double beta0, long long kfirst, long long kcount);
+static int run_launch(ssb200_plan *p, const Launch &L, const DevJobs &dj);
+
+// zero Lx, assemble the columns this rank computes; everything is enqueued on the plan's stream, nothing is synchronized
+extern "C" int ssb200_dist_begin(ssb200_plan *p, const double beta[2])
+{
+    if (!p || !p->haveA) { set_error("no plan / no matrix uploaded"); return SSB_CHOLMOD_INVALID; }
+    HostPlan &hp = p->hp;
+    CU_TRY(cudaSetDevice(p->device));
+    p->stats.kernel_launches = 0; p->factor_on_device = false;
+    if (hp.nsuper == 0) return 0;
+    CU_TRY(cudaMemsetAsync(p->d_Lx, 0, (size_t) hp.xsize * sizeof(double), p->stream));
+    fill_int_kernel<<<(unsigned) ((hp.nsuper + 255) / 256), 256, 0, p->stream>>>(p->d_info, hp.nsuper, INT_MAX);
+    p->stats.kernel_launches++;
+    return scatter_A(p, beta ? beta[0] : 0.0, 0, hp.n);
+}
+
+extern "C" int ssb200_dist_run_step(ssb200_plan *p, ssb_long k)
+{
+    if (!p || k < 0 || k >= (ssb_long) p->hp.steps.size()) return SSB_CHOLMOD_INVALID;
+    const DistStep &st = p->hp.steps[k];
+    for (int t = st.launch_begin; t < st.launch_end; t++)
+        if (run_launch(p, p->hp.launches[t], p->jobs)) return SSB_CHOLMOD_GPU_PROBLEM;
+    CU_TRY(cudaGetLastError());
+    return 0;
+}
+
+// Synchronizes; *first_bad_column = smallest column at which one of THIS rank's diagonal blocks failed (n if none).  The
+// caller takes the minimum over the ranks.  The reference's partial refactorization of the failing supernode
+// (t_cholmod_super_numeric.c:944-967) is not reproduced in the sharded path: ssb200_dist_zero_from() zeroes the failing
+// supernode and everything after it on every rank.
+extern "C" int ssb200_dist_end(ssb200_plan *p, ssb_long *first_bad_column)
+{
+    if (!p) return SSB_CHOLMOD_INVALID;
+    HostPlan &hp = p->hp;
+    if (first_bad_column) *first_bad_column = hp.n;
+    if (hp.nsuper == 0) { p->factor_on_device = true; return 0; }
+    CU_TRY(cudaMemcpyAsync(p->h_info, p->d_info, hp.nsuper * sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+    CU_TRY(cudaStreamSynchronize(p->stream));
+    for (long long s = 0; s < hp.nsuper; s++)
+        if (p->h_info[s] != INT_MAX) { if (first_bad_column) *first_bad_column = hp.super[s] + p->h_info[s] - 1; break; }
+    p->stats.kernel_launches_total += p->stats.kernel_launches;
+    p->factor_on_device = true;
+    return 0;
+}
+
+extern "C" int ssb200_dist_zero_from(ssb200_plan *p, ssb_long column)
+{
+    if (!p || column < 0 || column >= p->hp.n) return SSB_CHOLMOD_INVALID;
+    const int s = p->hp.supermap[column];
+    const long long off = p->hp.px[s];
+    CU_TRY(cudaMemsetAsync(p->d_Lx + off, 0, (size_t) (p->hp.xsize - off) * sizeof(double), p->stream));
+    CU_TRY(cudaStreamSynchronize(p->stream));
+    return 0;
+}
+
+// dense flops this rank executes in one factorization, and the global total (load balance of the shard)
+extern "C" int ssb200_dist_flops(const ssb200_plan *p, double *mine, double *total)
+{
+    if (!p) return SSB_CHOLMOD_INVALID;
+    *mine = p->hp.my_flops; *total = p->hp.flops_update + p->hp.flops_potrf + p->hp.flops_trsm;
+    return 0;
+}
+
 extern "C" int ssb200_plan_set_owner(ssb200_plan *plan, const int32_t *owner, int rank)
 {
     (void) plan; (void) owner; (void) rank;
-    set_error("ssb200_plan_set_owner: elimination-tree sharding is not implemented in this round");
+    set_error("ssb200_plan_set_owner: use ssb200_plan_create_dist (the shard is computed by the plan builder)");
     return SSB_CHOLMOD_NOT_INSTALLED;
 }
 
@@ -316,7 +411,7 @@ static int scatter_A(ssb200_plan *p, double beta0, long long kfirst, long long k
     DevCsc F{p->bufF->p, p->bufF->i, p->bufF->haveNz ? p->bufF->nz : nullptr, p->bufF->x};
     const int T = 128;
     const long long g = (kcount + T - 1) / T;
-    scatter_A_kernel<<<(unsigned) g, T, 0, p->stream>>>(dev_sym(p), p->stype, A, F, beta0, p->d_Lx, kfirst, kcount, nullptr);
+    scatter_A_kernel<<<(unsigned) g, T, 0, p->stream>>>(dev_sym(p), p->stype, A, F, beta0, p->d_Lx, kfirst, kcount, p->d_owner, p->hp.nranks, p->hp.rank);
     p->stats.kernel_launches++;
     CU_TRY(cudaGetLastError());
     return 0;

@@ -73,6 +73,9 @@ struct Launch {
 struct CopyTask { int after_launch; long long off, cnt; };
 constexpr int COPY_FLUSH_LEVEL = 8;  // supernodes up to this etree level are copied in merged ranges after that level
 
+// One step of the distributed schedule.  Every rank walks the same step list (same broadcasts); only the launches differ.
+struct DistStep { int launch_begin, launch_end; int bcast_src; long long off, cnt; };
+
 struct Update { int d, s; int p0, nd1, nd2; long long map_off; };
 
 struct HostPlan {
@@ -96,6 +99,11 @@ struct HostPlan {
     std::vector<Launch> launches;    // in execution order
     std::vector<int> level_launch_begin; // nlevels+1
     std::vector<CopyTask> copy_tasks;    // sorted by after_launch
+    // ---- elimination-tree shard over several GPUs (one process per GPU) -------------------------------------
+    int nranks = 1, rank = 0;
+    std::vector<int> owner;              // per supernode: rank that computes it, or -1 = its 256-column panels are cyclic over ranks
+    std::vector<DistStep> steps;         // launches [begin,end) of this rank, then an optional broadcast of a finished Lx range
+    double my_flops = 0;                 // dense flops this rank executes
     // solve schedule: supernodes ordered by level
     std::vector<int> level_ptr;      // nlevels+1
     std::vector<int> level_nodes;    // supernodes sorted by level
@@ -109,11 +117,12 @@ struct HostPlan {
 
 // Builds everything above from the symbolic factor.  Returns false (plan.error set) on invalid structure.
 bool build_host_plan(long long n, long long nsuper, const long long *super, const long long *pi, const long long *px,
-                     const long long *s, const int *owner, int rank, HostPlan &plan);
+                     const long long *s, int nranks, int rank, HostPlan &plan);
 
 // Job lists for factorizing ONE supernode restricted to its first ncol_limit columns (not-positive-definite repeat,
 // t_cholmod_super_numeric.c:944-967).  Appends launches to `out`.
-void append_factor_jobs(const HostPlan &hp, const std::vector<int> &snodes, int ncol_limit, HostPlan &out, bool panel_copies = false);
+void append_factor_jobs(const HostPlan &hp, const std::vector<int> &snodes, int ncol_limit, HostPlan &out, bool panel_copies = false,
+                        int only_panel_J0 = -1);
 
 int gemm_tile_size(int kind);       // 128 for L_GEMM_BIG, 64 for L_GEMM_SMALL
 

@@ -472,16 +472,19 @@ __device__ __forceinline__ int find_row(const int *__restrict__ rows, int nrows,
 
 // one thread per column k of L: copy A(k:n,k) (stype<0) or (A*F)(k:n,k) (stype==0) into its supernode, add beta.
 // Entries outside the pattern of L are dropped (the reference only avoids the segfault, :366-378).
-// only_snode >= 0 restricts the kernel to the columns of that supernode (not-posdef repeat).
+// [kfirst, kfirst+kcount) restricts the kernel to a column range (not-posdef repeat of one supernode).
 __global__ void scatter_A_kernel(DevSym sym, int stype, DevCsc A, DevCsc F, double beta, double *__restrict__ Lx,
-                                 long long kfirst, long long kcount, const int *__restrict__ owner_mask)
+                                 long long kfirst, long long kcount, const int *__restrict__ owner, int nranks, int rank)
 {
     const long long t = blockIdx.x * (long long) blockDim.x + threadIdx.x;
     if (t >= kcount) return;
     const long long k = kfirst + t;
     const int s = sym.supermap[k];
-    if (owner_mask && !owner_mask[s]) return;
     const int k1 = sym.super[s];
+    if (owner) {        // sharded factorization: only the rank that computes this column assembles it
+        const int o = owner[s];
+        if (o >= 0 ? (o != rank) : ((int) ((k - k1) / NB_OUTER) % nranks != rank)) return;
+    }
     const long long psi = sym.pi[s];
     const int nsrow = (int) (sym.pi[s + 1] - psi);
     const int *__restrict__ rows = sym.ls + psi;

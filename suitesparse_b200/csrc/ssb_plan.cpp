@@ -69,7 +69,8 @@ inline void route_gemm(const GemmJob &j, std::vector<GemmJob> &small, std::vecto
 
 // Blocked factorization steps for a set of mutually independent supernodes (one etree level, or one repeated
 // supernode with ncol_limit >= 0).  Appends to out.{potrf_jobs,trsm_jobs,trsm_tiles,gemm_jobs,gemm_tiles,launches}.
-void append_factor_jobs(const HostPlan &hp, const std::vector<int> &snodes, int ncol_limit, HostPlan &out, bool panel_copies)
+void append_factor_jobs(const HostPlan &hp, const std::vector<int> &snodes, int ncol_limit, HostPlan &out, bool panel_copies,
+                        int only_panel_J0)
 {
     int maxcol = 0;
     for (int s : snodes) {
@@ -78,7 +79,7 @@ void append_factor_jobs(const HostPlan &hp, const std::vector<int> &snodes, int 
         maxcol = std::max(maxcol, nscol);
     }
     std::vector<GemmJob> gs, gb;
-    for (int J0 = 0; J0 < maxcol; J0 += NB_OUTER) {
+    for (int J0 = (only_panel_J0 >= 0 ? only_panel_J0 : 0); J0 < maxcol; J0 += NB_OUTER) {
         for (int j0 = J0; j0 < std::min(J0 + NB_OUTER, maxcol); j0 += NB_INNER) {
             Launch LP{}; LP.kind = L_POTRF; LP.phase = 1; LP.job0 = (long long) out.potrf_jobs.size();
             // rows-below jobs: narrow panels go to the substitution kernel, wide ones to the tensor-core kernel.  Both job
@@ -146,6 +147,7 @@ void append_factor_jobs(const HostPlan &hp, const std::vector<int> &snodes, int 
                 out.copy_tasks.push_back(CopyTask{after, hp.px[s] + (long long) J0 * nsrow, (long long) W * nsrow});
             }
         }
+        if (only_panel_J0 >= 0) break;          // distributed supernode: the trailing update is split over the ranks by the caller
         // outer trailing update with the whole NB_OUTER-wide panel
         for (int s : snodes) {
             int nscol = hp.super[s + 1] - hp.super[s];
@@ -166,7 +168,7 @@ void append_factor_jobs(const HostPlan &hp, const std::vector<int> &snodes, int 
 }
 
 bool build_host_plan(long long n, long long nsuper, const long long *super, const long long *pi, const long long *px,
-                     const long long *s, const int *owner, int rank, HostPlan &hp)
+                     const long long *s, int nranks, int rank, HostPlan &hp)
 {
     hp = HostPlan();
     if (n < 0 || nsuper < 0 || (nsuper > 0 && (!super || !pi || !px || !s))) { hp.error = "null symbolic arrays"; return false; }
@@ -226,75 +228,195 @@ bool build_host_plan(long long n, long long nsuper, const long long *super, cons
     for (auto &u : ups) { u.map_off = moff; moff += u.nd2; }
     hp.relmap_size = moff;
     hp.updates.swap(ups);
+    // ---- shard: which rank computes which supernode ---------------------------------------------------------------
+    hp.nranks = std::max(1, nranks); hp.rank = rank;
+    std::vector<double> sn_flops(nsuper, 0.0);          // dense flops with this supernode as the target
+    for (int t = 0; t < (int) nsuper; t++) {
+        const double nscol = hp.super[t + 1] - hp.super[t], nsrow = (double) (hp.pi[t + 1] - hp.pi[t]);
+        sn_flops[t] = nscol * nscol * nscol / 3.0 + nscol * nscol * (nsrow - nscol);
+    }
+    for (const Update &u : hp.updates) {
+        const double ndcol = hp.super[u.d + 1] - hp.super[u.d];
+        sn_flops[u.s] += 2.0 * ndcol * ((double) u.nd1 * u.nd2 - 0.5 * (double) u.nd1 * (u.nd1 - 1));
+    }
+    hp.owner.assign(nsuper, 0);
+    std::vector<int> first_desc(nsuper);                // subtree of t = supernodes [first_desc[t], t] (postordered etree)
+    if (hp.nranks > 1) {
+        std::vector<double> sub(sn_flops);
+        for (int t = 0; t < (int) nsuper; t++) first_desc[t] = t;
+        for (int t = 0; t < (int) nsuper; t++)
+            if (hp.parent[t] >= 0) { sub[hp.parent[t]] += sub[t]; first_desc[hp.parent[t]] = std::min(first_desc[hp.parent[t]], first_desc[t]); }
+        std::vector<std::vector<int>> kids(nsuper);
+        std::vector<int> cand;                          // roots of the candidate subtrees
+        double total = 0;
+        for (int t = 0; t < (int) nsuper; t++) { if (hp.parent[t] >= 0) kids[hp.parent[t]].push_back(t); else { cand.push_back(t); total += sub[t]; } }
+        std::vector<char> in_top(nsuper, 0);
+        // split the heaviest subtree until there are enough, small enough subtrees to balance the ranks
+        for (;;) {
+            int best = -1;
+            for (int c = 0; c < (int) cand.size(); c++) if (best < 0 || sub[cand[c]] > sub[cand[best]]) best = c;
+            if (best < 0) break;
+            const int r = cand[best];
+            const bool enough = (int) cand.size() >= 4 * hp.nranks && sub[r] <= total / (4.0 * hp.nranks);
+            if (enough || kids[r].empty() || sub[r] < 1e-4 * total) break;
+            in_top[r] = 1;
+            cand.erase(cand.begin() + best);
+            for (int k : kids[r]) cand.push_back(k);
+        }
+        // longest-processing-time-first assignment of the subtrees
+        std::sort(cand.begin(), cand.end(), [&](int a, int b) { return sub[a] > sub[b] || (sub[a] == sub[b] && a < b); });
+        std::vector<double> load(hp.nranks, 0.0);
+        for (int r : cand) {
+            const int q = (int) (std::min_element(load.begin(), load.end()) - load.begin());
+            load[q] += sub[r];
+            for (int t = first_desc[r]; t <= r; t++) hp.owner[t] = q;
+        }
+        // supernodes above the cut: wide ones are shared panel-cyclically, narrow ones go to the least loaded rank
+        for (int t = 0; t < (int) nsuper; t++) {
+            if (!in_top[t]) continue;
+            const int nscol = hp.super[t + 1] - hp.super[t];
+            if (nscol >= 2 * NB_OUTER) { hp.owner[t] = -1; for (auto &v : load) v += sn_flops[t] / hp.nranks; }
+            else { const int q = (int) (std::min_element(load.begin(), load.end()) - load.begin()); load[q] += sn_flops[t]; hp.owner[t] = q; }
+        }
+        // subtree roots / narrow top supernodes: their finished Lx ranges are broadcast after their level
+        for (int r : cand) first_desc[r] = -1 - first_desc[r];     // mark: negative = broadcast root, range starts at -1-value
+        for (int t = 0; t < (int) nsuper; t++) if (in_top[t] && hp.owner[t] >= 0) first_desc[t] = -1 - t;
+    }
+    auto mine_whole = [&](int sn) { return hp.owner[sn] == hp.rank; };
+    auto close_step = [&](int &step_begin, int src, long long off, long long cnt) {
+        hp.steps.push_back(DistStep{step_begin, (int) hp.launches.size(), src, off, cnt});
+        step_begin = (int) hp.launches.size();
+    };
     // ---- per level launches ----------------------------------------------------------------------------------
     hp.level_launch_begin.assign(hp.nlevels + 1, 0);
     size_t upos = 0;
     std::vector<GemmJob> gs, gb;
     std::vector<int> nodes;
+    int step_begin = 0;
     for (int l = 0; l < hp.nlevels; l++) {
         hp.level_launch_begin[l] = (int) hp.launches.size();
-        // which targets receive more than one update in this level -> atomics needed (different CTAs, same entries)
         size_t ubeg = upos;
         while (upos < hp.updates.size() && hp.level[hp.updates[upos].s] == l) upos++;
         for (size_t t = ubeg; t < upos; t++) {
             const Update &u = hp.updates[t];
-            if (owner && owner[u.s] != rank) continue;
             const int ndcol = hp.super[u.d + 1] - hp.super[u.d];
             const int ndrow = (int) (hp.pi[u.d + 1] - hp.pi[u.d]);
             const int nsrow = (int) (hp.pi[u.s + 1] - hp.pi[u.s]);
-            GemmJob g{};
-            g.a_off = hp.px[u.d] + u.p0;
-            g.c_off = hp.px[u.s];
-            g.map_off = u.map_off; g.lda = ndrow; g.ldc = nsrow; g.K = ndcol; g.nd1 = u.nd1; g.nd2 = u.nd2; g.atomic = 1;
-            route_gemm(g, gs, gb);
             const double tri = (double) u.nd1 * u.nd2 - 0.5 * (double) u.nd1 * (u.nd1 - 1);
             hp.flops_update += 2.0 * ndcol * tri;
             hp.bytes_update_panel += 8.0 * (double) u.nd2 * ndcol;
             hp.bytes_update_scatter += 16.0 * tri;
+            GemmJob g{};
+            g.a_off = hp.px[u.d] + u.p0;
+            g.c_off = hp.px[u.s];
+            g.map_off = u.map_off; g.lda = ndrow; g.ldc = nsrow; g.K = ndcol; g.nd1 = u.nd1; g.nd2 = u.nd2; g.atomic = 1;
+            if (hp.owner[u.s] >= 0) {
+                if (!mine_whole(u.s)) continue;
+                hp.my_flops += 2.0 * ndcol * tri;
+                route_gemm(g, gs, gb);
+            } else {
+                // panel-cyclic target: cut the update where its target column crosses a 256-column panel boundary; a cut
+                // at local row jlo is itself a valid update (rows jlo.. of the descendant, columns [jlo, jhi))
+                const int k1 = hp.super[u.s];
+                const int *rows = hp.ls.data() + hp.pi[u.d] + u.p0;
+                int jlo = 0;
+                while (jlo < u.nd1) {
+                    const int blk = (rows[jlo] - k1) / NB_OUTER;
+                    int jhi = jlo + 1;
+                    while (jhi < u.nd1 && (rows[jhi] - k1) / NB_OUTER == blk) jhi++;
+                    if (blk % hp.nranks == hp.rank) {
+                        GemmJob h = g;
+                        h.a_off += jlo; h.map_off += jlo; h.nd1 = jhi - jlo; h.nd2 = u.nd2 - jlo;
+                        hp.my_flops += 2.0 * ndcol * ((double) h.nd1 * h.nd2 - 0.5 * (double) h.nd1 * (h.nd1 - 1));
+                        route_gemm(h, gs, gb);
+                    }
+                    jlo = jhi;
+                }
+            }
         }
         emit_update_launches(hp, gs, gb, 0);
         nodes.clear();
         for (int t = hp.level_ptr[l]; t < hp.level_ptr[l + 1]; t++) {
             const int sn = hp.level_nodes[t];
-            if (owner && owner[sn] != rank) continue;
-            nodes.push_back(sn);
             const double nscol = hp.super[sn + 1] - hp.super[sn], nsrow = (double) (hp.pi[sn + 1] - hp.pi[sn]);
             hp.flops_potrf += nscol * nscol * nscol / 3.0;
             hp.flops_trsm += nscol * nscol * (nsrow - nscol);
+            if (hp.owner[sn] < 0 || !mine_whole(sn)) continue;
+            nodes.push_back(sn);
+            hp.my_flops += nscol * nscol * nscol / 3.0 + nscol * nscol * (nsrow - nscol);
         }
         const int flush = std::min(COPY_FLUSH_LEVEL, hp.nlevels - 1);
-        if (!nodes.empty()) append_factor_jobs(hp, nodes, -1, hp, /*panel_copies=*/l > flush);
-        if (l == flush && !hp.launches.empty()) {
+        if (!nodes.empty()) append_factor_jobs(hp, nodes, -1, hp, /*panel_copies=*/hp.nranks == 1 && l > flush);
+        if (hp.nranks == 1 && l == flush && !hp.launches.empty()) {
             // every supernode of level <= flush is final: merge consecutive indices into contiguous Lx ranges
             const int after = (int) hp.launches.size() - 1;
             long long run_off = -1, run_end = -1;
             for (int t = 0; t < (int) nsuper; t++) {
-                const bool mine = hp.level[t] <= flush && (!owner || owner[t] == rank);
-                if (mine) {
+                const bool low = hp.level[t] <= flush;
+                if (low) {
                     if (run_off < 0) run_off = hp.px[t];
                     run_end = hp.px[t + 1];
                 }
-                if ((!mine || t == (int) nsuper - 1) && run_off >= 0) {
+                if ((!low || t == (int) nsuper - 1) && run_off >= 0) {
                     hp.copy_tasks.push_back(CopyTask{after, run_off, run_end - run_off});
                     run_off = -1;
                 }
             }
         }
+        if (hp.nranks > 1) {
+            // panel-cyclic supernodes of this level: owner factorizes a 256-column panel, broadcasts it, everybody updates
+            // the panels it owns
+            for (int t = hp.level_ptr[l]; t < hp.level_ptr[l + 1]; t++) {
+                const int sn = hp.level_nodes[t];
+                if (hp.owner[sn] >= 0) continue;
+                const int nscol = hp.super[sn + 1] - hp.super[sn];
+                const long long nsrow = hp.pi[sn + 1] - hp.pi[sn];
+                std::vector<int> one{sn};
+                for (int J0 = 0; J0 < nscol; J0 += NB_OUTER) {
+                    const int W = std::min(NB_OUTER, nscol - J0);
+                    const int src = (J0 / NB_OUTER) % hp.nranks;
+                    if (src == hp.rank) {
+                        append_factor_jobs(hp, one, -1, hp, false, J0);
+                        hp.my_flops += (double) W * W * W / 3.0 + (double) W * W * (nsrow - J0 - W);
+                    }
+                    close_step(step_begin, src, hp.px[sn] + (long long) J0 * nsrow, (long long) W * nsrow);
+                    // trailing update of the panels this rank owns
+                    for (int J1 = J0 + NB_OUTER; J1 < nscol; J1 += NB_OUTER) {
+                        if ((J1 / NB_OUTER) % hp.nranks != hp.rank) continue;
+                        const int W1 = std::min(NB_OUTER, nscol - J1);
+                        GemmJob g{};
+                        g.a_off = hp.px[sn] + J1 + (long long) J0 * nsrow;
+                        g.c_off = hp.px[sn] + J1 + (long long) J1 * nsrow;
+                        g.map_off = -1; g.lda = (int) nsrow; g.ldc = (int) nsrow; g.K = W; g.nd1 = W1; g.nd2 = (int) (nsrow - J1); g.atomic = 1;
+                        hp.my_flops += 2.0 * W * ((double) g.nd1 * g.nd2 - 0.5 * (double) g.nd1 * (g.nd1 - 1));
+                        route_gemm(g, gs, gb);
+                    }
+                    emit_update_launches(hp, gs, gb, 1);
+                }
+            }
+            // finished subtrees / narrow top supernodes of this level: replicate them
+            for (int t = hp.level_ptr[l]; t < hp.level_ptr[l + 1]; t++) {
+                const int sn = hp.level_nodes[t];
+                if (first_desc[sn] >= 0 || hp.owner[sn] < 0) continue;
+                const int lo = -1 - first_desc[sn];
+                close_step(step_begin, hp.owner[sn], hp.px[lo], hp.px[sn + 1] - hp.px[lo]);
+            }
+        }
     }
     hp.level_launch_begin[hp.nlevels] = (int) hp.launches.size();
+    close_step(step_begin, -1, 0, 0);
+    if (hp.nranks == 1) hp.my_flops = hp.flops_update + hp.flops_potrf + hp.flops_trsm;
     // ---- solve schedule: per level, per 64-column block index ------------------------------------------------
     for (int l = 0; l < hp.nlevels; l++) {
         int maxcol = 0;
         for (int t = hp.level_ptr[l]; t < hp.level_ptr[l + 1]; t++) {
             const int sn = hp.level_nodes[t];
-            if (owner && owner[sn] != rank) continue;
             maxcol = std::max(maxcol, hp.super[sn + 1] - hp.super[sn]);
         }
         for (int j0 = 0; j0 < maxcol; j0 += NB_INNER) {
             SolveStep st{(long long) hp.solve_jobs.size(), 0, (long long) hp.solve_tiles.size(), 0};
             for (int t = hp.level_ptr[l]; t < hp.level_ptr[l + 1]; t++) {
                 const int sn = hp.level_nodes[t];
-                if (owner && owner[sn] != rank) continue;
                 const int nscol = hp.super[sn + 1] - hp.super[sn];
                 if (nscol <= j0) continue;
                 const int nsrow = (int) (hp.pi[sn + 1] - hp.pi[sn]);
@@ -326,12 +448,46 @@ extern "C" int ssb200_plan_summary(long long n, long long nsuper, const long lon
                                    const long long *s, double *out, int *level_of_supernode)
 {
     ssb::HostPlan hp;
-    if (!ssb::build_host_plan(n, nsuper, super, pi, px, s, nullptr, 0, hp)) return -4;
+    if (!ssb::build_host_plan(n, nsuper, super, pi, px, s, 1, 0, hp)) return -4;
     out[0] = hp.nlevels; out[1] = (double) hp.updates.size(); out[2] = (double) hp.relmap_size; out[3] = (double) hp.launches.size();
     out[4] = (double) hp.gemm_jobs.size(); out[5] = (double) hp.gemm_tiles.size(); out[6] = (double) hp.potrf_jobs.size();
     out[7] = (double) hp.trsm_jobs.size(); out[8] = (double) hp.trsm_tiles.size(); out[9] = (double) hp.solve_steps.size();
     out[10] = (double) hp.solve_jobs.size(); out[11] = hp.flops_update; out[12] = hp.flops_potrf; out[13] = hp.flops_trsm;
     out[14] = hp.bytes_update_panel; out[15] = hp.bytes_update_scatter;
     if (level_of_supernode) for (long long t = 0; t < nsuper; t++) level_of_supernode[t] = hp.level[t];
+    return 0;
+}
+
+// ---- host-only export of one rank's schedule (no GPU): tests/emulate_plan.py replays it in numpy, with gloo broadcasts
+// between ranks, to check the shard + schedule logic on a CPU-only box -------------------------------------------------
+static ssb::HostPlan *g_export = nullptr;
+
+extern "C" int ssb200_export_begin(long long n, long long nsuper, const long long *super, const long long *pi, const long long *px,
+                                   const long long *s, int nranks, int rank, long long *sizes /*[8]*/)
+{
+    delete g_export; g_export = new ssb::HostPlan();
+    if (!ssb::build_host_plan(n, nsuper, super, pi, px, s, nranks, rank, *g_export)) { delete g_export; g_export = nullptr; return -4; }
+    sizes[0] = (long long) g_export->launches.size(); sizes[1] = (long long) g_export->gemm_jobs.size();
+    sizes[2] = (long long) g_export->potrf_jobs.size(); sizes[3] = (long long) g_export->trsm_jobs.size();
+    sizes[4] = (long long) g_export->steps.size(); sizes[5] = (long long) g_export->updates.size();
+    sizes[6] = g_export->relmap_size; sizes[7] = g_export->nlevels;
+    return 0;
+}
+
+// launches[nl*4] = kind, job0, njobs, phase; gemm[ng*8] = a_off,c_off,map_off,lda,ldc,K,nd1,nd2; panel arrays [..*6] = x_off,lda,w,
+// rows_below,col0,snode; steps[ns*5] = launch_begin,launch_end,src,off,cnt; updates[nu*6] = d,s,p0,nd1,nd2,map_off; owner[nsuper]
+extern "C" int ssb200_export_fetch(long long *launches, long long *gemm, long long *potrf, long long *trsm, long long *steps,
+                                   long long *updates, int *owner)
+{
+    if (!g_export) return -4;
+    const ssb::HostPlan &hp = *g_export;
+    for (size_t t = 0; t < hp.launches.size(); t++) { const auto &L = hp.launches[t]; launches[4 * t] = L.kind; launches[4 * t + 1] = L.job0; launches[4 * t + 2] = L.njobs; launches[4 * t + 3] = L.phase; }
+    for (size_t t = 0; t < hp.gemm_jobs.size(); t++) { const auto &g = hp.gemm_jobs[t]; long long *o = gemm + 8 * t; o[0] = g.a_off; o[1] = g.c_off; o[2] = g.map_off; o[3] = g.lda; o[4] = g.ldc; o[5] = g.K; o[6] = g.nd1; o[7] = g.nd2; }
+    auto panel = [](const std::vector<ssb::PanelJob> &v, long long *out) { for (size_t t = 0; t < v.size(); t++) { long long *o = out + 6 * t; o[0] = v[t].x_off; o[1] = v[t].lda; o[2] = v[t].w; o[3] = v[t].rows_below; o[4] = v[t].col0; o[5] = v[t].snode; } };
+    panel(hp.potrf_jobs, potrf); panel(hp.trsm_jobs, trsm);
+    for (size_t t = 0; t < hp.steps.size(); t++) { const auto &st = hp.steps[t]; long long *o = steps + 5 * t; o[0] = st.launch_begin; o[1] = st.launch_end; o[2] = st.bcast_src; o[3] = st.off; o[4] = st.cnt; }
+    for (size_t t = 0; t < hp.updates.size(); t++) { const auto &u = hp.updates[t]; long long *o = updates + 6 * t; o[0] = u.d; o[1] = u.s; o[2] = u.p0; o[3] = u.nd1; o[4] = u.nd2; o[5] = u.map_off; }
+    for (size_t t = 0; t < hp.owner.size(); t++) owner[t] = hp.owner[t];
+    delete g_export; g_export = nullptr;
     return 0;
 }

@@ -1,0 +1,101 @@
+"""Elimination-tree shard of one factorization over several B200s: one process per GPU (torchrun), NCCL over NVLink only
+where the path has a real exchange step — the broadcast of a finished subtree / of a finished 256-column panel of a wide
+top supernode to the ranks whose updates read it.  The schedule (who computes what, and which Lx range is
+broadcast after which step) comes from the C++ plan builder (ssb_plan.cpp); this module only walks it:
+
+    for every step k:   enqueue this rank's kernels of the step;   if the step ends with a broadcast: dist.broadcast(Lx[off:off+cnt], src)
+
+Kernels and collectives share one CUDA stream, so no host synchronisation happens inside a factorization.
+"""
+from __future__ import annotations
+import ctypes as C
+import numpy as np
+from . import plain
+
+c_long = C.c_int64
+
+
+class _DevArray:
+    """__cuda_array_interface__ view of raw device memory, so torch can wrap it without a copy."""
+
+    def __init__(self, ptr: int, count: int):
+        self.__cuda_array_interface__ = {"shape": (count,), "typestr": "<f8", "data": (ptr, False), "version": 2}
+
+
+class ShardedFactor:
+    def __init__(self, n, super_, pi, px, s, device_index: int, rank: int | None = None, world: int | None = None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.rank = dist.get_rank() if rank is None else rank
+        self.world = dist.get_world_size() if world is None else world
+        self.lib = plain._lib()
+        L = self.lib
+        L.ssb200_plan_create_dist.restype = C.c_void_p
+        L.ssb200_plan_create_dist.argtypes = [c_long, c_long, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
+        L.ssb200_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+        L.ssb200_dist_num_steps.restype = c_long; L.ssb200_dist_num_steps.argtypes = [C.c_void_p]
+        L.ssb200_dist_step_info.argtypes = [C.c_void_p, c_long, C.POINTER(C.c_int), C.POINTER(c_long), C.POINTER(c_long)]
+        L.ssb200_dist_begin.argtypes = [C.c_void_p, C.c_void_p]
+        L.ssb200_dist_run_step.argtypes = [C.c_void_p, c_long]
+        L.ssb200_dist_end.argtypes = [C.c_void_p, C.POINTER(c_long)]
+        L.ssb200_dist_zero_from.argtypes = [C.c_void_p, c_long]
+        L.ssb200_dist_flops.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        a = [np.ascontiguousarray(v, dtype=np.int64) for v in (super_, pi, px, s)]
+        self.n = int(n)
+        h = L.ssb200_plan_create_dist(self.n, a[0].size - 1, *[v.ctypes.data_as(C.c_void_p) for v in a], device_index, self.world, self.rank)
+        if not h:
+            raise plain.SsbError(L.ssb200_last_error().decode())
+        self.plan = plain.Plan(self.n, None, None, None, None, handle=h)
+        self.plan.owned = True
+        self.device = torch.device("cuda", device_index)
+        self.stream = torch.cuda.Stream(device=self.device)          # kernels and NCCL broadcasts share this stream
+        L.ssb200_set_stream(self.plan.h, C.c_void_p(self.stream.cuda_stream))
+        self.xsize = self.plan.xsize
+        self.Lx = torch.as_tensor(_DevArray(L.ssb200_device_Lx(self.plan.h), max(self.xsize, 1)), device=self.device)
+        ns = L.ssb200_dist_num_steps(self.plan.h)
+        self.steps = []
+        src, off, cnt = C.c_int(), c_long(), c_long()
+        for k in range(ns):
+            L.ssb200_dist_step_info(self.plan.h, k, C.byref(src), C.byref(off), C.byref(cnt))
+            self.steps.append((src.value, off.value, cnt.value))
+        mine, total = C.c_double(), C.c_double()
+        L.ssb200_dist_flops(self.plan.h, C.byref(mine), C.byref(total))
+        self.my_flops, self.total_flops = mine.value, total.value
+
+    def upload_A(self, A_lower, F=None):
+        return self.plan.upload_A(A_lower, F)
+
+    def factorize_resident(self, beta: float = 0.0):
+        """Returns (status, minor): status 0 ok, 1 not positive definite (every rank gets the same answer)."""
+        torch, dist, L, h = self.torch, self.dist, self.lib, self.plan.h
+        b = (C.c_double * 2)(beta, 0.0)
+        with torch.cuda.stream(self.stream):
+            self.plan._check(L.ssb200_dist_begin(h, b))
+            for k, (src, off, cnt) in enumerate(self.steps):
+                self.plan._check(L.ssb200_dist_run_step(h, k))
+                if src >= 0 and self.world > 1:
+                    dist.broadcast(self.Lx[off:off + cnt], src)
+            bad = c_long(self.n)
+            self.plan._check(L.ssb200_dist_end(h, C.byref(bad)))
+            minor = bad.value
+            if self.world > 1:
+                t = torch.tensor([minor], dtype=torch.int64, device=self.device)
+                dist.all_reduce(t, op=dist.ReduceOp.MIN)
+                minor = int(t.item())
+            if minor < self.n:
+                self.plan._check(L.ssb200_dist_zero_from(h, minor))
+                return 1, minor
+        return 0, self.n
+
+    def download_L(self, out=None):
+        self.stream.synchronize()
+        return self.plan.download_L(out)
+
+    def solve(self, X, which: int = 2):
+        """Every rank holds the complete factor after a factorization, so the solve is local (replicated)."""
+        self.stream.synchronize()
+        return self.plan.solve(X, which)
+
+    def close(self):
+        self.plan.close()

@@ -1,0 +1,99 @@
+"""numpy replay of the host plan (ssb_plan.cpp) — TEST INFRASTRUCTURE.  Executes one rank's launch list job by job on
+the CPU (no tiles, no CUDA), optionally with broadcasts between ranks, so that the update enumeration, the etree shard,
+the panel-cyclic distribution and the step/broadcast order can be checked against the oracle without a GPU."""
+import ctypes as C
+import numpy as np
+from conftest import B200_LIB
+
+L_GEMM_BIG, L_GEMM_SMALL, L_POTRF, L_TRSM, L_TRSM_TC = range(5)
+NB_OUTER = 256
+
+
+def export_plan(n, super_, pi, px, s, nranks=1, rank=0):
+    lib = C.CDLL(B200_LIB)
+    a = [np.ascontiguousarray(v, dtype=np.int64) for v in (super_, pi, px, s)]
+    sizes = np.zeros(8, dtype=np.int64)
+    P = lambda v: v.ctypes.data_as(C.c_void_p)
+    rc = lib.ssb200_export_begin(C.c_int64(n), C.c_int64(len(super_) - 1), *[P(v) for v in a], C.c_int(nranks), C.c_int(rank), P(sizes))
+    assert rc == 0, rc
+    nl, ng, npo, nt, ns, nu = [int(v) for v in sizes[:6]]
+    out = dict(launches=np.zeros((nl, 4), np.int64), gemm=np.zeros((ng, 8), np.int64), potrf=np.zeros((npo, 6), np.int64),
+               trsm=np.zeros((nt, 6), np.int64), steps=np.zeros((ns, 5), np.int64), updates=np.zeros((nu, 6), np.int64),
+               owner=np.zeros(len(super_) - 1, np.int32))
+    rc = lib.ssb200_export_fetch(*[P(out[k]) for k in ("launches", "gemm", "potrf", "trsm", "steps", "updates", "owner")])
+    assert rc == 0
+    out.update(relmap_size=int(sizes[6]), nlevels=int(sizes[7]), nranks=nranks, rank=rank)
+    return out
+
+
+def relmap_of(plan, pi, s):
+    rel = np.zeros(max(plan["relmap_size"], 1), dtype=np.int64)
+    for d, sn, p0, nd1, nd2, moff in plan["updates"]:
+        rows = s[pi[d] + p0: pi[d] + p0 + nd2]
+        tgt = s[pi[sn]: pi[sn + 1]]
+        pos = np.searchsorted(tgt, rows)
+        assert np.all(tgt[pos] == rows)
+        rel[moff: moff + nd2] = pos
+    return rel
+
+
+def assemble(plan, super_, pi, px, s, S_lower, Lx, beta=0.0):
+    """scatter_A_kernel with the ownership rule of the shard."""
+    nsuper = len(super_) - 1
+    Sp, Si, Sx = S_lower.indptr, S_lower.indices, S_lower.data
+    for sn in range(nsuper):
+        k1, k2 = int(super_[sn]), int(super_[sn + 1])
+        rows = s[pi[sn]: pi[sn + 1]]; nsrow = len(rows)
+        for k in range(k1, k2):
+            o = plan["owner"][sn]
+            if plan["nranks"] > 1 and (o != plan["rank"] if o >= 0 else ((k - k1) // NB_OUTER) % plan["nranks"] != plan["rank"]):
+                continue
+            for p in range(Sp[k], Sp[k + 1]):
+                i = Si[p]
+                if i >= k:
+                    pos = np.searchsorted(rows, i)
+                    if pos < nsrow and rows[pos] == i:
+                        Lx[px[sn] + pos + (k - k1) * nsrow] = Sx[p]
+            if beta:
+                Lx[px[sn] + (k - k1) * (nsrow + 1)] += beta
+
+
+def run_launches(plan, rel, Lx, lo, hi):
+    for kind, job0, njobs, _ in plan["launches"][lo:hi]:
+        if kind in (L_GEMM_BIG, L_GEMM_SMALL):
+            for a_off, c_off, moff, lda, ldc, K, nd1, nd2 in plan["gemm"][job0: job0 + njobs]:
+                idx = a_off + np.arange(nd2)[:, None] + np.arange(K)[None, :] * lda
+                Pm = Lx[idx]
+                Cm = Pm @ Pm[:nd1].T
+                ii, jj = np.nonzero(np.arange(nd2)[:, None] >= np.arange(nd1)[None, :])
+                if moff >= 0:
+                    tgt = c_off + rel[moff + ii] + rel[moff + jj] * ldc
+                else:
+                    tgt = c_off + ii + jj * ldc
+                np.subtract.at(Lx, tgt, Cm[ii, jj])
+        elif kind == L_POTRF:
+            for x_off, lda, w, rows_below, col0, snode in plan["potrf"][job0: job0 + njobs]:
+                idx = x_off + np.arange(w)[:, None] + np.arange(w)[None, :] * lda
+                Bm = np.tril(Lx[idx]); Bm = Bm + np.tril(Bm, -1).T
+                Lc = np.linalg.cholesky(Bm)
+                ii, jj = np.tril_indices(w)
+                Lx[idx[ii, jj]] = Lc[ii, jj]
+        else:
+            for x_off, lda, w, rows_below, col0, snode in plan["trsm"][job0: job0 + njobs]:
+                idx = x_off + np.arange(w)[:, None] + np.arange(w)[None, :] * lda
+                L11 = np.tril(Lx[idx])
+                bidx = x_off + w + np.arange(rows_below)[:, None] + np.arange(w)[None, :] * lda
+                Lx[bidx] = np.linalg.solve(L11, Lx[bidx].T).T
+
+
+def factorize_emulated(n, super_, pi, px, s, S_lower, nranks=1, rank=0, bcast=None, beta=0.0):
+    """bcast(buf_view, src) replicates a finished Lx range (None for a single rank)."""
+    plan = export_plan(n, super_, pi, px, s, nranks, rank)
+    rel = relmap_of(plan, pi, s)
+    Lx = np.zeros(int(px[-1]))
+    assemble(plan, super_, pi, px, s, S_lower, Lx, beta)
+    for lo, hi, src, off, cnt in plan["steps"]:
+        run_launches(plan, rel, Lx, lo, hi)
+        if src >= 0 and bcast is not None:
+            bcast(Lx[off: off + cnt], int(src))
+    return Lx, plan
