@@ -192,16 +192,19 @@ void ssb200_plan_destroy(ssb200_plan *plan);
  * are shared panel-cyclically (256-column panels).  Every rank keeps the whole Lx array; a finished subtree / panel is
  * replicated by ONE broadcast of a contiguous Lx range, issued by the caller (torch.distributed / NCCL) between steps:
  *     ssb200_upload_A(); ssb200_dist_begin();
- *     for k < ssb200_dist_num_steps(): ssb200_dist_run_step(k); ssb200_dist_step_info(k,&src,&off,&cnt); if (src>=0) broadcast(Lx+off, cnt, src);
+ *     for k < ssb200_dist_num_steps():  ssb200_dist_step_info(k,&src,&off,&cnt,&wait);
+ *         if (wait) wait for every broadcast started so far;   ssb200_dist_run_step(k, 0);
+ *         if (src >= 0) start broadcast(Lx+off, cnt, src) asynchronously, ordered after the launches above;
+ *         ssb200_dist_run_step(k, 1);          // look-ahead work that overlaps the broadcast
  *     ssb200_dist_end(&bad);  minor = min over ranks of bad;  if (minor < n) ssb200_dist_zero_from(minor);
- * All kernels and the broadcasts must share one stream: ssb200_set_stream(plan, cudaStream_t). */
+ * Kernels go to the stream given by ssb200_set_stream(plan, cudaStream_t); the caller orders its broadcasts against it. */
 ssb200_plan *ssb200_plan_create_dist(ssb_long n, ssb_long nsuper, const ssb_long *super, const ssb_long *pi,
                                      const ssb_long *px, const ssb_long *s, int device, int nranks, int rank);
 int      ssb200_set_stream(ssb200_plan *plan, void *cuda_stream);      /* NULL: back to the plan's own stream */
 ssb_long ssb200_dist_num_steps(const ssb200_plan *plan);
-int      ssb200_dist_step_info(const ssb200_plan *plan, ssb_long k, int *src, ssb_long *off, ssb_long *cnt);
+int      ssb200_dist_step_info(const ssb200_plan *plan, ssb_long k, int *src, ssb_long *off, ssb_long *cnt, int *wait_remote);
 int      ssb200_dist_begin(ssb200_plan *plan, const double beta[2]);
-int      ssb200_dist_run_step(ssb200_plan *plan, ssb_long k);
+int      ssb200_dist_run_step(ssb200_plan *plan, ssb_long k, int part);
 int      ssb200_dist_end(ssb200_plan *plan, ssb_long *first_bad_column);
 int      ssb200_dist_zero_from(ssb200_plan *plan, ssb_long column);
 int      ssb200_dist_flops(const ssb200_plan *plan, double *mine, double *total);

@@ -8,7 +8,8 @@ from suitesparse_b200.dist import ShardedFactor
 
 rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); local = int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
-dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)     # broadcasts must preempt queued GEMM tiles
+dist.init_process_group("nccl", device_id=torch.device("cuda", local), pg_options=opts)
 kind, N = sys.argv[1], int(sys.argv[2]); reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 ch = Cholmod(gpu=True)
 A, p = gen.make_problem(kind, N)
@@ -34,6 +35,29 @@ for it in range(reps):
     torch.cuda.synchronize()
     t = torch.tensor([e0.elapsed_time(e1)], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX)
     times.append(t.item())
+    if it == reps - 1 and sf.phase_event is not None:
+        print(f"[rank {rank}] total {e0.elapsed_time(e1):.1f} ms, subtree phase {e0.elapsed_time(sf.phase_event):.1f} ms, top phase {sf.phase_event.elapsed_time(e1):.1f} ms", flush=True)
+if os.environ.get("SSB200_DIST_STEPTIME"):
+    ev_full = sf.step_events
+    dt_full = np.array([ev_full[k].elapsed_time(ev_full[k + 1]) for k in range(len(ev_full) - 1)])
+    os.environ["SSB200_DIST_DEBUG"] = "nocomm"
+    sf.factorize_resident(); torch.cuda.synchronize()
+    ev_nc = sf.step_events
+    dt_nc = np.array([ev_nc[k].elapsed_time(ev_nc[k + 1]) for k in range(len(ev_nc) - 1)])
+    os.environ["SSB200_DIST_DEBUG"] = ""
+    if rank == 0:
+        st = np.array(sf.steps)
+        cyc = (st[:, 3] == 1)
+        print("steps", len(st), "sum full %.1f nocomm %.1f" % (dt_full.sum(), dt_nc.sum()))
+        # group: consecutive runs of wait_remote steps by size of bcast
+        big = np.argsort(dt_full - dt_nc)[::-1][:25]
+        for k in sorted(big):
+            print("  step %4d src %2d cnt %10d wait %d  full %.3f ms  nocomm %.3f ms" % (k, st[k, 0], st[k, 2], st[k, 3], dt_full[k], dt_nc[k]))
+        lo = int(np.argmax(cyc)) if cyc.any() else len(st)
+        print("subtree part: full %.1f nocomm %.1f | top part: full %.1f nocomm %.1f" % (dt_full[:lo].sum(), dt_nc[:lo].sum(), dt_full[lo:].sum(), dt_nc[lo:].sum()))
+        # top part by bcast size class
+        for name, sel in (("panel steps cnt<2e6", (st[:, 2] < 2e6) & cyc), ("2e6..5e6", (st[:, 2] >= 2e6) & (st[:, 2] < 5e6) & cyc), (">=5e6", (st[:, 2] >= 5e6) & cyc)):
+            print("  %-22s n=%4d full %.1f nocomm %.1f" % (name, sel.sum(), dt_full[sel].sum(), dt_nc[sel].sum()))
 fl = ch.cm.fl
 if rank == 0:
     print(f"{kind}{N} world={world} status={st} minor={minor} ms={['%.1f' % v for v in times]} best GF/s={fl / min(times) / 1e6:.1f}", flush=True)

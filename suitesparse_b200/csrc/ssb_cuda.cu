@@ -231,12 +231,13 @@ extern "C" int ssb200_set_stream(ssb200_plan *p, void *stream)
 
 extern "C" ssb_long ssb200_dist_num_steps(const ssb200_plan *p) { return p ? (ssb_long) p->hp.steps.size() : 0; }
 
-// step k: *src = broadcasting rank (-1: none), [*off, *off+*cnt) = the Lx range that is final on src after the step's launches
-extern "C" int ssb200_dist_step_info(const ssb200_plan *p, ssb_long k, int *src, ssb_long *off, ssb_long *cnt)
+// step k: *src = broadcasting rank (-1: none), [*off, *off+*cnt) = the Lx range that is final on src after part 0 of the
+// step's launches; *wait_remote != 0: every broadcast started earlier must have landed before the step's launches run
+extern "C" int ssb200_dist_step_info(const ssb200_plan *p, ssb_long k, int *src, ssb_long *off, ssb_long *cnt, int *wait_remote)
 {
     if (!p || k < 0 || k >= (ssb_long) p->hp.steps.size()) return SSB_CHOLMOD_INVALID;
     const DistStep &st = p->hp.steps[k];
-    *src = st.bcast_src; *off = st.off; *cnt = st.cnt;
+    *src = st.bcast_src; *off = st.off; *cnt = st.cnt; *wait_remote = st.wait_remote;
     return 0;
 }
 
@@ -257,11 +258,13 @@ extern "C" int ssb200_dist_begin(ssb200_plan *p, const double beta[2])
     return scatter_A(p, beta ? beta[0] : 0.0, 0, hp.n);
 }
 
-extern "C" int ssb200_dist_run_step(ssb200_plan *p, ssb_long k)
+// part 0: the launches before the step's broadcast starts; part 1: the look-ahead launches that overlap it
+extern "C" int ssb200_dist_run_step(ssb200_plan *p, ssb_long k, int part)
 {
     if (!p || k < 0 || k >= (ssb_long) p->hp.steps.size()) return SSB_CHOLMOD_INVALID;
     const DistStep &st = p->hp.steps[k];
-    for (int t = st.launch_begin; t < st.launch_end; t++)
+    const int lo = part == 0 ? st.launch_begin : st.launch_mid, hi = part == 0 ? st.launch_mid : st.launch_end;
+    for (int t = lo; t < hi; t++)
         if (run_launch(p, p->hp.launches[t], p->jobs)) return SSB_CHOLMOD_GPU_PROBLEM;
     CU_TRY(cudaGetLastError());
     return 0;

@@ -74,7 +74,11 @@ struct CopyTask { int after_launch; long long off, cnt; };
 constexpr int COPY_FLUSH_LEVEL = 8;  // supernodes up to this etree level are copied in merged ranges after that level
 
 // One step of the distributed schedule.  Every rank walks the same step list (same broadcasts); only the launches differ.
-struct DistStep { int launch_begin, launch_end; int bcast_src; long long off, cnt; };
+//   [wait for every outstanding broadcast, if wait_remote]  launches [begin, mid)  [start the broadcast, asynchronously]
+//   launches [mid, end)
+// The post-range is the look-ahead: work that does not depend on the broadcast just started (trailing updates with the
+// previous panel) runs while the next panel travels.
+struct DistStep { int launch_begin, launch_mid, launch_end; int bcast_src; long long off, cnt; int wait_remote; };
 
 struct Update { int d, s; int p0, nd1, nd2; long long map_off; };
 

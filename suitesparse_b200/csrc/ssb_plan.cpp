@@ -271,21 +271,39 @@ bool build_host_plan(long long n, long long nsuper, const long long *super, cons
             load[q] += sub[r];
             for (int t = first_desc[r]; t <= r; t++) hp.owner[t] = q;
         }
-        // supernodes above the cut: wide ones are shared panel-cyclically, narrow ones go to the least loaded rank
-        for (int t = 0; t < (int) nsuper; t++) {
-            if (!in_top[t]) continue;
-            const int nscol = hp.super[t + 1] - hp.super[t];
-            if (nscol >= 2 * NB_OUTER) { hp.owner[t] = -1; for (auto &v : load) v += sn_flops[t] / hp.nranks; }
-            else { const int q = (int) (std::min_element(load.begin(), load.end()) - load.begin()); load[q] += sn_flops[t]; hp.owner[t] = q; }
+        // Supernodes above the cut.  Only a supernode whose own work would unbalance the ranks (more than half of one
+        // rank's fair share) is shared panel-cyclically: a panel step costs a serial panel factorization plus a broadcast
+        // (~0.7 ms), which only pays when the trailing update per panel is large.  The others are whole-owned; the top
+        // supernodes of one etree level run side by side on different ranks (LPT inside the level, on top of the ranks'
+        // subtree loads only for tie-breaking).
+        std::vector<std::vector<int>> top_by_level(hp.nlevels);
+        for (int t = 0; t < (int) nsuper; t++) if (in_top[t]) top_by_level[hp.level[t]].push_back(t);
+        for (int l = 0; l < hp.nlevels; l++) {
+            auto &v = top_by_level[l];
+            std::sort(v.begin(), v.end(), [&](int a, int b) { return sn_flops[a] > sn_flops[b] || (sn_flops[a] == sn_flops[b] && a < b); });
+            std::vector<double> lvl(hp.nranks, 0.0);
+            for (int t : v) {
+                const int nscol = hp.super[t + 1] - hp.super[t];
+                if (nscol >= 2 * NB_OUTER && sn_flops[t] > 0.5 * total / hp.nranks) { hp.owner[t] = -1; continue; }
+                int q = 0;
+                for (int r = 1; r < hp.nranks; r++) if (lvl[r] < lvl[q] || (lvl[r] == lvl[q] && load[r] < load[q])) q = r;
+                lvl[q] += sn_flops[t]; load[q] += sn_flops[t]; hp.owner[t] = q;
+            }
         }
         // subtree roots / narrow top supernodes: their finished Lx ranges are broadcast after their level
         for (int r : cand) first_desc[r] = -1 - first_desc[r];     // mark: negative = broadcast root, range starts at -1-value
         for (int t = 0; t < (int) nsuper; t++) if (in_top[t] && hp.owner[t] >= 0) first_desc[t] = -1 - t;
     }
     auto mine_whole = [&](int sn) { return hp.owner[sn] == hp.rank; };
-    auto close_step = [&](int &step_begin, int src, long long off, long long cnt) {
-        hp.steps.push_back(DistStep{step_begin, (int) hp.launches.size(), src, off, cnt});
-        step_begin = (int) hp.launches.size();
+    // lowest etree level that holds a supernode above the subtree cut: from there on a step may read remote data
+    int top_min_level = hp.nlevels;
+    if (hp.nranks > 1)
+        for (int t = 0; t < (int) nsuper; t++) if (hp.owner[t] < 0 || first_desc[t] == -1 - t) top_min_level = std::min(top_min_level, hp.level[t]);
+    int step_mid = -1;                                  // >= 0: launch index where the current step's post-range starts
+    auto close_step = [&](int &step_begin, int src, long long off, long long cnt, int level) {
+        const int end = (int) hp.launches.size();
+        hp.steps.push_back(DistStep{step_begin, step_mid >= 0 ? step_mid : end, end, src, off, cnt, level >= top_min_level ? 1 : 0});
+        step_begin = end; step_mid = -1;
     };
     // ---- per level launches ----------------------------------------------------------------------------------
     hp.level_launch_begin.assign(hp.nlevels + 1, 0);
@@ -364,34 +382,42 @@ bool build_host_plan(long long n, long long nsuper, const long long *super, cons
             }
         }
         if (hp.nranks > 1) {
-            // panel-cyclic supernodes of this level: owner factorizes a 256-column panel, broadcasts it, everybody updates
-            // the panels it owns
+            // panel-cyclic supernodes of this level, with a look-ahead of one panel: the owner of panel J+1 first brings that
+            // panel up to date with panel J and factorizes it, the broadcast of panel J+1 starts, and only then everybody
+            // runs the rest of the trailing update with panel J (which overlaps the broadcast).
             for (int t = hp.level_ptr[l]; t < hp.level_ptr[l + 1]; t++) {
                 const int sn = hp.level_nodes[t];
                 if (hp.owner[sn] >= 0) continue;
                 const int nscol = hp.super[sn + 1] - hp.super[sn];
                 const long long nsrow = hp.pi[sn + 1] - hp.pi[sn];
+                const int npan = (nscol + NB_OUTER - 1) / NB_OUTER;
                 std::vector<int> one{sn};
-                for (int J0 = 0; J0 < nscol; J0 += NB_OUTER) {
-                    const int W = std::min(NB_OUTER, nscol - J0);
-                    const int src = (J0 / NB_OUTER) % hp.nranks;
-                    if (src == hp.rank) {
-                        append_factor_jobs(hp, one, -1, hp, false, J0);
-                        hp.my_flops += (double) W * W * W / 3.0 + (double) W * W * (nsrow - J0 - W);
-                    }
-                    close_step(step_begin, src, hp.px[sn] + (long long) J0 * nsrow, (long long) W * nsrow);
-                    // trailing update of the panels this rank owns
-                    for (int J1 = J0 + NB_OUTER; J1 < nscol; J1 += NB_OUTER) {
-                        if ((J1 / NB_OUTER) % hp.nranks != hp.rank) continue;
-                        const int W1 = std::min(NB_OUTER, nscol - J1);
-                        GemmJob g{};
-                        g.a_off = hp.px[sn] + J1 + (long long) J0 * nsrow;
-                        g.c_off = hp.px[sn] + J1 + (long long) J1 * nsrow;
-                        g.map_off = -1; g.lda = (int) nsrow; g.ldc = (int) nsrow; g.K = W; g.nd1 = W1; g.nd2 = (int) (nsrow - J1); g.atomic = 1;
-                        hp.my_flops += 2.0 * W * ((double) g.nd1 * g.nd2 - 0.5 * (double) g.nd1 * (g.nd1 - 1));
-                        route_gemm(g, gs, gb);
-                    }
+                auto panel_w = [&](int J) { return std::min(NB_OUTER, nscol - J * NB_OUTER); };
+                auto factor_panel = [&](int J) {
+                    const int J0 = J * NB_OUTER, W = panel_w(J);
+                    append_factor_jobs(hp, one, -1, hp, false, J0);
+                    hp.my_flops += (double) W * W * W / 3.0 + (double) W * W * (nsrow - J0 - W);
+                };
+                auto update_block = [&](int J, int J1) {       // block J1 -= panel J contribution
+                    const int J0 = J * NB_OUTER, C0 = J1 * NB_OUTER, W = panel_w(J), W1 = panel_w(J1);
+                    GemmJob g{};
+                    g.a_off = hp.px[sn] + C0 + (long long) J0 * nsrow;
+                    g.c_off = hp.px[sn] + C0 + (long long) C0 * nsrow;
+                    g.map_off = -1; g.lda = (int) nsrow; g.ldc = (int) nsrow; g.K = W; g.nd1 = W1; g.nd2 = (int) (nsrow - C0); g.atomic = 1;
+                    hp.my_flops += 2.0 * W * ((double) g.nd1 * g.nd2 - 0.5 * (double) g.nd1 * (g.nd1 - 1));
+                    route_gemm(g, gs, gb);
+                };
+                // prologue: panel 0
+                if (0 % hp.nranks == hp.rank) factor_panel(0);
+                close_step(step_begin, 0, hp.px[sn], (long long) panel_w(0) * nsrow, l);
+                for (int J = 0; J < npan; J++) {
+                    const bool own_next = (J + 1 < npan) && ((J + 1) % hp.nranks == hp.rank);
+                    if (own_next) { update_block(J, J + 1); emit_update_launches(hp, gs, gb, 1); factor_panel(J + 1); }
+                    step_mid = (int) hp.launches.size();
+                    for (int J1 = J + 2; J1 < npan; J1++) if (J1 % hp.nranks == hp.rank) update_block(J, J1);
                     emit_update_launches(hp, gs, gb, 1);
+                    if (J + 1 < npan) close_step(step_begin, (J + 1) % hp.nranks, hp.px[sn] + (long long) (J + 1) * NB_OUTER * nsrow, (long long) panel_w(J + 1) * nsrow, l);
+                    else close_step(step_begin, -1, 0, 0, l);
                 }
             }
             // finished subtrees / narrow top supernodes of this level: replicate them
@@ -399,12 +425,12 @@ bool build_host_plan(long long n, long long nsuper, const long long *super, cons
                 const int sn = hp.level_nodes[t];
                 if (first_desc[sn] >= 0 || hp.owner[sn] < 0) continue;
                 const int lo = -1 - first_desc[sn];
-                close_step(step_begin, hp.owner[sn], hp.px[lo], hp.px[sn + 1] - hp.px[lo]);
+                close_step(step_begin, hp.owner[sn], hp.px[lo], hp.px[sn + 1] - hp.px[lo], l);
             }
         }
     }
     hp.level_launch_begin[hp.nlevels] = (int) hp.launches.size();
-    close_step(step_begin, -1, 0, 0);
+    close_step(step_begin, -1, 0, 0, hp.nlevels);
     if (hp.nranks == 1) hp.my_flops = hp.flops_update + hp.flops_potrf + hp.flops_trsm;
     // ---- solve schedule: per level, per 64-column block index ------------------------------------------------
     for (int l = 0; l < hp.nlevels; l++) {
@@ -475,7 +501,7 @@ extern "C" int ssb200_export_begin(long long n, long long nsuper, const long lon
 }
 
 // launches[nl*4] = kind, job0, njobs, phase; gemm[ng*8] = a_off,c_off,map_off,lda,ldc,K,nd1,nd2; panel arrays [..*6] = x_off,lda,w,
-// rows_below,col0,snode; steps[ns*5] = launch_begin,launch_end,src,off,cnt; updates[nu*6] = d,s,p0,nd1,nd2,map_off; owner[nsuper]
+// rows_below,col0,snode; steps[ns*7] = launch_begin,launch_mid,launch_end,src,off,cnt,wait_remote; updates[nu*6] = d,s,p0,nd1,nd2,map_off; owner[nsuper]
 extern "C" int ssb200_export_fetch(long long *launches, long long *gemm, long long *potrf, long long *trsm, long long *steps,
                                    long long *updates, int *owner)
 {
@@ -485,7 +511,7 @@ extern "C" int ssb200_export_fetch(long long *launches, long long *gemm, long lo
     for (size_t t = 0; t < hp.gemm_jobs.size(); t++) { const auto &g = hp.gemm_jobs[t]; long long *o = gemm + 8 * t; o[0] = g.a_off; o[1] = g.c_off; o[2] = g.map_off; o[3] = g.lda; o[4] = g.ldc; o[5] = g.K; o[6] = g.nd1; o[7] = g.nd2; }
     auto panel = [](const std::vector<ssb::PanelJob> &v, long long *out) { for (size_t t = 0; t < v.size(); t++) { long long *o = out + 6 * t; o[0] = v[t].x_off; o[1] = v[t].lda; o[2] = v[t].w; o[3] = v[t].rows_below; o[4] = v[t].col0; o[5] = v[t].snode; } };
     panel(hp.potrf_jobs, potrf); panel(hp.trsm_jobs, trsm);
-    for (size_t t = 0; t < hp.steps.size(); t++) { const auto &st = hp.steps[t]; long long *o = steps + 5 * t; o[0] = st.launch_begin; o[1] = st.launch_end; o[2] = st.bcast_src; o[3] = st.off; o[4] = st.cnt; }
+    for (size_t t = 0; t < hp.steps.size(); t++) { const auto &st = hp.steps[t]; long long *o = steps + 7 * t; o[0] = st.launch_begin; o[1] = st.launch_mid; o[2] = st.launch_end; o[3] = st.bcast_src; o[4] = st.off; o[5] = st.cnt; o[6] = st.wait_remote; }
     for (size_t t = 0; t < hp.updates.size(); t++) { const auto &u = hp.updates[t]; long long *o = updates + 6 * t; o[0] = u.d; o[1] = u.s; o[2] = u.p0; o[3] = u.nd1; o[4] = u.nd2; o[5] = u.map_off; }
     for (size_t t = 0; t < hp.owner.size(); t++) owner[t] = hp.owner[t];
     delete g_export; g_export = nullptr;

@@ -35,9 +35,9 @@ class ShardedFactor:
         L.ssb200_plan_create_dist.argtypes = [c_long, c_long, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
         L.ssb200_set_stream.argtypes = [C.c_void_p, C.c_void_p]
         L.ssb200_dist_num_steps.restype = c_long; L.ssb200_dist_num_steps.argtypes = [C.c_void_p]
-        L.ssb200_dist_step_info.argtypes = [C.c_void_p, c_long, C.POINTER(C.c_int), C.POINTER(c_long), C.POINTER(c_long)]
+        L.ssb200_dist_step_info.argtypes = [C.c_void_p, c_long, C.POINTER(C.c_int), C.POINTER(c_long), C.POINTER(c_long), C.POINTER(C.c_int)]
         L.ssb200_dist_begin.argtypes = [C.c_void_p, C.c_void_p]
-        L.ssb200_dist_run_step.argtypes = [C.c_void_p, c_long]
+        L.ssb200_dist_run_step.argtypes = [C.c_void_p, c_long, C.c_int]
         L.ssb200_dist_end.argtypes = [C.c_void_p, C.POINTER(c_long)]
         L.ssb200_dist_zero_from.argtypes = [C.c_void_p, c_long]
         L.ssb200_dist_flops.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
@@ -52,13 +52,15 @@ class ShardedFactor:
         self.stream = torch.cuda.Stream(device=self.device)          # kernels and NCCL broadcasts share this stream
         L.ssb200_set_stream(self.plan.h, C.c_void_p(self.stream.cuda_stream))
         self.xsize = self.plan.xsize
+        self._copy_stream = None
         self.Lx = torch.as_tensor(_DevArray(L.ssb200_device_Lx(self.plan.h), max(self.xsize, 1)), device=self.device)
         ns = L.ssb200_dist_num_steps(self.plan.h)
         self.steps = []
-        src, off, cnt = C.c_int(), c_long(), c_long()
+        src, off, cnt, wt = C.c_int(), c_long(), c_long(), C.c_int()
         for k in range(ns):
-            L.ssb200_dist_step_info(self.plan.h, k, C.byref(src), C.byref(off), C.byref(cnt))
-            self.steps.append((src.value, off.value, cnt.value))
+            L.ssb200_dist_step_info(self.plan.h, k, C.byref(src), C.byref(off), C.byref(cnt), C.byref(wt))
+            self.steps.append((src.value, off.value, cnt.value, wt.value))
+        self.comm_stream = torch.cuda.Stream(device=self.device)     # broadcasts are issued here so they overlap the look-ahead work
         mine, total = C.c_double(), C.c_double()
         L.ssb200_dist_flops(self.plan.h, C.byref(mine), C.byref(total))
         self.my_flops, self.total_flops = mine.value, total.value
@@ -66,16 +68,53 @@ class ShardedFactor:
     def upload_A(self, A_lower, F=None):
         return self.plan.upload_A(A_lower, F)
 
-    def factorize_resident(self, beta: float = 0.0):
-        """Returns (status, minor): status 0 ok, 1 not positive definite (every rank gets the same answer)."""
+    def factorize_resident(self, beta: float = 0.0, host_out=None):
+        """Returns (status, minor): status 0 ok, 1 not positive definite (every rank gets the same answer).
+        host_out: pinned host tensor of xsize doubles (or None).  A range of L is final on every rank right after its
+        broadcast, so it is copied to host_out on a second stream while the factorization continues."""
         torch, dist, L, h = self.torch, self.dist, self.lib, self.plan.h
         b = (C.c_double * 2)(beta, 0.0)
+        if host_out is not None and self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        import os
+        dbg = os.environ.get("SSB200_DIST_DEBUG", "")      # "nocomm" / "nocompute": timing experiments only (wrong factor)
+        do_comm, do_compute = dbg != "nocomm", dbg != "nocompute"
+        self.phase_event = None
+        self.step_events = [] if dbg or os.environ.get("SSB200_DIST_STEPTIME") else None
         with torch.cuda.stream(self.stream):
             self.plan._check(L.ssb200_dist_begin(h, b))
-            for k, (src, off, cnt) in enumerate(self.steps):
-                self.plan._check(L.ssb200_dist_run_step(h, k))
-                if src >= 0 and self.world > 1:
-                    dist.broadcast(self.Lx[off:off + cnt], src)
+            pending = []                                  # broadcasts in flight: (work, off, cnt)
+            for k, (src, off, cnt, wait_remote) in enumerate(self.steps):
+                if self.step_events is not None:
+                    ev = torch.cuda.Event(enable_timing=True); ev.record(); self.step_events.append(ev)
+                if wait_remote and self.phase_event is None:
+                    self.phase_event = torch.cuda.Event(enable_timing=True); self.phase_event.record()   # subtree phase ends here
+                if wait_remote and pending:
+                    for w, _, _ in pending:
+                        w.wait()                          # stream-level: self.stream waits for the NCCL stream
+                    pending = []
+                if do_compute:
+                    self.plan._check(L.ssb200_dist_run_step(h, k, 0))
+                if src >= 0:
+                    if self.world > 1 and do_comm:
+                        self.comm_stream.wait_stream(self.stream)
+                        with torch.cuda.stream(self.comm_stream):
+                            w = dist.broadcast(self.Lx[off:off + cnt], src, async_op=True)
+                        pending.append((w, off, cnt))
+                    if host_out is not None:
+                        # the range is final everywhere once its broadcast has landed: stream it to the host
+                        with torch.cuda.stream(self._copy_stream):
+                            if self.world > 1 and do_comm:
+                                w.wait()
+                            else:
+                                self._copy_stream.wait_stream(self.stream)
+                            host_out[off:off + cnt].copy_(self.Lx[off:off + cnt], non_blocking=True)
+                if do_compute:
+                    self.plan._check(L.ssb200_dist_run_step(h, k, 1))
+            for w, _, _ in pending:
+                w.wait()
+            if self.step_events is not None:
+                ev = torch.cuda.Event(enable_timing=True); ev.record(); self.step_events.append(ev)
             bad = c_long(self.n)
             self.plan._check(L.ssb200_dist_end(h, C.byref(bad)))
             minor = bad.value
@@ -85,7 +124,12 @@ class ShardedFactor:
                 minor = int(t.item())
             if minor < self.n:
                 self.plan._check(L.ssb200_dist_zero_from(h, minor))
+                if host_out is not None:
+                    self._copy_stream.synchronize()
+                    host_out.copy_(self.Lx[:self.xsize])
                 return 1, minor
+        if host_out is not None:
+            self._copy_stream.synchronize()
         return 0, self.n
 
     def download_L(self, out=None):

@@ -18,7 +18,7 @@ def export_plan(n, super_, pi, px, s, nranks=1, rank=0):
     assert rc == 0, rc
     nl, ng, npo, nt, ns, nu = [int(v) for v in sizes[:6]]
     out = dict(launches=np.zeros((nl, 4), np.int64), gemm=np.zeros((ng, 8), np.int64), potrf=np.zeros((npo, 6), np.int64),
-               trsm=np.zeros((nt, 6), np.int64), steps=np.zeros((ns, 5), np.int64), updates=np.zeros((nu, 6), np.int64),
+               trsm=np.zeros((nt, 6), np.int64), steps=np.zeros((ns, 7), np.int64), updates=np.zeros((nu, 6), np.int64),
                owner=np.zeros(len(super_) - 1, np.int32))
     rc = lib.ssb200_export_fetch(*[P(out[k]) for k in ("launches", "gemm", "potrf", "trsm", "steps", "updates", "owner")])
     assert rc == 0
@@ -92,8 +92,41 @@ def factorize_emulated(n, super_, pi, px, s, S_lower, nranks=1, rank=0, bcast=No
     rel = relmap_of(plan, pi, s)
     Lx = np.zeros(int(px[-1]))
     assemble(plan, super_, pi, px, s, S_lower, Lx, beta)
-    for lo, hi, src, off, cnt in plan["steps"]:
-        run_launches(plan, rel, Lx, lo, hi)
+    for lo, mid, hi, src, off, cnt, wait in plan["steps"]:
+        run_launches(plan, rel, Lx, lo, mid)
         if src >= 0 and bcast is not None:
-            bcast(Lx[off: off + cnt], int(src))
+            bcast(Lx[off: off + cnt], int(src))          # synchronous here; the lock-step test models the asynchrony
+        run_launches(plan, rel, Lx, mid, hi)
     return Lx, plan
+
+
+def run_lockstep(plans, rel, Lx):
+    """All ranks in one process, with ASYNCHRONOUS broadcast semantics: a broadcast is snapshotted when it starts and
+    only delivered when a later step declares wait_remote (or at the end) — reading remote data too early shows up as a
+    wrong factor.  Returns the number of doubles broadcast."""
+    nr = len(plans)
+    pending, total = [], 0
+    for k in range(len(plans[0]["steps"])):
+        infos = set()
+        if plans[0]["steps"][k][6]:
+            for src, off, data in pending:
+                for r in range(nr):
+                    if r != src:
+                        Lx[r][off: off + len(data)] = data
+            pending = []
+        for r in range(nr):
+            lo, mid, hi, src, off, cnt, wait = plans[r]["steps"][k]
+            run_launches(plans[r], rel, Lx[r], lo, mid)
+            infos.add((int(src), int(off), int(cnt), int(wait)))
+        assert len(infos) == 1, infos                      # every rank issues the same collective
+        src, off, cnt, wait = infos.pop()
+        if src >= 0:
+            pending.append((src, off, Lx[src][off: off + cnt].copy())); total += cnt
+        for r in range(nr):
+            lo, mid, hi = plans[r]["steps"][k][:3]
+            run_launches(plans[r], rel, Lx[r], mid, hi)
+    for src, off, data in pending:
+        for r in range(nr):
+            if r != src:
+                Lx[r][off: off + len(data)] = data
+    return total

@@ -25,7 +25,7 @@ def _worker(rank, world, port, name, q):
 
     Lx, plan = E.factorize_emulated(int(g["n"]), g["super"], g["pi"], g["px"], g["s"], S, nranks=world, rank=rank, bcast=bcast)
     err = persuper_relerr(g["px"], Lx, g["Lx"])
-    nb = sum(1 for st in plan["steps"] if st[2] >= 0)
+    nb = sum(1 for st in plan["steps"] if st[3] >= 0)
     mine = int((plan["owner"] == rank).sum())
     q.put((rank, err, nb, mine, int((plan["owner"] < 0).sum())))
     dist.barrier(); dist.destroy_process_group()
@@ -76,20 +76,7 @@ def test_sharded_schedule_with_cyclic_supernode_single_process():
     Lx = [np.zeros(int(f["px"][-1])) for _ in range(nr)]
     for r in range(nr):
         E.assemble(plans[r], f["super"], f["pi"], f["px"], f["s"], Sl, Lx[r])
-    nbytes = 0
-    for k in range(len(plans[0]["steps"])):
-        infos = set()
-        for r in range(nr):
-            lo, hi, src, off, cnt = plans[r]["steps"][k]
-            E.run_launches(plans[r], rel, Lx[r], lo, hi)
-            infos.add((int(src), int(off), int(cnt)))
-        assert len(infos) == 1                                     # every rank issues the same collective
-        src, off, cnt = infos.pop()
-        if src >= 0:
-            nbytes += cnt
-            for r in range(nr):
-                if r != src:
-                    Lx[r][off:off + cnt] = Lx[src][off:off + cnt]
+    nbytes = E.run_lockstep(plans, rel, Lx)
     assert nbytes == int(f["px"][-1])                              # all of L replicated exactly once
     for r in range(nr):
         assert persuper_relerr(f["px"], Lx[r], Lo) < 1e-11
