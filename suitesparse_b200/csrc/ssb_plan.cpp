@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <numeric>
 #include <cstring>
+#include <cstdlib>
 
 namespace ssb {
 
@@ -271,23 +272,52 @@ bool build_host_plan(long long n, long long nsuper, const long long *super, cons
             load[q] += sub[r];
             for (int t = first_desc[r]; t <= r; t++) hp.owner[t] = q;
         }
-        // Supernodes above the cut.  Only a supernode whose own work would unbalance the ranks (more than half of one
-        // rank's fair share) is shared panel-cyclically: a panel step costs a serial panel factorization plus a broadcast
-        // (~0.7 ms), which only pays when the trailing update per panel is large.  The others are whole-owned; the top
-        // supernodes of one etree level run side by side on different ranks (LPT inside the level, on top of the ranks'
-        // subtree loads only for tie-breaking).
+        // Supernodes above the cut, level by level (a level is a barrier: its supernodes read the lower levels).  A top
+        // supernode is either whole-owned - the top supernodes of one level then run side by side on different ranks - or
+        // shared panel-cyclically by all ranks.  A panel step costs a serial panel factorization plus a broadcast
+        // (tau ~ 0.6 ms), so sharing only pays for supernodes that dominate their level.  Per level, the heaviest whole
+        // supernodes are turned cyclic one by one while the modelled level time
+        //     sum_cyclic max(npanels * tau, flops / (N * rate))  +  max_rank(whole load) / rate
+        // keeps going down.
+        const double rate = 25e12;
+        double tau = 0.6e-3;
+        if (const char *e = getenv("SSB200_DIST_TAU")) tau = atof(e);      // seconds per panel step (tests set 0 to force sharing)
         std::vector<std::vector<int>> top_by_level(hp.nlevels);
         for (int t = 0; t < (int) nsuper; t++) if (in_top[t]) top_by_level[hp.level[t]].push_back(t);
         for (int l = 0; l < hp.nlevels; l++) {
             auto &v = top_by_level[l];
+            if (v.empty()) continue;
             std::sort(v.begin(), v.end(), [&](int a, int b) { return sn_flops[a] > sn_flops[b] || (sn_flops[a] == sn_flops[b] && a < b); });
-            std::vector<double> lvl(hp.nranks, 0.0);
-            for (int t : v) {
-                const int nscol = hp.super[t + 1] - hp.super[t];
-                if (nscol >= 2 * NB_OUTER && sn_flops[t] > 0.5 * total / hp.nranks) { hp.owner[t] = -1; continue; }
-                int q = 0;
-                for (int r = 1; r < hp.nranks; r++) if (lvl[r] < lvl[q] || (lvl[r] == lvl[q] && load[r] < load[q])) q = r;
-                lvl[q] += sn_flops[t]; load[q] += sn_flops[t]; hp.owner[t] = q;
+            auto model = [&](int ncyc, std::vector<int> *assign) {
+                double tc = 0;
+                for (int i = 0; i < ncyc; i++) {
+                    const int nscol = hp.super[v[i] + 1] - hp.super[v[i]];
+                    tc += std::max(((nscol + NB_OUTER - 1) / NB_OUTER) * tau, sn_flops[v[i]] / (hp.nranks * rate));
+                }
+                std::vector<double> lvl(hp.nranks, 0.0);
+                if (assign) assign->assign(v.size(), -1);
+                for (int i = ncyc; i < (int) v.size(); i++) {
+                    int q = 0;
+                    for (int r = 1; r < hp.nranks; r++) if (lvl[r] < lvl[q] || (lvl[r] == lvl[q] && load[r] < load[q])) q = r;
+                    lvl[q] += sn_flops[v[i]];
+                    if (assign) (*assign)[i] = q;
+                }
+                return tc + *std::max_element(lvl.begin(), lvl.end()) / rate;
+            };
+            int ncyc = 0;
+            double best = model(0, nullptr);
+            while (ncyc < (int) v.size()) {
+                const int nscol = hp.super[v[ncyc] + 1] - hp.super[v[ncyc]];
+                if (nscol < 2 * NB_OUTER) break;
+                const double t1 = model(ncyc + 1, nullptr);
+                if (t1 >= best) break;
+                best = t1; ncyc++;
+            }
+            std::vector<int> assign;
+            model(ncyc, &assign);
+            for (int i = 0; i < (int) v.size(); i++) {
+                hp.owner[v[i]] = assign[i];
+                if (assign[i] >= 0) load[assign[i]] += sn_flops[v[i]];
             }
         }
         // subtree roots / narrow top supernodes: their finished Lx ranges are broadcast after their level
