@@ -47,7 +47,7 @@ struct ssb200_plan {
     int *d_super = nullptr, *d_ls = nullptr, *d_supermap = nullptr, *d_relmap = nullptr, *d_info = nullptr;
     long long *d_pi = nullptr, *d_px = nullptr;
     double *d_Lx = nullptr;
-    double *d_winv = nullptr; long long winv_slots = 0;   // inverses of the wide diagonal blocks of the running step
+    double *d_winv = nullptr; long long winv_slots = 0;   // inverses of the wide 64x64 diagonal blocks (trsm_tc + solves)
     DevJobs jobs;
     SolveJob *d_solve_jobs = nullptr; int *d_solve_tiles = nullptr;
     int *h_info = nullptr;                 // pinned
@@ -57,8 +57,9 @@ struct ssb200_plan {
     int stype = -1;
     double *d_X = nullptr; size_t capX = 0;
     bool factor_on_device = false;
+    bool winv_valid = false;               // d_winv matches d_Lx (false after ssb200_upload_L or a sharded factorization)
     // the whole solve sequence is replayed as one CUDA graph (thousands of tiny dependent kernels)
-    cudaGraphExec_t solve_graph = nullptr; double *sg_X = nullptr; long long sg_nrhs = 0, sg_ldx = 0; int sg_which = -1;
+    cudaGraphExec_t solve_graph = nullptr; double *sg_X = nullptr; long long sg_nrhs = 0, sg_ldx = 0; int sg_which = -1; bool sg_winv = false;
     std::vector<cudaEvent_t> events;
     ssb200_stats stats{};
     std::vector<float> launch_ms;          // device time of every launch of the last factorize (debug / tuning)
@@ -286,6 +287,7 @@ extern "C" int ssb200_dist_end(ssb200_plan *p, ssb_long *first_bad_column)
         if (p->h_info[s] != INT_MAX) { if (first_bad_column) *first_bad_column = hp.super[s] + p->h_info[s] - 1; break; }
     p->stats.kernel_launches_total += p->stats.kernel_launches;
     p->factor_on_device = true;
+    p->winv_valid = (hp.nranks == 1);      // the inverses exist only on the rank that factorized the block
     return 0;
 }
 
@@ -459,7 +461,6 @@ static int handle_not_posdef(ssb200_plan *p, int sfail, int info, double beta0, 
     }
     std::vector<int> one{sfail};
     append_factor_jobs(hp, one, ncol_new, tmp);
-    if (tmp.max_winv_slots > p->winv_slots) { set_error("internal: winv workspace too small"); return SSB_CHOLMOD_GPU_PROBLEM; }
     DevJobs dj;
     size_t saved = p->device_bytes;
     if (upload_jobs(p, tmp, dj)) return SSB_CHOLMOD_GPU_PROBLEM;
@@ -557,6 +558,7 @@ static int factorize_impl(ssb200_plan *p, const double beta[2], int quick_return
     cudaEventElapsedTime(&ms, p->events[0], p->events[ev]); p->stats.ms_total = ms;
     p->stats.kernel_launches_total += p->stats.kernel_launches;
     p->factor_on_device = true;
+    p->winv_valid = (status == 0);
     if (Lx_host) {
         if (streaming && status == 0) {
             // only the tail of the copy stream is still exposed
@@ -599,6 +601,7 @@ extern "C" int ssb200_upload_L(ssb200_plan *p, const double *Lx_host)
     if (p->hp.xsize > 0) CU_TRY(cudaMemcpyAsync(p->d_Lx, Lx_host, (size_t) p->hp.xsize * sizeof(double), cudaMemcpyHostToDevice, p->stream));
     CU_TRY(cudaStreamSynchronize(p->stream));
     p->factor_on_device = true;
+    p->winv_valid = false;                 // the inverses of the diagonal blocks belong to the previous factor
     return 0;
 }
 
@@ -627,7 +630,7 @@ extern "C" int ssb200_solve_resident(ssb200_plan *p, int which, double *dX, ssb_
     const int nsteps = (int) hp.solve_steps.size();
     static int use_graph = -1;
     if (use_graph < 0) { const char *v = getenv("SSB200_SOLVE_GRAPH"); use_graph = (v && atoi(v) == 0) ? 0 : 1; }
-    const bool cached = use_graph && p->solve_graph && p->sg_X == dX && p->sg_nrhs == nrhs && p->sg_ldx == ldx && p->sg_which == which;
+    const bool cached = use_graph && p->solve_graph && p->sg_X == dX && p->sg_nrhs == nrhs && p->sg_ldx == ldx && p->sg_which == which && p->sg_winv == p->winv_valid;
     if (!cached) {
         if (use_graph) {
             if (p->solve_graph) { cudaGraphExecDestroy(p->solve_graph); p->solve_graph = nullptr; }
@@ -636,7 +639,7 @@ extern "C" int ssb200_solve_resident(ssb200_plan *p, int which, double *dX, ssb_
         if (which == 0 || which == 2) {
             for (int t = 0; t < nsteps; t++) {
                 const SolveStep &st = hp.solve_steps[t];
-                lsolve_diag_kernel<<<st.njobs, SOLVE_THREADS, 0, p->stream>>>(p->d_solve_jobs + st.job0, p->d_Lx, dX, (int) nrhs, ldx);
+                lsolve_diag_kernel<<<st.njobs, SOLVE_THREADS, 0, p->stream>>>(p->d_solve_jobs + st.job0, p->d_Lx, p->winv_valid ? p->d_winv : nullptr, dX, (int) nrhs, ldx);
                 if (st.ntiles > 0)
                     lsolve_update_kernel<<<st.ntiles, SOLVE_THREADS, 0, p->stream>>>(p->d_solve_jobs + st.job0, p->d_solve_tiles + st.tile0, p->d_Lx, p->d_ls, dX, (int) nrhs, ldx);
             }
@@ -646,7 +649,7 @@ extern "C" int ssb200_solve_resident(ssb200_plan *p, int which, double *dX, ssb_
                 const SolveStep &st = hp.solve_steps[t];
                 if (st.ntiles > 0)
                     ltsolve_update_kernel<<<st.ntiles, SOLVE_THREADS, 0, p->stream>>>(p->d_solve_jobs + st.job0, p->d_solve_tiles + st.tile0, p->d_Lx, p->d_ls, dX, (int) nrhs, ldx);
-                ltsolve_diag_kernel<<<st.njobs, SOLVE_THREADS, 0, p->stream>>>(p->d_solve_jobs + st.job0, p->d_Lx, dX, (int) nrhs, ldx);
+                ltsolve_diag_kernel<<<st.njobs, SOLVE_THREADS, 0, p->stream>>>(p->d_solve_jobs + st.job0, p->d_Lx, p->winv_valid ? p->d_winv : nullptr, dX, (int) nrhs, ldx);
             }
         }
         if (use_graph) {
@@ -655,7 +658,7 @@ extern "C" int ssb200_solve_resident(ssb200_plan *p, int which, double *dX, ssb_
             cudaError_t ie = cudaGraphInstantiate(&p->solve_graph, g, 0);
             cudaGraphDestroy(g);
             if (ie != cudaSuccess) { p->solve_graph = nullptr; set_error(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ie)); return SSB_CHOLMOD_GPU_PROBLEM; }
-            p->sg_X = dX; p->sg_nrhs = nrhs; p->sg_ldx = ldx; p->sg_which = which;
+            p->sg_X = dX; p->sg_nrhs = nrhs; p->sg_ldx = ldx; p->sg_which = which; p->sg_winv = p->winv_valid;
         }
     }
     // launches of one solve: a diag kernel per step and an update kernel per step that has rows below, per direction

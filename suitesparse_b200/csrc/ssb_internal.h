@@ -39,7 +39,7 @@ struct PanelJob {
     int col0;            // first column of this step inside its supernode (for info)
     int snode;           // supernode index (for info)
     int tile_start;      // trsm: first tile of this job inside its launch
-    int winv_slot;       // >= 0: potrf also writes the inverse of the diagonal block to winv[slot]; trsm_tc reads it
+    int winv_slot;       // >= 0: potrf also writes the inverse of the diagonal block to winv[slot]; trsm_tc and the solves read it
     int pad;
 };
 
@@ -51,7 +51,7 @@ struct SolveJob {
     int lda, w, rows_below;
     int xcol0;           // first column (= row of X) of the block
     int tile_start;
-    int pad;
+    int winv_slot;       // >= 0: the inverse of the diagonal block is in winv[slot] (diagonal solve = 64x64 mat-vec)
 };
 constexpr int SOLVE_ROWS = 128;     // rows per solve-update tile
 struct SolveStep { long long job0; int njobs; long long tile0; int ntiles; };
@@ -88,6 +88,7 @@ struct HostPlan {
     std::vector<long long> pi, px;   // nsuper+1
     std::vector<int> ls;             // ssize (row indices, < 2^31)
     std::vector<int> supermap;       // n
+    std::vector<int> winv_base;      // per supernode: first inverse slot of its blocks, or -1
     std::vector<int> level;          // etree level of every supernode
     std::vector<int> parent;
     int nlevels = 0;
@@ -99,7 +100,7 @@ struct HostPlan {
     std::vector<PanelJob> potrf_jobs;
     std::vector<PanelJob> trsm_jobs;
     std::vector<int> trsm_tiles;
-    int max_winv_slots = 0;          // inverse-diagonal-block workspace slots needed by the widest launch
+    int max_winv_slots = 0;          // number of inverse-diagonal-block slots (one per wide 64-column block, kept for the solves)
     std::vector<Launch> launches;    // in execution order
     std::vector<int> level_launch_begin; // nlevels+1
     std::vector<CopyTask> copy_tasks;    // sorted by after_launch
@@ -125,6 +126,9 @@ bool build_host_plan(long long n, long long nsuper, const long long *super, cons
 
 // Job lists for factorizing ONE supernode restricted to its first ncol_limit columns (not-positive-definite repeat,
 // t_cholmod_super_numeric.c:944-967).  Appends launches to `out`.
+// slot of the inverse of the 64-column diagonal block starting at column j0 of supernode s (-1: none kept)
+int winv_slot_of(const HostPlan &hp, int s, int j0);
+
 void append_factor_jobs(const HostPlan &hp, const std::vector<int> &snodes, int ncol_limit, HostPlan &out, bool panel_copies = false,
                         int only_panel_J0 = -1);
 

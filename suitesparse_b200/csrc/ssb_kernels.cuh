@@ -536,15 +536,36 @@ __global__ void fill_int_kernel(int *p, long long n, int v)
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int SOLVE_THREADS = 128;
 
-// forward, step (a): x1 <- L11^{-1} x1 for every right-hand side
+// forward, step (a): x1 <- L11^{-1} x1 for every right-hand side.  Wide blocks have their inverse W = L11^{-1} from the
+// factorization: the solve is a 64x64 mat-vec (no column-by-column barriers); narrow blocks substitute in shared memory.
 __global__ void __launch_bounds__(SOLVE_THREADS) lsolve_diag_kernel(const SolveJob *__restrict__ jobs, const double *__restrict__ Lx,
-                                                                   double *__restrict__ X, int nrhs, long long ldx)
+                                                                   const double *__restrict__ winv, double *__restrict__ X, int nrhs, long long ldx)
 {
     constexpr int LDS = NB_INNER + 1;
     __shared__ double T[NB_INNER * LDS];
     __shared__ double xs[NB_INNER];
     const SolveJob job = jobs[blockIdx.x];
     const int w = job.w, tid = threadIdx.x;
+    if (winv && job.winv_slot >= 0) {
+        const double *__restrict__ W = winv + (long long) job.winv_slot * (NB_INNER * NB_INNER);   // W(i,k) at W[i + 64k]
+        for (int r = 0; r < nrhs; r++) {
+            double *__restrict__ x = X + r * ldx + job.xcol0;
+            __syncthreads();
+            if (tid < w) xs[tid] = x[tid];
+            __syncthreads();
+            // two threads per row: even/odd k, 32 independent loads each, coalesced over the rows
+            const int i = tid & 63, half = tid >> 6;
+            double acc = 0.0;
+            if (i < w) {
+#pragma unroll 8
+                for (int k = half; k <= i; k += 2) acc += W[i + NB_INNER * k] * xs[k];
+            }
+            T[tid] = acc;
+            __syncthreads();
+            if (tid < w) x[tid] = T[tid] + T[tid + 64];
+        }
+        return;
+    }
     const double *__restrict__ A = Lx + job.x_off;
     for (int e = tid; e < w * w; e += SOLVE_THREADS) {
         const int i = e % w, j = e / w;
@@ -643,15 +664,37 @@ __global__ void __launch_bounds__(SOLVE_THREADS) ltsolve_update_kernel(const Sol
     }
 }
 
-// backward, step (b): x1 <- L11^{-T} x1
+// backward, step (b): x1 <- L11^{-T} x1  (W^T mat-vec for wide blocks: thread i sums W(k,i) x(k), k >= i; W is staged
+// through shared memory so that the global reads stay coalesced)
 __global__ void __launch_bounds__(SOLVE_THREADS) ltsolve_diag_kernel(const SolveJob *__restrict__ jobs, const double *__restrict__ Lx,
-                                                                    double *__restrict__ X, int nrhs, long long ldx)
+                                                                    const double *__restrict__ winv, double *__restrict__ X, int nrhs, long long ldx)
 {
     constexpr int LDS = NB_INNER + 1;
     __shared__ double T[NB_INNER * LDS];
     __shared__ double xs[NB_INNER];
+    __shared__ double part[SOLVE_THREADS];
     const SolveJob job = jobs[blockIdx.x];
     const int w = job.w, tid = threadIdx.x;
+    if (winv && job.winv_slot >= 0) {
+        const double *__restrict__ W = winv + (long long) job.winv_slot * (NB_INNER * NB_INNER);
+        for (int e = tid; e < NB_INNER * NB_INNER; e += SOLVE_THREADS) T[(e & 63) * LDS + (e >> 6)] = W[e];   // T[k][i] = W(k,i)
+        for (int r = 0; r < nrhs; r++) {
+            double *__restrict__ x = X + r * ldx + job.xcol0;
+            __syncthreads();
+            if (tid < w) xs[tid] = x[tid];
+            __syncthreads();
+            const int i = tid & 63, half = tid >> 6;
+            double acc = 0.0;
+            if (i < w) {
+#pragma unroll 8
+                for (int k = i + half; k < w; k += 2) acc += T[k * LDS + i] * xs[k];
+            }
+            part[tid] = acc;
+            __syncthreads();
+            if (tid < w) x[tid] = part[tid] + part[tid + 64];
+        }
+        return;
+    }
     const double *__restrict__ A = Lx + job.x_off;
     for (int e = tid; e < w * w; e += SOLVE_THREADS) {
         const int i = e % w, j = e / w;

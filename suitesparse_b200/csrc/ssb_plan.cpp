@@ -16,6 +16,18 @@ namespace ssb {
 
 int gemm_tile_size(int kind) { return kind == L_GEMM_BIG ? 128 : 64; }
 
+// A supernode keeps the inverses of its 64x64 diagonal blocks if it is wider than 32 columns and has rows below; block b
+// (columns [64b, 64b+w)) qualifies if w >= TRSM_TC_MIN_W and rows remain below it.
+int winv_slot_of(const HostPlan &hp, int s, int j0)
+{
+    if (hp.winv_base.empty() || hp.winv_base[s] < 0) return -1;
+    const int nscol = hp.super[s + 1] - hp.super[s];
+    const int nsrow = (int) (hp.pi[s + 1] - hp.pi[s]);
+    const int w = std::min(NB_INNER, nscol - j0);
+    if (w < TRSM_TC_MIN_W || nsrow - j0 - w <= 0) return -1;
+    return hp.winv_base[s] + j0 / NB_INNER;
+}
+
 namespace {
 
 // Append one launch of gemm jobs (already final except tile_start) of a given kind; builds the tile->job array.
@@ -86,7 +98,6 @@ void append_factor_jobs(const HostPlan &hp, const std::vector<int> &snodes, int 
             // rows-below jobs: narrow panels go to the substitution kernel, wide ones to the tensor-core kernel.  Both job
             // lists live in trsm_jobs (substitution jobs of this step first), each with its own tile->job array.
             std::vector<PanelJob> sub_jobs, tc_jobs;
-            int nslots = 0;
             for (int s : snodes) {
                 int nscol = hp.super[s + 1] - hp.super[s];
                 if (ncol_limit >= 0) nscol = std::min(nscol, ncol_limit);
@@ -96,7 +107,7 @@ void append_factor_jobs(const HostPlan &hp, const std::vector<int> &snodes, int 
                 PanelJob pj{};
                 pj.x_off = hp.px[s] + j0 + (long long) j0 * nsrow;
                 pj.lda = nsrow; pj.w = w; pj.rows_below = nsrow - j0 - w; pj.col0 = j0; pj.snode = s; pj.tile_start = 0;
-                pj.winv_slot = (pj.rows_below > 0 && w >= TRSM_TC_MIN_W) ? nslots++ : -1;
+                pj.winv_slot = winv_slot_of(hp, s, j0);
                 out.potrf_jobs.push_back(pj);
                 LP.njobs++; LP.flops += (double) w * w * w / 3.0;
                 if (pj.rows_below > 0) {
@@ -113,7 +124,6 @@ void append_factor_jobs(const HostPlan &hp, const std::vector<int> &snodes, int 
                     }
                 }
             }
-            out.max_winv_slots = std::max(out.max_winv_slots, nslots);
             auto emit_trsm = [&](std::vector<PanelJob> &jobs, int kind) {
                 Launch LT{}; LT.kind = kind; LT.phase = 1; LT.job0 = (long long) out.trsm_jobs.size();
                 LT.tile0 = (long long) out.trsm_tiles.size();
@@ -229,6 +239,17 @@ bool build_host_plan(long long n, long long nsuper, const long long *super, cons
     for (auto &u : ups) { u.map_off = moff; moff += u.nd2; }
     hp.relmap_size = moff;
     hp.updates.swap(ups);
+    // ---- inverse-diagonal-block slots (tensor-core trsm during the factorization, mat-vec diagonal solves afterwards) --
+    hp.winv_base.assign(nsuper, -1);
+    {
+        int slots = 0;
+        for (int t = 0; t < (int) nsuper; t++) {
+            const int nscol = hp.super[t + 1] - hp.super[t];
+            const int nsrow = (int) (hp.pi[t + 1] - hp.pi[t]);
+            if (nscol >= TRSM_TC_MIN_W && nsrow > nscol - 0) { hp.winv_base[t] = slots; slots += (nscol + NB_INNER - 1) / NB_INNER; }
+        }
+        hp.max_winv_slots = slots;
+    }
     // ---- shard: which rank computes which supernode ---------------------------------------------------------------
     hp.nranks = std::max(1, nranks); hp.rank = rank;
     std::vector<double> sn_flops(nsuper, 0.0);          // dense flops with this supernode as the target
@@ -482,6 +503,7 @@ bool build_host_plan(long long n, long long nsuper, const long long *super, cons
                 sj.ls_off = hp.pi[sn] + j0 + sj.w;
                 sj.lda = nsrow; sj.rows_below = nsrow - j0 - sj.w; sj.xcol0 = hp.super[sn] + j0;
                 sj.tile_start = st.ntiles;
+                sj.winv_slot = winv_slot_of(hp, sn, j0);
                 const int nt = (sj.rows_below + SOLVE_ROWS - 1) / SOLVE_ROWS;
                 for (int q = 0; q < nt; q++) hp.solve_tiles.push_back(st.njobs);
                 st.ntiles += nt;

@@ -179,3 +179,61 @@ def test_full_size_properties_lap7_128():
     assert pl is not None and pl.stats()["nsuper"] == f["nsuper"]
     ch.free_factor(L)
     ch.b200.cholmod_l_gpu_deallocate(C.byref(ch.cm))
+
+
+def test_sharded_api_single_rank():
+    """The step-driven sharded path (ssb200_dist_*) with one rank: same factor as the oracle, streamed host copy equal to
+    the device factor.  The multi-rank schedule itself is covered on the CPU by tests/test_dist_cpu.py (gloo + emulator)
+    and on 2/4/8 B200 by scripts/dist_check.py."""
+    import torch
+    from suitesparse_b200 import gen, cholmod_host as H
+    from suitesparse_b200.dist import ShardedFactor
+    from oracle import oracle
+    ch = H.Cholmod(gpu=True)
+    A, p = gen.make_problem("lap27", 16)
+    S = ch.sparse(A, +1); L = ch.analyze(S, p)
+    f = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in ch.factor_arrays(L).items()}
+    S2 = ch.lower_permuted(S, L); s2 = S2.contents; n = s2.nrow
+    Ap = H._np_view(s2.p, n + 1, np.int64).copy(); Ai = H._np_view(s2.i, int(Ap[n]), np.int64).copy(); Ax = H._np_view(s2.x, int(Ap[n]), np.float64).copy()
+    Sl = sp.csc_matrix((Ax, Ai, Ap), shape=(n, n))
+    sf = ShardedFactor(n, f["super"], f["pi"], f["px"], f["s"], 0, rank=0, world=1)
+    sf.upload_A(Sl)
+    host = torch.empty(sf.xsize, dtype=torch.float64, pin_memory=True)
+    st, minor = sf.factorize_resident(host_out=host)
+    assert (st, minor) == (0, n)
+    st_o, minor_o, Lo = oracle.factorize(n, f["super"], f["pi"], f["px"], f["s"], Sl)
+    assert persuper_relerr(f["px"], host.numpy(), Lo) < TOL_L
+    assert np.array_equal(host.numpy(), sf.download_L())
+    # not positive definite: every rank reports the same failing column; the failing supernode and the rest are zeroed
+    Sbad = Sl.copy().tolil(); kbad = n // 2; Sbad[kbad, kbad] = -1.0; Sbad = Sbad.tocsc(); Sbad.sort_indices()
+    sf.upload_A(Sbad)
+    st, minor = sf.factorize_resident()
+    st_o, minor_o, Lo = oracle.factorize(n, f["super"], f["pi"], f["px"], f["s"], Sbad, quick_return=True)
+    assert st == 1 and minor == minor_o
+    Lx = sf.download_L()
+    sbad = int(np.searchsorted(f["super"], minor, side="right") - 1)
+    assert np.all(Lx[int(f["px"][sbad]):] == 0.0)
+    assert persuper_relerr(f["px"][: sbad + 1], Lx, Lo) < TOL_L
+    sf.close(); ch.free_sparse(S2); ch.free_factor(L)
+
+
+def test_stale_host_registration_is_detected():
+    """Regression: the drop-in layer page-locks L->x.  When the application frees a factor and the allocator reuses the
+    range, the old registration must not be trusted (DMA would land in the old physical pages)."""
+    from suitesparse_b200 import gen, cholmod_host as H
+    from oracle import oracle
+    ch = H.Cholmod(gpu=True)
+    for rep, N in enumerate((14, 14, 15, 14, 13, 14)):
+        A, p = gen.make_problem("lap7", N)
+        S = ch.sparse(A, +1)
+        L = ch.analyze(S, p)
+        assert ch.factorize(S, L) == 1 and ch.cm.status == 0
+        f = ch.factor_arrays(L)
+        assert f["xsize"] >= (1 << 16)                      # large enough to be page-locked
+        n = f["n"]
+        S2 = ch.lower_permuted(S, L); s2 = S2.contents
+        Ap = H._np_view(s2.p, n + 1, np.int64); Ai = H._np_view(s2.i, int(Ap[n]), np.int64); Ax = H._np_view(s2.x, int(Ap[n]), np.float64)
+        st, minor, Lo = oracle.factorize(n, f["super"], f["pi"], f["px"], f["s"], sp.csc_matrix((Ax, Ai, Ap), shape=(n, n)))
+        assert persuper_relerr(f["px"], f["x"], Lo) < TOL_L, f"repetition {rep}"
+        ch.free_sparse(S2)
+        ch.free_factor(L)                                   # no cholmod_l_gpu_deallocate: the cache keeps the stale pin
