@@ -606,18 +606,26 @@ __global__ void __launch_bounds__(SOLVE_THREADS) lsolve_update_kernel(const Solv
         __syncthreads();
         if (tid < w) xs[tid] = x[job.xcol0 + tid];
         __syncthreads();
-        if (!live) continue;
         double acc = 0.0;
         int c = 0;
+        for (; c + 32 <= w; c += 32) {                  // 32 independent loads in flight per thread
+            double v[32];
+#pragma unroll
+            for (int q = 0; q < 32; q++) v[q] = live ? __ldcs(row + (long long) (c + q) * lda) : 0.0;
+            __syncwarp();                               // scheduling fence: all 32 loads are issued before the first FMA
+#pragma unroll
+            for (int q = 0; q < 32; q++) acc += v[q] * xs[c + q];
+        }
         for (; c + 8 <= w; c += 8) {
             double v[8];
 #pragma unroll
-            for (int q = 0; q < 8; q++) v[q] = __ldcs(row + (long long) (c + q) * lda);
+            for (int q = 0; q < 8; q++) v[q] = live ? __ldcs(row + (long long) (c + q) * lda) : 0.0;
+            __syncwarp();
 #pragma unroll
             for (int q = 0; q < 8; q++) acc += v[q] * xs[c + q];
         }
-        for (; c < w; c++) acc += __ldcs(row + (long long) c * lda) * xs[c];
-        red_add_f64(x + xrow, -acc);
+        for (; c < w; c++) acc += (live ? __ldcs(row + (long long) c * lda) : 0.0) * xs[c];
+        if (live) red_add_f64(x + xrow, -acc);
     }
 }
 
@@ -641,21 +649,27 @@ __global__ void __launch_bounds__(SOLVE_THREADS) ltsolve_update_kernel(const Sol
         __syncthreads();
         for (int r = tid; r < SOLVE_ROWS; r += SOLVE_THREADS) xr[r] = (r < nr) ? x[ls[job.ls_off + r0 + r]] : 0.0;
         __syncthreads();
-        for (int c0 = warp * 4; c0 < w; c0 += NW * 4) {
-            double acc[4] = {0.0, 0.0, 0.0, 0.0};
+        constexpr int CPW = 8;                          // columns per warp per round: CPW*RPL loads in flight per lane
+        for (int c0 = warp * CPW; c0 < w; c0 += NW * CPW) {
+            double acc[CPW], v[CPW][RPL];
 #pragma unroll
-            for (int q = 0; q < 4; q++) {
-                if (c0 + q < w) {
-                    const double *__restrict__ col = L2 + (long long) (c0 + q) * lda;
+            for (int q = 0; q < CPW; q++) {
+                const double *__restrict__ col = L2 + (long long) (c0 + q) * lda;
 #pragma unroll
-                    for (int t = 0; t < RPL; t++) {
-                        const int r = lane + 32 * t;
-                        if (r < nr) acc[q] += __ldcs(col + r) * xr[r];
-                    }
+                for (int t = 0; t < RPL; t++) {
+                    const int r = lane + 32 * t;
+                    v[q][t] = (c0 + q < w && r < nr) ? __ldcs(col + r) : 0.0;
                 }
             }
+            asm volatile("" ::: "memory");              // CPW*RPL loads in flight per lane before the first FMA
 #pragma unroll
-            for (int q = 0; q < 4; q++) {
+            for (int q = 0; q < CPW; q++) {
+                acc[q] = 0.0;
+#pragma unroll
+                for (int t = 0; t < RPL; t++) acc[q] += v[q][t] * xr[lane + 32 * t];
+            }
+#pragma unroll
+            for (int q = 0; q < CPW; q++) {
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
                 if (lane == 0 && c0 + q < w) red_add_f64(x + job.xcol0 + c0 + q, -acc[q]);

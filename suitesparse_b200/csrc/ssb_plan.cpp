@@ -246,7 +246,7 @@ bool build_host_plan(long long n, long long nsuper, const long long *super, cons
         for (int t = 0; t < (int) nsuper; t++) {
             const int nscol = hp.super[t + 1] - hp.super[t];
             const int nsrow = (int) (hp.pi[t + 1] - hp.pi[t]);
-            if (nscol >= TRSM_TC_MIN_W && nsrow > nscol - 0) { hp.winv_base[t] = slots; slots += (nscol + NB_INNER - 1) / NB_INNER; }
+            if (nscol >= TRSM_TC_MIN_W && nsrow > NB_INNER / 2) { hp.winv_base[t] = slots; slots += (nscol + NB_INNER - 1) / NB_INNER; }
         }
         hp.max_winv_slots = slots;
     }

@@ -129,6 +129,10 @@ class ShardedFactor:
                     host_out.copy_(self.Lx[:self.xsize])
                 return 1, minor
         if host_out is not None:
+            if self.world == 1:                           # nothing is broadcast with one rank: plain copy at the end
+                with torch.cuda.stream(self._copy_stream):
+                    self._copy_stream.wait_stream(self.stream)
+                    host_out[:self.xsize].copy_(self.Lx[:self.xsize], non_blocking=True)
             self._copy_stream.synchronize()
         return 0, self.n
 
