@@ -14,8 +14,11 @@ REF_LIB = os.path.join(HERE, "_ref", "libcholmod_ref.so")
 def build(ref: bool = True):
     """Compile the C restatement, and the reference build when /root/reference is present."""
     subprocess.check_call(["make", "-s", "-C", HERE, "port"])
-    if ref and os.path.isdir(os.environ.get("SSB200_REFERENCE", "/root/reference")) and not os.path.exists(REF_LIB):
-        subprocess.check_call(["make", "-s", "-C", HERE, "ref"])
+    if ref and os.path.isdir(os.environ.get("SSB200_REFERENCE", "/root/reference")):
+        if not os.path.exists(REF_LIB):
+            subprocess.check_call(["make", "-s", "-C", HERE, "ref"])
+        if not os.path.exists(os.path.join(HERE, "_ref", "cholmod_l_demo")):
+            subprocess.check_call(["make", "-s", "-C", HERE, "demo"])
 
 
 _lib = None

@@ -924,6 +924,11 @@ extern "C" int cholmod_l_super_numeric(ssb_cholmod_sparse *A, ssb_cholmod_sparse
     }
     L->is_ll = 1;
     std::lock_guard<std::mutex> lk(g_cache_mu);
+    {
+        static int verbose = -1;
+        if (verbose < 0) { const char *v = getenv("SSB200_VERBOSE"); verbose = (v && atoi(v)) ? 1 : 0; }
+        if (verbose) fprintf(stderr, "[suitesparse_b200] cholmod_l_super_numeric: n=%zu nsuper=%zu xsize=%zu (CUDA path)\n", L->n, L->nsuper, L->xsize);
+    }
     CacheEntry *e = cache_get_plan(L);
     if (!e) { RAISE(Common, SSB_CHOLMOD_GPU_PROBLEM, ssb200_last_error()); return 0; }
     pin_host_x(e, L);
@@ -971,6 +976,11 @@ static int super_solve_common(ssb_cholmod_factor *L, ssb_cholmod_dense *X, ssb_c
     if (L->n == 0 || X->ncol == 0) return 1;
     if (L->xtype != SSB_CHOLMOD_REAL) { RAISE(Common, SSB_CHOLMOD_NOT_INSTALLED, "suitesparse_b200: complex supernodal solve is not provided on the GPU path"); return 0; }
     std::lock_guard<std::mutex> lk(g_cache_mu);
+    {
+        static int verbose = -1;
+        if (verbose < 0) { const char *v = getenv("SSB200_VERBOSE"); verbose = (v && atoi(v)) ? 1 : 0; }
+        if (verbose) fprintf(stderr, "[suitesparse_b200] cholmod_l_super_%ssolve: n=%zu nrhs=%zu (CUDA path)\n", which ? "lt" : "l", L->n, X->ncol);
+    }
     CacheEntry *e = cache_get_plan(L);
     if (!e) { RAISE(Common, SSB_CHOLMOD_GPU_PROBLEM, ssb200_last_error()); return 0; }
     if (!value_fingerprint_ok(e, L)) {
