@@ -9,9 +9,13 @@ namespace ssb {
 
 // Blocking of one supernode's dense factorization (potrf of the diagonal block + trsm of the rows below,
 // t_cholmod_super_numeric.c:864,997), done as ONE right-looking blocked Cholesky of the tall nsrow x nscol block:
-//   outer panel NB columns: trailing update with K = NB (every C element is re-read once per NB columns)
-//   inner panel nb columns: unblocked potrf of the nb x nb block, substitution trsm of the rows below, K = nb update
-constexpr int NB_OUTER = 256;
+//   three nested panel widths 64 / 256 / 1024: the K = 64 update stays inside the 256-wide panel, the K = 256 update
+//   inside the 1024-wide panel, and only the K = 1024 update touches the whole trailing block, so that the bulk of the
+//   flops runs in GEMMs whose C tile is re-read once per 1024 columns
+//   inner panel: potrf of the 64 x 64 block (+ its inverse), trsm of the rows below, K = 64 update
+constexpr int NB_OUTER = 1024;     // outermost panel: its trailing update runs with K = 1024 (C re-read once per 1024 columns)
+constexpr int NB_MID = 256;        // middle panel: K = 256 update, confined to the outer panel; also the panel width of the
+                                   // panel-cyclic distribution over GPUs and the granularity of the device-to-host streaming
 constexpr int NB_INNER = 64;
 constexpr int TRSM_ROWS = 128;      // rows per trsm tile
 

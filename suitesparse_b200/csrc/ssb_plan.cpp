@@ -92,87 +92,92 @@ void append_factor_jobs(const HostPlan &hp, const std::vector<int> &snodes, int 
         maxcol = std::max(maxcol, nscol);
     }
     std::vector<GemmJob> gs, gb;
-    for (int J0 = (only_panel_J0 >= 0 ? only_panel_J0 : 0); J0 < maxcol; J0 += NB_OUTER) {
-        for (int j0 = J0; j0 < std::min(J0 + NB_OUTER, maxcol); j0 += NB_INNER) {
-            Launch LP{}; LP.kind = L_POTRF; LP.phase = 1; LP.job0 = (long long) out.potrf_jobs.size();
-            // rows-below jobs: narrow panels go to the substitution kernel, wide ones to the tensor-core kernel.  Both job
-            // lists live in trsm_jobs (substitution jobs of this step first), each with its own tile->job array.
-            std::vector<PanelJob> sub_jobs, tc_jobs;
-            for (int s : snodes) {
-                int nscol = hp.super[s + 1] - hp.super[s];
-                if (ncol_limit >= 0) nscol = std::min(nscol, ncol_limit);
-                if (nscol <= j0) continue;
-                const int nsrow = (int) (hp.pi[s + 1] - hp.pi[s]);
-                const int w = std::min(NB_INNER, nscol - j0);
-                PanelJob pj{};
-                pj.x_off = hp.px[s] + j0 + (long long) j0 * nsrow;
-                pj.lda = nsrow; pj.w = w; pj.rows_below = nsrow - j0 - w; pj.col0 = j0; pj.snode = s; pj.tile_start = 0;
-                pj.winv_slot = winv_slot_of(hp, s, j0);
-                out.potrf_jobs.push_back(pj);
-                LP.njobs++; LP.flops += (double) w * w * w / 3.0;
-                if (pj.rows_below > 0) {
-                    (pj.winv_slot >= 0 ? tc_jobs : sub_jobs).push_back(pj);
-                    // inner trailing update: remaining columns of the outer panel
-                    const int outer_end = std::min(J0 + NB_OUTER, nscol);
-                    const int ct = outer_end - (j0 + w);
-                    if (ct > 0) {
-                        GemmJob g{};
-                        g.a_off = hp.px[s] + (j0 + w) + (long long) j0 * nsrow;
-                        g.c_off = hp.px[s] + (j0 + w) + (long long) (j0 + w) * nsrow;
-                        g.map_off = -1; g.lda = nsrow; g.ldc = nsrow; g.K = w; g.nd1 = ct; g.nd2 = nsrow - j0 - w; g.atomic = 1;
-                        route_gemm(g, gs, gb);
+    // trailing update of one supernode: columns [c0, c1) of the tall block, with the finished panel [p0, p0+W) (K = W)
+    auto trailing = [&](int s, int p0, int W, int c1) {
+        const int nsrow = (int) (hp.pi[s + 1] - hp.pi[s]);
+        const int c0 = p0 + W;
+        if (c1 - c0 <= 0) return;
+        GemmJob g{};
+        g.a_off = hp.px[s] + c0 + (long long) p0 * nsrow;
+        g.c_off = hp.px[s] + c0 + (long long) c0 * nsrow;
+        g.map_off = -1; g.lda = nsrow; g.ldc = nsrow; g.K = W; g.nd1 = c1 - c0; g.nd2 = nsrow - c0; g.atomic = 1;
+        route_gemm(g, gs, gb);
+    };
+    auto ncols = [&](int s) { const int c = hp.super[s + 1] - hp.super[s]; return ncol_limit >= 0 ? std::min(c, ncol_limit) : c; };
+    const int O_first = only_panel_J0 >= 0 ? (only_panel_J0 / NB_OUTER) * NB_OUTER : 0;
+    for (int O0 = O_first; O0 < maxcol; O0 += NB_OUTER) {
+        const int O1 = std::min(O0 + NB_OUTER, maxcol);
+        for (int M0 = (only_panel_J0 >= 0 ? only_panel_J0 : O0); M0 < O1; M0 += NB_MID) {
+            const int M1 = std::min(M0 + NB_MID, maxcol);
+            for (int j0 = M0; j0 < M1; j0 += NB_INNER) {
+                Launch LP{}; LP.kind = L_POTRF; LP.phase = 1; LP.job0 = (long long) out.potrf_jobs.size();
+                // rows-below jobs: narrow panels go to the substitution kernel, wide ones to the tensor-core kernel.  Both
+                // job lists live in trsm_jobs (substitution jobs of this step first), each with its own tile->job array.
+                std::vector<PanelJob> sub_jobs, tc_jobs;
+                for (int s : snodes) {
+                    const int nscol = ncols(s);
+                    if (nscol <= j0) continue;
+                    const int nsrow = (int) (hp.pi[s + 1] - hp.pi[s]);
+                    const int w = std::min(NB_INNER, nscol - j0);
+                    PanelJob pj{};
+                    pj.x_off = hp.px[s] + j0 + (long long) j0 * nsrow;
+                    pj.lda = nsrow; pj.w = w; pj.rows_below = nsrow - j0 - w; pj.col0 = j0; pj.snode = s; pj.tile_start = 0;
+                    pj.winv_slot = winv_slot_of(hp, s, j0);
+                    out.potrf_jobs.push_back(pj);
+                    LP.njobs++; LP.flops += (double) w * w * w / 3.0;
+                    if (pj.rows_below > 0) {
+                        (pj.winv_slot >= 0 ? tc_jobs : sub_jobs).push_back(pj);
+                        trailing(s, j0, w, std::min(M0 + NB_MID, nscol));      // K = 64 update inside the middle panel
                     }
                 }
+                auto emit_trsm = [&](std::vector<PanelJob> &jobs, int kind) {
+                    Launch LT{}; LT.kind = kind; LT.phase = 1; LT.job0 = (long long) out.trsm_jobs.size();
+                    LT.tile0 = (long long) out.trsm_tiles.size();
+                    long long ttiles = 0;
+                    for (PanelJob &pj : jobs) {
+                        pj.tile_start = (int) ttiles;
+                        const int nt = (pj.rows_below + TRSM_ROWS - 1) / TRSM_ROWS;
+                        for (int q = 0; q < nt; q++) out.trsm_tiles.push_back(LT.njobs);
+                        ttiles += nt;
+                        out.trsm_jobs.push_back(pj);
+                        LT.njobs++; LT.flops += (double) pj.w * pj.w * pj.rows_below;
+                    }
+                    LT.ntiles = (int) ttiles;
+                    return LT;
+                };
+                Launch LT = emit_trsm(sub_jobs, L_TRSM);
+                Launch LT2 = emit_trsm(tc_jobs, L_TRSM_TC);
+                if (LP.njobs) out.launches.push_back(LP);
+                if (LT.njobs) out.launches.push_back(LT);
+                if (LT2.njobs) out.launches.push_back(LT2);
+                emit_update_launches(out, gs, gb, 1);
             }
-            auto emit_trsm = [&](std::vector<PanelJob> &jobs, int kind) {
-                Launch LT{}; LT.kind = kind; LT.phase = 1; LT.job0 = (long long) out.trsm_jobs.size();
-                LT.tile0 = (long long) out.trsm_tiles.size();
-                long long ttiles = 0;
-                for (PanelJob &pj : jobs) {
-                    pj.tile_start = (int) ttiles;
-                    const int nt = (pj.rows_below + TRSM_ROWS - 1) / TRSM_ROWS;
-                    for (int q = 0; q < nt; q++) out.trsm_tiles.push_back(LT.njobs);
-                    ttiles += nt;
-                    out.trsm_jobs.push_back(pj);
-                    LT.njobs++; LT.flops += (double) pj.w * pj.w * pj.rows_below;
+            // columns [M0, M0+Wm) of every active supernode are final now: they can stream to the host while the
+            // trailing updates run
+            if (panel_copies && !out.launches.empty()) {
+                const int after = (int) out.launches.size() - 1;
+                for (int s : snodes) {
+                    const int nscol = ncols(s);
+                    if (nscol <= M0) continue;
+                    const long long nsrow = hp.pi[s + 1] - hp.pi[s];
+                    const int Wm = std::min(NB_MID, nscol - M0);
+                    out.copy_tasks.push_back(CopyTask{after, hp.px[s] + (long long) M0 * nsrow, (long long) Wm * nsrow});
                 }
-                LT.ntiles = (int) ttiles;
-                return LT;
-            };
-            Launch LT = emit_trsm(sub_jobs, L_TRSM);
-            Launch LT2 = emit_trsm(tc_jobs, L_TRSM_TC);
-            if (LP.njobs) out.launches.push_back(LP);
-            if (LT.njobs) out.launches.push_back(LT);
-            if (LT2.njobs) out.launches.push_back(LT2);
+            }
+            if (only_panel_J0 >= 0) return;         // distributed supernode: the caller splits the trailing update over the ranks
+            // K = 256 update inside the outer panel
+            for (int s : snodes) {
+                const int nscol = ncols(s);
+                if (nscol <= M0) continue;
+                trailing(s, M0, std::min(NB_MID, nscol - M0), std::min(O0 + NB_OUTER, nscol));
+            }
             emit_update_launches(out, gs, gb, 1);
         }
-        // columns [J0, J0+W) of every active supernode are final now: they can stream to the host while the trailing
-        // update runs
-        if (panel_copies && !out.launches.empty()) {
-            const int after = (int) out.launches.size() - 1;
-            for (int s : snodes) {
-                const int nscol = hp.super[s + 1] - hp.super[s];
-                if (nscol <= J0) continue;
-                const long long nsrow = hp.pi[s + 1] - hp.pi[s];
-                const int W = std::min(NB_OUTER, nscol - J0);
-                out.copy_tasks.push_back(CopyTask{after, hp.px[s] + (long long) J0 * nsrow, (long long) W * nsrow});
-            }
-        }
-        if (only_panel_J0 >= 0) break;          // distributed supernode: the trailing update is split over the ranks by the caller
-        // outer trailing update with the whole NB_OUTER-wide panel
+        // K = 1024 update of everything behind the outer panel
         for (int s : snodes) {
-            int nscol = hp.super[s + 1] - hp.super[s];
-            if (ncol_limit >= 0) nscol = std::min(nscol, ncol_limit);
-            if (nscol <= J0) continue;
-            const int nsrow = (int) (hp.pi[s + 1] - hp.pi[s]);
-            const int W = std::min(NB_OUTER, nscol - J0);
-            const int ct = nscol - (J0 + W);
-            if (ct <= 0) continue;
-            GemmJob g{};
-            g.a_off = hp.px[s] + (J0 + W) + (long long) J0 * nsrow;
-            g.c_off = hp.px[s] + (J0 + W) + (long long) (J0 + W) * nsrow;
-            g.map_off = -1; g.lda = nsrow; g.ldc = nsrow; g.K = W; g.nd1 = ct; g.nd2 = nsrow - J0 - W; g.atomic = 1;
-            route_gemm(g, gs, gb);
+            const int nscol = ncols(s);
+            if (nscol <= O0) continue;
+            trailing(s, O0, std::min(NB_OUTER, nscol - O0), nscol);
         }
         emit_update_launches(out, gs, gb, 1);
     }
@@ -313,7 +318,7 @@ bool build_host_plan(long long n, long long nsuper, const long long *super, cons
                 double tc = 0;
                 for (int i = 0; i < ncyc; i++) {
                     const int nscol = hp.super[v[i] + 1] - hp.super[v[i]];
-                    tc += std::max(((nscol + NB_OUTER - 1) / NB_OUTER) * tau, sn_flops[v[i]] / (hp.nranks * rate));
+                    tc += std::max(((nscol + NB_MID - 1) / NB_MID) * tau, sn_flops[v[i]] / (hp.nranks * rate));
                 }
                 std::vector<double> lvl(hp.nranks, 0.0);
                 if (assign) assign->assign(v.size(), -1);
@@ -329,7 +334,7 @@ bool build_host_plan(long long n, long long nsuper, const long long *super, cons
             double best = model(0, nullptr);
             while (ncyc < (int) v.size()) {
                 const int nscol = hp.super[v[ncyc] + 1] - hp.super[v[ncyc]];
-                if (nscol < 2 * NB_OUTER) break;
+                if (nscol < 2 * NB_MID) break;
                 const double t1 = model(ncyc + 1, nullptr);
                 if (t1 >= best) break;
                 best = t1; ncyc++;
@@ -390,9 +395,9 @@ bool build_host_plan(long long n, long long nsuper, const long long *super, cons
                 const int *rows = hp.ls.data() + hp.pi[u.d] + u.p0;
                 int jlo = 0;
                 while (jlo < u.nd1) {
-                    const int blk = (rows[jlo] - k1) / NB_OUTER;
+                    const int blk = (rows[jlo] - k1) / NB_MID;
                     int jhi = jlo + 1;
-                    while (jhi < u.nd1 && (rows[jhi] - k1) / NB_OUTER == blk) jhi++;
+                    while (jhi < u.nd1 && (rows[jhi] - k1) / NB_MID == blk) jhi++;
                     if (blk % hp.nranks == hp.rank) {
                         GemmJob h = g;
                         h.a_off += jlo; h.map_off += jlo; h.nd1 = jhi - jlo; h.nd2 = u.nd2 - jlo;
@@ -441,16 +446,16 @@ bool build_host_plan(long long n, long long nsuper, const long long *super, cons
                 if (hp.owner[sn] >= 0) continue;
                 const int nscol = hp.super[sn + 1] - hp.super[sn];
                 const long long nsrow = hp.pi[sn + 1] - hp.pi[sn];
-                const int npan = (nscol + NB_OUTER - 1) / NB_OUTER;
+                const int npan = (nscol + NB_MID - 1) / NB_MID;
                 std::vector<int> one{sn};
-                auto panel_w = [&](int J) { return std::min(NB_OUTER, nscol - J * NB_OUTER); };
+                auto panel_w = [&](int J) { return std::min(NB_MID, nscol - J * NB_MID); };
                 auto factor_panel = [&](int J) {
-                    const int J0 = J * NB_OUTER, W = panel_w(J);
+                    const int J0 = J * NB_MID, W = panel_w(J);
                     append_factor_jobs(hp, one, -1, hp, false, J0);
                     hp.my_flops += (double) W * W * W / 3.0 + (double) W * W * (nsrow - J0 - W);
                 };
                 auto update_block = [&](int J, int J1) {       // block J1 -= panel J contribution
-                    const int J0 = J * NB_OUTER, C0 = J1 * NB_OUTER, W = panel_w(J), W1 = panel_w(J1);
+                    const int J0 = J * NB_MID, C0 = J1 * NB_MID, W = panel_w(J), W1 = panel_w(J1);
                     GemmJob g{};
                     g.a_off = hp.px[sn] + C0 + (long long) J0 * nsrow;
                     g.c_off = hp.px[sn] + C0 + (long long) C0 * nsrow;
@@ -467,7 +472,7 @@ bool build_host_plan(long long n, long long nsuper, const long long *super, cons
                     step_mid = (int) hp.launches.size();
                     for (int J1 = J + 2; J1 < npan; J1++) if (J1 % hp.nranks == hp.rank) update_block(J, J1);
                     emit_update_launches(hp, gs, gb, 1);
-                    if (J + 1 < npan) close_step(step_begin, (J + 1) % hp.nranks, hp.px[sn] + (long long) (J + 1) * NB_OUTER * nsrow, (long long) panel_w(J + 1) * nsrow, l);
+                    if (J + 1 < npan) close_step(step_begin, (J + 1) % hp.nranks, hp.px[sn] + (long long) (J + 1) * NB_MID * nsrow, (long long) panel_w(J + 1) * nsrow, l);
                     else close_step(step_begin, -1, 0, 0, l);
                 }
             }

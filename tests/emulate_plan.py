@@ -6,7 +6,7 @@ import numpy as np
 from conftest import B200_LIB
 
 L_GEMM_BIG, L_GEMM_SMALL, L_POTRF, L_TRSM, L_TRSM_TC = range(5)
-NB_OUTER = 256
+NB_MID = 256
 
 
 def export_plan(n, super_, pi, px, s, nranks=1, rank=0):
@@ -46,7 +46,7 @@ def assemble(plan, super_, pi, px, s, S_lower, Lx, beta=0.0):
         rows = s[pi[sn]: pi[sn + 1]]; nsrow = len(rows)
         for k in range(k1, k2):
             o = plan["owner"][sn]
-            if plan["nranks"] > 1 and (o != plan["rank"] if o >= 0 else ((k - k1) // NB_OUTER) % plan["nranks"] != plan["rank"]):
+            if plan["nranks"] > 1 and (o != plan["rank"] if o >= 0 else ((k - k1) // NB_MID) % plan["nranks"] != plan["rank"]):
                 continue
             for p in range(Sp[k], Sp[k + 1]):
                 i = Si[p]
