@@ -9,6 +9,10 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <thread>
+#include <condition_variable>
+#include <deque>
+#include <atomic>
 #include <string>
 #include <vector>
 #include <algorithm>
@@ -33,6 +37,33 @@ struct DevJobs {
     PanelJob *potrf_jobs = nullptr, *trsm_jobs = nullptr; int *trsm_tiles = nullptr;
 };
 
+// Device-to-host streaming runs on a helper thread: cudaMemcpyAsync into cudaHostRegister'ed (4 KiB-paged) memory costs
+// the CALLING thread ~100 us per 50 MB (DMA descriptors), which would starve the latency-bound potrf/trsm launch chain.
+struct CopyJob { cudaEvent_t gate; const double *src; double *dst; size_t bytes; };
+struct Copier {
+    std::thread th; std::mutex mu; std::condition_variable cv; std::deque<CopyJob> q;
+    bool stop = false; std::atomic<int> pending{0}; std::atomic<int> failed{0};
+    int device = 0; cudaStream_t stream = nullptr;
+    void start(int dev, cudaStream_t s) { device = dev; stream = s; th = std::thread([this] { run(); }); }
+    void run()
+    {
+        cudaSetDevice(device);
+        for (;;) {
+            CopyJob j;
+            { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [this] { return stop || !q.empty(); }); if (q.empty()) return; j = q.front(); q.pop_front(); }
+            if (j.gate && cudaStreamWaitEvent(stream, j.gate, 0) != cudaSuccess) failed++;
+            if (cudaMemcpyAsync(j.dst, j.src, j.bytes, cudaMemcpyDeviceToHost, stream) != cudaSuccess) failed++;
+            pending--;
+        }
+    }
+    void push(const CopyJob &j) { pending++; { std::lock_guard<std::mutex> lk(mu); q.push_back(j); } cv.notify_one(); }
+    void drain() { while (pending.load() > 0) std::this_thread::yield(); }
+    void shutdown() { if (th.joinable()) { { std::lock_guard<std::mutex> lk(mu); stop = true; } cv.notify_one(); th.join(); } }
+};
+
+// parameters baked into the captured factorization graph
+struct FactorGraphKey { double beta0; double *host; int stype; const void *a[4]; const void *f[4]; };
+
 struct CscBuf { long long *p = nullptr, *i = nullptr, *nz = nullptr; double *x = nullptr; size_t capP = 0, capI = 0, capNz = 0, capX = 0; bool haveNz = false; };
 static void free_cscbuf(CscBuf *b) { if (!b) return; if (b->p) cudaFree(b->p); if (b->i) cudaFree(b->i); if (b->nz) cudaFree(b->nz); if (b->x) cudaFree(b->x); delete b; }
 
@@ -44,6 +75,10 @@ struct ssb200_plan {
     int *d_owner = nullptr;                  // sharded plans: owner rank per supernode (-1 = panel-cyclic)
     cudaStream_t copy_stream = nullptr;      // device-to-host streaming of finished supernodes
     cudaEvent_t copy_gate = nullptr, copy_done = nullptr;
+    std::vector<cudaEvent_t> copy_gates;     // one per copy-task group
+    cudaGraphExec_t fgraph = nullptr; FactorGraphKey fg_key{}; size_t fg_ev = 0; ssb_long fg_launches = 0;
+    std::vector<std::pair<int, size_t>> fg_marks;   // (launch index, event index) of the last enqueue / capture
+    Copier *copier = nullptr;
     int *d_super = nullptr, *d_ls = nullptr, *d_supermap = nullptr, *d_relmap = nullptr, *d_info = nullptr;
     long long *d_pi = nullptr, *d_px = nullptr;
     double *d_Lx = nullptr;
@@ -108,8 +143,11 @@ static void plan_free(ssb200_plan *p)
     for (void *q : ptrs) if (q) cudaFree(q);
     free_cscbuf(p->bufA); free_cscbuf(p->bufF);
     if (p->solve_graph) cudaGraphExecDestroy(p->solve_graph);
+    if (p->fgraph) cudaGraphExecDestroy(p->fgraph);
     if (p->h_info) cudaFreeHost(p->h_info);
     for (auto e : p->events) cudaEventDestroy(e);
+    if (p->copier) { p->copier->shutdown(); delete p->copier; }
+    for (auto e : p->copy_gates) cudaEventDestroy(e);
     if (p->copy_gate) cudaEventDestroy(p->copy_gate);
     if (p->copy_done) cudaEventDestroy(p->copy_done);
     if (p->copy_stream) cudaStreamDestroy(p->copy_stream);
@@ -482,6 +520,65 @@ static bool host_is_pinned(const void *ptr)
     return at.type == cudaMemoryTypeHost;
 }
 
+// Enqueue one whole factorization on the plan's stream: zero, assemble, every launch bracketed by timing events, the
+// device-to-host copies of finished ranges on the copy stream, and the read-back of the potrf info array.
+// capture == true: the calls are being recorded into a CUDA graph (copies are issued here, the copy stream joins the
+// capture through the gate events and is joined back at the end); otherwise the helper thread issues the copies.
+static int enqueue_factorization(ssb200_plan *p, double beta0, double *Lx_host, bool streaming, bool capture, int stop_level,
+                                 std::vector<std::pair<int, size_t>> &marks, size_t &ev)
+{
+    HostPlan &hp = p->hp;
+    const bool timing = !capture;      // events recorded by graph nodes cannot be used with cudaEventElapsedTime
+    marks.clear(); ev = 0;
+    if (timing) cudaEventRecord(get_event(p, ev), p->stream);                     // 0: start
+    ev++;
+    // zero all supernodes (:305-317); in pieces, a captured memset node does not take 2^32 bytes or more
+    for (size_t off = 0, tot = (size_t) hp.xsize * sizeof(double); off < tot; off += (size_t) 1 << 30)
+        CU_TRY(cudaMemsetAsync((char *) p->d_Lx + off, 0, std::min<size_t>((size_t) 1 << 30, tot - off), p->stream));
+    {
+        const long long g = (hp.nsuper + 255) / 256;
+        fill_int_kernel<<<(unsigned) g, 256, 0, p->stream>>>(p->d_info, hp.nsuper, INT_MAX);
+        p->stats.kernel_launches++;
+    }
+    if (scatter_A(p, beta0, 0, hp.n)) return SSB_CHOLMOD_GPU_PROBLEM;
+    if (timing) cudaEventRecord(get_event(p, ev), p->stream);                     // 1: assembled
+    ev++;
+    size_t ctask = 0, cgroup = 0;
+    bool copies_captured = false;
+    for (int l = 0; l < hp.nlevels && l < stop_level; l++) {
+        for (int t = hp.level_launch_begin[l]; t < hp.level_launch_begin[l + 1]; t++) {
+            const Launch &L = hp.launches[t];
+            if (timing) cudaEventRecord(get_event(p, ev), p->stream);
+            marks.push_back({t, ev}); ev++;
+            if (run_launch(p, L, p->jobs)) return SSB_CHOLMOD_GPU_PROBLEM;
+            if (streaming && ctask < hp.copy_tasks.size() && hp.copy_tasks[ctask].after_launch == t) {
+                // these ranges of Lx are final: copy them out behind this point of the compute stream
+                cudaEvent_t gate = p->copy_gates[cgroup++];
+                CU_TRY(cudaEventRecord(gate, p->stream));
+                if (capture) { CU_TRY(cudaStreamWaitEvent(p->copy_stream, gate, 0)); copies_captured = true; }
+                for (bool first = true; ctask < hp.copy_tasks.size() && hp.copy_tasks[ctask].after_launch == t; ctask++, first = false) {
+                    const CopyTask &ct = hp.copy_tasks[ctask];
+                    if (capture)
+                        CU_TRY(cudaMemcpyAsync(Lx_host + ct.off, p->d_Lx + ct.off, (size_t) ct.cnt * sizeof(double), cudaMemcpyDeviceToHost, p->copy_stream));
+                    else
+                        p->copier->push(CopyJob{first ? gate : nullptr, p->d_Lx + ct.off, Lx_host + ct.off, (size_t) ct.cnt * sizeof(double)});
+                }
+            }
+        }
+    }
+    if (timing) cudaEventRecord(get_event(p, ev), p->stream);
+    marks.push_back({-1, ev}); ev++;                                               // end of the compute chain
+    CU_TRY(cudaMemcpyAsync(p->h_info, p->d_info, hp.nsuper * sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+    if (capture && copies_captured) {                                              // join the copy stream back into the capture
+        CU_TRY(cudaEventRecord(p->copy_gate, p->copy_stream));
+        CU_TRY(cudaStreamWaitEvent(p->stream, p->copy_gate, 0));
+    }
+    if (timing) cudaEventRecord(get_event(p, ev), p->stream);
+    ev++;                                                                          // everything, copies included
+    CU_TRY(cudaGetLastError());
+    return 0;
+}
+
 static int factorize_impl(ssb200_plan *p, const double beta[2], int quick_return_if_not_posdef, ssb_long *minor_out, double *Lx_host)
 {
     if (!p) { set_error("null plan"); return SSB_CHOLMOD_INVALID; }
@@ -493,78 +590,103 @@ static int factorize_impl(ssb200_plan *p, const double beta[2], int quick_return
     p->factor_on_device = false;
     if (hp.nsuper == 0) { p->factor_on_device = true; return 0; }
     const double beta0 = beta ? beta[0] : 0.0;
-    size_t ev = 0;
-    cudaEventRecord(get_event(p, ev++), p->stream);                               // 0: start
-    CU_TRY(cudaMemsetAsync(p->d_Lx, 0, (size_t) hp.xsize * sizeof(double), p->stream));   // zero all supernodes (:305-317)
-    {
-        const long long g = (hp.nsuper + 255) / 256;
-        fill_int_kernel<<<(unsigned) g, 256, 0, p->stream>>>(p->d_info, hp.nsuper, INT_MAX);
-        p->stats.kernel_launches++;
-    }
-    if (scatter_A(p, beta0, 0, hp.n)) return SSB_CHOLMOD_GPU_PROBLEM;
-    cudaEventRecord(get_event(p, ev++), p->stream);                               // 1: assembled
     const char *stop = getenv("SSB200_DEBUG_STOP_LEVEL");                          // debugging aid: stop after this many levels
     const int stop_level = stop ? atoi(stop) : INT_MAX;
-    // every launch is bracketed by events on the plan's stream: (launch index, event index) pairs
-    std::vector<std::pair<int, size_t>> marks;
-    static int stream_d2h = -1;
+    (void) cudaGetLastError();                                                     // drop stale errors of earlier calls
+    static int stream_d2h = -1, use_graph = -2;
     if (stream_d2h < 0) { const char *v = getenv("SSB200_STREAM_D2H"); stream_d2h = (v && atoi(v) == 0) ? 0 : 1; }
+    if (use_graph == -2) { const char *v = getenv("SSB200_FACTOR_GRAPH"); use_graph = v ? (atoi(v) ? 1 : 0) : -1; }
     const bool streaming = Lx_host && stream_d2h && stop_level == INT_MAX && host_is_pinned(Lx_host);
-    size_t ctask = 0;
-    for (int l = 0; l < hp.nlevels && l < stop_level; l++) {
-        for (int t = hp.level_launch_begin[l]; t < hp.level_launch_begin[l + 1]; t++) {
-            const Launch &L = hp.launches[t];
-            cudaEventRecord(get_event(p, ev), p->stream); marks.push_back({t, ev}); ev++;
-            if (run_launch(p, L, p->jobs)) return SSB_CHOLMOD_GPU_PROBLEM;
-            if (streaming && ctask < hp.copy_tasks.size() && hp.copy_tasks[ctask].after_launch == t) {
-                // these ranges of Lx are final: copy them out behind the compute stream
-                CU_TRY(cudaEventRecord(p->copy_gate, p->stream));
-                CU_TRY(cudaStreamWaitEvent(p->copy_stream, p->copy_gate, 0));
-                for (; ctask < hp.copy_tasks.size() && hp.copy_tasks[ctask].after_launch == t; ctask++) {
-                    const CopyTask &ct = hp.copy_tasks[ctask];
-                    CU_TRY(cudaMemcpyAsync(Lx_host + ct.off, p->d_Lx + ct.off, (size_t) ct.cnt * sizeof(double), cudaMemcpyDeviceToHost, p->copy_stream));
-                }
-            }
-        }
+    // Graph replay by default when the factor streams to the host: the ~2700 dependent launches then do not cross the PCIe
+    // link that the streaming saturates (+24 us per launch otherwise).  Resident factorizations keep the per-launch events
+    // (per-kernel statistics) unless SSB200_FACTOR_GRAPH=1.
+    const bool graph = stop_level == INT_MAX && (use_graph == 1 || (use_graph == -1 && streaming));
+    // everything the enqueue needs exists before a capture starts
+    while (p->events.size() < hp.launches.size() + 8) { cudaEvent_t e; CU_TRY(cudaEventCreate(&e)); p->events.push_back(e); }
+    {
+        size_t groups = 0; int last = -1;
+        for (const CopyTask &ct : hp.copy_tasks) if (ct.after_launch != last) { groups++; last = ct.after_launch; }
+        while (p->copy_gates.size() < groups) { cudaEvent_t e; CU_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); p->copy_gates.push_back(e); }
     }
-    cudaEventRecord(get_event(p, ev), p->stream); marks.push_back({-1, ev}); ev++;
-    CU_TRY(cudaGetLastError());
-    CU_TRY(cudaMemcpyAsync(p->h_info, p->d_info, hp.nsuper * sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+    if (streaming && !graph && !p->copier) { p->copier = new Copier(); p->copier->start(p->device, p->copy_stream); }
+
+    std::vector<std::pair<int, size_t>> &marks = p->fg_marks;
+    size_t ev = 0;
+    if (graph) {
+        // The whole factorization is one CUDA graph (thousands of small dependent launches; replaying it also keeps the
+        // launch chain off the PCIe link that the host streaming saturates).  Rebuilt when a baked-in parameter changes.
+        FactorGraphKey key; memset(&key, 0, sizeof(key));
+        key.beta0 = beta0; key.host = streaming ? Lx_host : nullptr; key.stype = p->stype;
+        key.a[0] = p->bufA->p; key.a[1] = p->bufA->i; key.a[2] = p->bufA->x; key.a[3] = p->bufA->haveNz ? p->bufA->nz : nullptr;
+        key.f[0] = p->bufF->p; key.f[1] = p->bufF->i; key.f[2] = p->bufF->x; key.f[3] = p->bufF->haveNz ? p->bufF->nz : nullptr;
+        if (!p->fgraph || memcmp(&key, &p->fg_key, sizeof(key)) != 0) {
+            if (p->fgraph) { cudaGraphExecDestroy(p->fgraph); p->fgraph = nullptr; }
+            CU_TRY(cudaStreamBeginCapture(p->stream, cudaStreamCaptureModeThreadLocal));
+            const int rc = enqueue_factorization(p, beta0, Lx_host, streaming, true, stop_level, marks, ev);
+            cudaGraph_t g = nullptr;
+            cudaError_t ce = cudaStreamEndCapture(p->stream, &g);
+            if (rc || ce != cudaSuccess) { if (g) cudaGraphDestroy(g); (void) cudaGetLastError(); if (!rc) set_error(std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce)); return SSB_CHOLMOD_GPU_PROBLEM; }
+            ce = cudaGraphInstantiate(&p->fgraph, g, 0);
+            cudaGraphDestroy(g);
+            if (ce != cudaSuccess) { p->fgraph = nullptr; set_error(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ce)); return SSB_CHOLMOD_GPU_PROBLEM; }
+            memcpy(&p->fg_key, &key, sizeof(key)); p->fg_ev = ev; p->fg_launches = p->stats.kernel_launches;
+        }
+        ev = p->fg_ev; p->stats.kernel_launches = p->fg_launches;
+        CU_TRY(cudaEventRecord(p->events[0], p->stream));
+        CU_TRY(cudaGraphLaunch(p->fgraph, p->stream));
+        CU_TRY(cudaEventRecord(p->events[1], p->stream));
+    } else {
+        if (enqueue_factorization(p, beta0, Lx_host, streaming, false, stop_level, marks, ev)) return SSB_CHOLMOD_GPU_PROBLEM;
+    }
     CU_TRY(cudaStreamSynchronize(p->stream));
-    // timings
+    // timings: events[0] start, [1] assembled, one per launch, end of compute (marks.back()), [ev-1] end of everything
     float ms = 0;
-    cudaEventElapsedTime(&ms, p->events[0], p->events[1]); p->stats.ms_assemble = ms;
-    p->stats.ms_update = p->stats.ms_factor = 0;
+    p->stats.ms_update = p->stats.ms_factor = p->stats.ms_assemble = 0;
     for (int k = 0; k < 6; k++) { p->stats.ms_kind[k] = 0; p->stats.flops_kind[k] = 0; p->stats.launches_kind[k] = 0; }
     p->launch_ms.assign(hp.launches.size(), 0.f);
-    for (size_t t = 0; t + 1 < marks.size(); t++) {
-        cudaEventElapsedTime(&ms, p->events[marks[t].second], p->events[marks[t + 1].second]);
-        const Launch &L = hp.launches[marks[t].first];
-        p->launch_ms[marks[t].first] = ms;
-        if (L.phase == 0) p->stats.ms_update += ms; else p->stats.ms_factor += ms;
-        p->stats.ms_kind[L.kind] += ms; p->stats.flops_kind[L.kind] += L.flops; p->stats.launches_kind[L.kind]++;
+    const size_t ev_compute_end = marks.back().second;
+    if (graph) {
+        // one replayed graph: only the total is known (copies to the host included)
+        cudaEventElapsedTime(&ms, p->events[0], p->events[1]); p->stats.ms_total = ms;
+        for (const Launch &L : hp.launches) { p->stats.flops_kind[L.kind] += L.flops; p->stats.launches_kind[L.kind]++; }
+    } else {
+        cudaEventElapsedTime(&ms, p->events[0], p->events[1]); p->stats.ms_assemble = ms;
+        for (size_t t = 0; t + 1 < marks.size(); t++) {
+            cudaEventElapsedTime(&ms, p->events[marks[t].second], p->events[marks[t + 1].second]);
+            const Launch &L = hp.launches[marks[t].first];
+            p->launch_ms[marks[t].first] = ms;
+            if (L.phase == 0) p->stats.ms_update += ms; else p->stats.ms_factor += ms;
+            p->stats.ms_kind[L.kind] += ms; p->stats.flops_kind[L.kind] += L.flops; p->stats.launches_kind[L.kind]++;
+        }
+        cudaEventElapsedTime(&ms, p->events[0], p->events[ev_compute_end]); p->stats.ms_total = ms;
     }
     int status = 0;
     int sfail = -1;
     for (long long s = 0; s < hp.nsuper; s++) if (p->h_info[s] != INT_MAX) { sfail = (int) s; break; }
+    if (streaming && !graph) {
+        p->copier->drain();                             // every copy has been enqueued on the copy stream
+        if (p->copier->failed.load()) { p->copier->failed = 0; set_error("device-to-host streaming failed"); return SSB_CHOLMOD_GPU_PROBLEM; }
+    }
     if (sfail >= 0) {
         status = SSB_CHOLMOD_NOT_POSDEF;
         ssb_long minor = hp.n;
+        CU_TRY(cudaStreamSynchronize(p->copy_stream));
         if (handle_not_posdef(p, sfail, p->h_info[sfail], beta0, quick_return_if_not_posdef, &minor)) return SSB_CHOLMOD_GPU_PROBLEM;
         if (minor_out) *minor_out = minor;
     }
-    cudaEventRecord(get_event(p, ev), p->stream);
-    CU_TRY(cudaStreamSynchronize(p->stream));
-    cudaEventElapsedTime(&ms, p->events[0], p->events[ev]); p->stats.ms_total = ms;
     p->stats.kernel_launches_total += p->stats.kernel_launches;
     p->factor_on_device = true;
     p->winv_valid = (status == 0);
     if (Lx_host) {
         if (streaming && status == 0) {
             // only the tail of the copy stream is still exposed
-            CU_TRY(cudaEventRecord(p->copy_done, p->copy_stream));
-            CU_TRY(cudaStreamSynchronize(p->copy_stream));
-            cudaEventElapsedTime(&ms, p->events[ev], p->copy_done); p->stats.ms_d2h = ms > 0 ? ms : 0;
+            if (graph) {
+                p->stats.ms_d2h = 0;                     // inside the graph's total
+            } else {
+                CU_TRY(cudaEventRecord(p->copy_done, p->copy_stream));
+                CU_TRY(cudaStreamSynchronize(p->copy_stream));
+                cudaEventElapsedTime(&ms, p->events[ev_compute_end], p->copy_done); p->stats.ms_d2h = ms > 0 ? ms : 0;
+            }
         } else {
             CU_TRY(cudaStreamSynchronize(p->copy_stream));
             int r2 = ssb200_download_L(p, Lx_host);        // not positive definite (rare) or pageable host memory: one plain copy
@@ -787,7 +909,8 @@ static CacheEntry *cache_find(const ssb_cholmod_factor *L)
     return nullptr;
 }
 
-static void unpin(CacheEntry *e) { if (e->pinned_ptr) { if (cudaHostUnregister(e->pinned_ptr) != cudaSuccess) (void) cudaGetLastError(); e->pinned_ptr = nullptr; e->pinned_bytes = 0; } }
+static void unpin(CacheEntry *e) { if (e->plan && e->plan->fgraph) { cudaGraphExecDestroy(e->plan->fgraph); e->plan->fgraph = nullptr; }   // its copy nodes point into this registration
+    if (e->pinned_ptr) { if (cudaHostUnregister(e->pinned_ptr) != cudaSuccess) (void) cudaGetLastError(); e->pinned_ptr = nullptr; e->pinned_bytes = 0; } }
 static void cache_drop(CacheEntry *e) { unpin(e); plan_free(e->plan); g_cache.erase(g_cache.begin() + (e - g_cache.data())); }
 
 // Page-lock the caller's L->x so the factor streams back at PCIe speed.  Best effort: a failure only costs bandwidth.

@@ -75,7 +75,7 @@ struct Launch {
 
 // Device-to-host streaming of the factor: the Lx range [off, off+cnt) is final once launch `after_launch` has run.
 struct CopyTask { int after_launch; long long off, cnt; };
-constexpr int COPY_FLUSH_LEVEL = 8;  // supernodes up to this etree level are copied in merged ranges after that level
+constexpr int COPY_MAX_PANEL_SNODES = 40;  // at most this many supernodes (the ones nearest the root) stream panel by panel
 
 // One step of the distributed schedule.  Every rank walks the same step list (same broadcasts); only the launches differ.
 //   [wait for every outstanding broadcast, if wait_remote]  launches [begin, mid)  [start the broadcast, asynchronously]

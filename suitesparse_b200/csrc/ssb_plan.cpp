@@ -367,6 +367,19 @@ bool build_host_plan(long long n, long long nsuper, const long long *super, cons
     std::vector<GemmJob> gs, gb;
     std::vector<int> nodes;
     int step_begin = 0;
+    // Host streaming: every copy is a host-side call between kernel launches, so only the few supernodes near the root are
+    // streamed panel by panel; everything up to the `flush` level goes out in merged contiguous ranges right after that
+    // level (the lowest level above which at most COPY_MAX_PANEL_SNODES supernodes remain).
+    int flush = hp.nlevels - 1;
+    {
+        int above = 0;
+        for (int l = hp.nlevels - 1; l >= 0; l--) {
+            above += hp.level_ptr[l + 1] - hp.level_ptr[l];
+            if (above > COPY_MAX_PANEL_SNODES) { flush = l; break; }
+            flush = l - 1;
+        }
+        flush = std::max(0, std::min(flush, hp.nlevels - 1));
+    }
     for (int l = 0; l < hp.nlevels; l++) {
         hp.level_launch_begin[l] = (int) hp.launches.size();
         size_t ubeg = upos;
@@ -419,7 +432,6 @@ bool build_host_plan(long long n, long long nsuper, const long long *super, cons
             nodes.push_back(sn);
             hp.my_flops += nscol * nscol * nscol / 3.0 + nscol * nscol * (nsrow - nscol);
         }
-        const int flush = std::min(COPY_FLUSH_LEVEL, hp.nlevels - 1);
         if (!nodes.empty()) append_factor_jobs(hp, nodes, -1, hp, /*panel_copies=*/hp.nranks == 1 && l > flush);
         if (hp.nranks == 1 && l == flush && !hp.launches.empty()) {
             // every supernode of level <= flush is final: merge consecutive indices into contiguous Lx ranges
