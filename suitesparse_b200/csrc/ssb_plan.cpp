@@ -330,14 +330,15 @@ bool build_host_plan(long long n, long long nsuper, const long long *super, cons
                 }
                 return tc + *std::max_element(lvl.begin(), lvl.end()) / rate;
             };
+            // every prefix of the flops-sorted list is tried: turning only ONE of several equally heavy supernodes cyclic
+            // does not shorten the level, turning all of them does
             int ncyc = 0;
             double best = model(0, nullptr);
-            while (ncyc < (int) v.size()) {
-                const int nscol = hp.super[v[ncyc] + 1] - hp.super[v[ncyc]];
+            for (int c = 1; c <= (int) v.size(); c++) {
+                const int nscol = hp.super[v[c - 1] + 1] - hp.super[v[c - 1]];
                 if (nscol < 2 * NB_MID) break;
-                const double t1 = model(ncyc + 1, nullptr);
-                if (t1 >= best) break;
-                best = t1; ncyc++;
+                const double t1 = model(c, nullptr);
+                if (t1 < best) { best = t1; ncyc = c; }
             }
             std::vector<int> assign;
             model(ncyc, &assign);
