@@ -9,6 +9,7 @@ Kernels and collectives share one CUDA stream, so no host synchronisation happen
 """
 from __future__ import annotations
 import ctypes as C
+import os
 import numpy as np
 from . import plain
 
@@ -65,13 +66,69 @@ class ShardedFactor:
         L.ssb200_dist_flops(self.plan.h, C.byref(mine), C.byref(total))
         self.my_flops, self.total_flops = mine.value, total.value
 
+    def shared_host_factor(self, name: str = "ssb200_Lx"):
+        """Host L->x in POSIX shared memory, mapped by every rank; each rank page-locks only the ranges it is the broadcast
+        source of (its share of the factor) and copies exactly those out over its own PCIe link, instead of rank 0 pulling
+        all of L.  Rank 0 is the application: after the factorization its view holds the whole factor.
+        Returns a torch tensor of xsize doubles, or None (on every rank) if the shared buffer could not be set up."""
+        torch, dist = self.torch, self.dist
+        path = f"/dev/shm/{name}_{os.environ.get('MASTER_PORT', '0')}"
+        nbytes = max(self.xsize, 1) * 8
+        ok = 1
+        t = None
+        try:
+            if self.rank == 0:
+                with open(path, "wb") as f:
+                    f.truncate(nbytes)
+            if self.world > 1:
+                dist.barrier()
+            t = torch.from_file(path, shared=True, size=max(self.xsize, 1), dtype=torch.float64)
+            # merge this rank's source ranges, round them to pages, pin them
+            mine = sorted((off, off + cnt) for (src, off, cnt, _) in self.steps if src == self.rank and cnt > 0)
+            merged = []
+            for a, b in mine:
+                a8, b8 = (a * 8) // 4096 * 4096, min(nbytes, -(-(b * 8) // 4096) * 4096)
+                if merged and a8 <= merged[-1][1]:
+                    merged[-1][1] = max(merged[-1][1], b8)
+                else:
+                    merged.append([a8, b8])
+            base = t.data_ptr()
+            self._pinned = []
+            for a8, b8 in merged:
+                rc = torch.cuda.cudart().cudaHostRegister(base + a8, b8 - a8, 0)
+                if int(rc) != 0:
+                    ok = 0
+                    break
+                self._pinned.append(base + a8)
+        except Exception:
+            ok = 0
+            try:
+                torch.cuda.synchronize()
+            except Exception:
+                pass
+        if self.world > 1:
+            flag = torch.tensor([ok], dtype=torch.int32, device=self.device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            ok = int(flag.item())
+        if self.rank == 0 and os.path.exists(path):
+            os.unlink(path)                               # the mappings keep it alive
+        if not ok:
+            for ptr in getattr(self, "_pinned", []):
+                torch.cuda.cudart().cudaHostUnregister(ptr)
+            self._pinned = []
+            return None
+        self._shared = t
+        return t
+
     def upload_A(self, A_lower, F=None):
         return self.plan.upload_A(A_lower, F)
 
-    def factorize_resident(self, beta: float = 0.0, host_out=None):
+    def factorize_resident(self, beta: float = 0.0, host_out=None, host_shared: bool = False):
         """Returns (status, minor): status 0 ok, 1 not positive definite (every rank gets the same answer).
         host_out: pinned host tensor of xsize doubles (or None).  A range of L is final on every rank right after its
-        broadcast, so it is copied to host_out on a second stream while the factorization continues."""
+        broadcast, so it is copied to host_out on a second stream while the factorization continues.
+        host_shared: host_out is the same shared-memory buffer on every rank (shared_host_factor()): each rank copies
+        only the ranges it is the source of, as soon as it has finished them."""
         torch, dist, L, h = self.torch, self.dist, self.lib, self.plan.h
         b = (C.c_double * 2)(beta, 0.0)
         if host_out is not None and self._copy_stream is None:
@@ -101,7 +158,12 @@ class ShardedFactor:
                         with torch.cuda.stream(self.comm_stream):
                             w = dist.broadcast(self.Lx[off:off + cnt], src, async_op=True)
                         pending.append((w, off, cnt))
-                    if host_out is not None:
+                    if host_out is not None and host_shared:
+                        if src == self.rank:              # final here since the launches above: no need to wait for the transfer
+                            self._copy_stream.wait_stream(self.stream)
+                            with torch.cuda.stream(self._copy_stream):
+                                host_out[off:off + cnt].copy_(self.Lx[off:off + cnt], non_blocking=True)
+                    elif host_out is not None:
                         # the range is final everywhere once its broadcast has landed: stream it to the host
                         with torch.cuda.stream(self._copy_stream):
                             if self.world > 1 and do_comm:
@@ -126,7 +188,10 @@ class ShardedFactor:
                 self.plan._check(L.ssb200_dist_zero_from(h, minor))
                 if host_out is not None:
                     self._copy_stream.synchronize()
-                    host_out.copy_(self.Lx[:self.xsize])
+                    if not host_shared or self.rank == 0:
+                        host_out[:self.xsize].copy_(self.Lx[:self.xsize])
+                    if host_shared and self.world > 1:
+                        dist.barrier()
                 return 1, minor
         if host_out is not None:
             if self.world == 1:                           # nothing is broadcast with one rank: plain copy at the end
@@ -134,6 +199,8 @@ class ShardedFactor:
                     self._copy_stream.wait_stream(self.stream)
                     host_out[:self.xsize].copy_(self.Lx[:self.xsize], non_blocking=True)
             self._copy_stream.synchronize()
+            if host_shared and self.world > 1:
+                dist.barrier()                            # every rank's share has landed in the shared buffer
         return 0, self.n
 
     def download_L(self, out=None):
