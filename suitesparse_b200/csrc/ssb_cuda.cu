@@ -123,6 +123,8 @@ static int configure_kernels_once()
     cudaError_t e2 = cudaFuncSetAttribute(gemm_nt_sub_kernel<64, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) gemm_smem_bytes<64, 16>());
     cudaError_t e3 = cudaFuncSetAttribute(gemm_nt_sub_kernel<128, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) gemm_smem_bytes<128, 32>());
     if (e3 != cudaSuccess) e1 = e3;
+    cudaError_t e5 = cudaFuncSetAttribute(potrf_block_kernel2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) potrf2_smem_bytes());
+    if (e5 != cudaSuccess) e1 = e5;
     cudaError_t e4 = cudaFuncSetAttribute(trsm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) trsm_tc_smem_bytes());
     if (e4 != cudaSuccess) e1 = e4;
     if (e1 != cudaSuccess || e2 != cudaSuccess) { set_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : e2)); return SSB_CHOLMOD_GPU_PROBLEM; }
@@ -427,7 +429,14 @@ static int run_launch(ssb200_plan *p, const Launch &L, const DevJobs &dj)
         gemm_nt_sub_kernel<64, 16><<<L.ntiles, gemm_threads<64>(), gemm_smem_bytes<64, 16>(), p->stream>>>(dj.gemm_jobs + L.job0, dj.gemm_tiles + L.tile0, p->d_Lx, p->d_relmap);
         break;
     case L_POTRF:
-        potrf_block_kernel<<<L.njobs, POTRF_THREADS, 0, p->stream>>>(dj.potrf_jobs + L.job0, p->d_Lx, p->d_info, p->d_winv);
+    {
+        // version 2 (16-column sub-panels, warp-shuffle diagonal) measured SLOWER on B200 (59 vs 46 ms at lap7 128^3): the
+        // shuffle chains are longer than version 1's one barrier per column.  Kept for experiments: SSB200_POTRF_V2=1.
+        static int v1 = -1;
+        if (v1 < 0) { const char *v = getenv("SSB200_POTRF_V2"); v1 = (v && atoi(v)) ? 0 : 1; }
+        if (v1) potrf_block_kernel<<<L.njobs, POTRF_THREADS, 0, p->stream>>>(dj.potrf_jobs + L.job0, p->d_Lx, p->d_info, p->d_winv);
+        else potrf_block_kernel2<<<L.njobs, POTRF_THREADS, potrf2_smem_bytes(), p->stream>>>(dj.potrf_jobs + L.job0, p->d_Lx, p->d_info, p->d_winv);
+    }
         break;
     case L_TRSM:
         trsm_rows_kernel<<<L.ntiles, TRSM_ROWS, 0, p->stream>>>(dj.trsm_jobs + L.job0, dj.trsm_tiles + L.tile0, p->d_Lx);

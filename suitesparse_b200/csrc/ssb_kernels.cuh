@@ -328,6 +328,149 @@ __global__ void __launch_bounds__(POTRF_THREADS) potrf_block_kernel(const PanelJ
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// diagonal block Cholesky, version 2: blocked by 16-column sub-panels so that the column-by-column part has NO block
+// barriers.  Per sub-panel: (1) ONE warp factorizes the 16x16 diagonal sub-block in registers with shuffles - lanes 0..15
+// hold its rows, lanes 16..31 hold the rows of its inverse, built by the same elimination; (2) all threads bring the rows
+// below up to date (R <- R * D^{-T} with the 16x16 inverse); (3) rank-16 update of the rest of the tile.  Then W = L^{-1}
+// is assembled block by block from the four 16x16 inverses.  ~4x fewer serialized steps than version 1.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int POTRF2_LDT = NB_INNER + 1;
+constexpr size_t potrf2_smem_bytes() { return (size_t) (2 * NB_INNER * POTRF2_LDT + 4 * 16 * 17 + 16 * 17) * sizeof(double); }
+
+__global__ void __launch_bounds__(POTRF_THREADS) potrf_block_kernel2(const PanelJob *__restrict__ jobs, double *__restrict__ Lx,
+                                                                    int *__restrict__ info, double *__restrict__ winv)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *T = reinterpret_cast<double *>(smem_raw);               // T[i*LDT + j], lower part of the tile
+    double *Wf = T + NB_INNER * POTRF2_LDT;                         // W[i*LDT + j]
+    double *Dinv = Wf + NB_INNER * POTRF2_LDT;                      // Dinv[p][a*17 + b]
+    double *Sb = Dinv + 4 * 16 * 17;                                // scratch block
+    __shared__ int failcol;
+    constexpr int LDT = POTRF2_LDT;
+    const PanelJob job = jobs[blockIdx.x];
+    const int w = job.w, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long lda = job.lda;
+    const bool want_inv = job.winv_slot >= 0;
+    double *__restrict__ A = Lx + job.x_off;
+    // tile, padded with the identity beyond w (the padded part factorizes trivially)
+    for (int e = tid; e < NB_INNER * NB_INNER; e += POTRF_THREADS) {
+        const int i = e & 63, j = e >> 6;
+        T[i * LDT + j] = (i < w && j < w && i >= j) ? A[i + j * lda] : ((i == j) ? 1.0 : 0.0);
+        Wf[i * LDT + j] = 0.0;
+    }
+    if (tid == 0) failcol = NB_INNER;
+    __syncthreads();
+    for (int p = 0; p < 4; p++) {
+        const int c0 = 16 * p;
+        if (c0 >= w) break;                                         // uniform
+        if (warp == 0) {
+            const int l = lane & 15;
+            const bool isY = lane >= 16;
+            double a[16];
+#pragma unroll
+            for (int c = 0; c < 16; c++) a[c] = isY ? ((c == l) ? 1.0 : 0.0) : ((c <= l) ? T[(c0 + l) * LDT + c0 + c] : 0.0);
+            int bad = NB_INNER;
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                double d = __shfl_sync(0xffffffffu, a[j], j);       // pivot, from the lane that holds row j of the block
+                if (!(d > 0.0)) { bad = min(bad, c0 + j); d = 1.0; }
+                const double rinv = rsqrt(d);
+                if (!isY) a[j] = (l == j) ? d * rinv : a[j] * rinv; // column j of L (zero above the diagonal)
+                const double lj = __shfl_sync(0xffffffffu, a[j], l);    // L(l,j) for this lane's row, also for the inverse lanes
+#pragma unroll
+                for (int k = 0; k < 16; k++) {
+                    if (k > j) {                                    // compile-time after unrolling
+                        const double lkj = __shfl_sync(0xffffffffu, a[j], k);
+                        if (!isY && l >= k) a[k] -= lj * lkj;
+                    }
+                }
+                if (isY && l == j) {
+#pragma unroll
+                    for (int c = 0; c < 16; c++) a[c] *= rinv;      // Y(j,:) /= L(j,j)
+                }
+#pragma unroll
+                for (int c = 0; c < 16; c++) {
+                    if (c <= j) {                                   // compile-time after unrolling
+                        const double yjc = __shfl_sync(0xffffffffu, a[c], 16 + j);
+                        if (isY && l > j) a[c] -= lj * yjc;         // Y(l,:) -= L(l,j) Y(j,:)
+                    }
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 16; c++) {
+                if (!isY) { if (c <= l) T[(c0 + l) * LDT + c0 + c] = a[c]; }
+                else Dinv[p * 272 + l * 17 + c] = (c <= l) ? a[c] : 0.0;
+            }
+            if (lane == 0 && bad < NB_INNER) failcol = min(failcol, bad);
+        }
+        __syncthreads();
+        const int r0 = c0 + 16, nrows = NB_INNER - r0;
+        if (nrows > 0) {
+            // (2) R <- R * D^{-T}: new(r,c) = sum_{k<=c} R(r,k) Dinv(c,k)
+            double nv[3];
+#pragma unroll
+            for (int q = 0; q < 3; q++) {
+                const int e = tid + q * POTRF_THREADS;
+                nv[q] = 0.0;
+                if (e < nrows * 16) {
+                    const int r = r0 + (e >> 4), c = e & 15;
+                    double acc = 0.0;
+                    for (int k = 0; k <= c; k++) acc += T[r * LDT + c0 + k] * Dinv[p * 272 + c * 17 + k];
+                    nv[q] = acc;
+                }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int q = 0; q < 3; q++) {
+                const int e = tid + q * POTRF_THREADS;
+                if (e < nrows * 16) T[(r0 + (e >> 4)) * LDT + c0 + (e & 15)] = nv[q];
+            }
+            __syncthreads();
+            // (3) rank-16 update of the rest of the tile (lower part)
+            for (int e = tid; e < nrows * nrows; e += POTRF_THREADS) {
+                const int r = r0 + e % nrows, c = r0 + e / nrows;
+                if (r >= c) {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int k = 0; k < 16; k++) acc += T[r * LDT + c0 + k] * T[c * LDT + c0 + k];
+                    T[r * LDT + c] -= acc;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    // L goes back to Lx
+    for (int e = tid; e < NB_INNER * NB_INNER; e += POTRF_THREADS) {
+        const int i = e & 63, j = e >> 6;
+        if (i < w && j < w && i >= j) A[i + j * lda] = T[i * LDT + j];
+    }
+    if (tid == 0 && failcol < w) atomicMin(&info[job.snode], job.col0 + failcol + 1);
+    if (!want_inv) return;
+    // W = L^{-1}: diagonal 16x16 blocks are Dinv; W(i,q) = -Dinv_i * sum_{k=q}^{i-1} L(i,k) W(k,q), block column by block column
+    {
+        const int a = tid >> 4, b = tid & 15;                       // one thread per entry of a 16x16 block
+        for (int pb = 0; pb < 4; pb++) Wf[(16 * pb + a) * LDT + 16 * pb + b] = Dinv[pb * 272 + a * 17 + b];
+        __syncthreads();
+        for (int q = 0; q < 3; q++) {
+            for (int i = q + 1; i < 4; i++) {
+                double acc = 0.0;
+                for (int k = q; k < i; k++)
+#pragma unroll
+                    for (int t = 0; t < 16; t++) acc += T[(16 * i + a) * LDT + 16 * k + t] * Wf[(16 * k + t) * LDT + 16 * q + b];
+                Sb[a * 17 + b] = acc;
+                __syncthreads();
+                double v = 0.0;
+                for (int t = 0; t <= a; t++) v += Dinv[i * 272 + a * 17 + t] * Sb[t * 17 + b];
+                Wf[(16 * i + a) * LDT + 16 * q + b] = -v;
+                __syncthreads();
+            }
+        }
+    }
+    double *__restrict__ W = winv + (long long) job.winv_slot * (NB_INNER * NB_INNER);
+    for (int e = tid; e < NB_INNER * NB_INNER; e += POTRF_THREADS) W[e] = Wf[(e & 63) * LDT + (e >> 6)];
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // rows below the diagonal block:  B <- B * L11^{-T}.  One CTA = TRSM_ROWS rows, one thread per row, the row kept in
 // registers (NC = compile-time bound on the block width), L11 broadcast from shared memory.
 // ------------------------------------------------------------------------------------------------------------------

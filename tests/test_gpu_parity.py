@@ -237,3 +237,56 @@ def test_stale_host_registration_is_detected():
         assert persuper_relerr(f["px"], f["x"], Lo) < TOL_L, f"repetition {rep}"
         ch.free_sparse(S2)
         ch.free_factor(L)                                   # no cholmod_l_gpu_deallocate: the cache keeps the stale pin
+
+
+def test_solve_leading_dimension_and_many_rhs():
+    """X with leading dimension d > nrow and several right-hand sides, through the drop-in solve symbols
+    (t_cholmod_super_solve.c:132-218,334-410 are the reference's nrhs > 1 branches)."""
+    from suitesparse_b200 import gen, cholmod_host as H
+    from oracle import oracle
+    ch = H.Cholmod(gpu=True)
+    A, p = gen.make_problem("lap7", 11)
+    S = ch.sparse(A, +1); L = ch.analyze(S, p)
+    assert ch.factorize(S, L) == 1
+    f = ch.factor_arrays(L); n = f["n"]; nrhs = 5; d = n + 7
+    rng = np.random.default_rng(42)
+    buf = np.full((d, nrhs), np.nan, order="F"); buf[:n, :] = rng.standard_normal((n, nrhs))
+    ref = buf[:n, :].copy()
+    X = H.Dense(); X.nrow = n; X.ncol = nrhs; X.d = d; X.nzmax = d * nrhs; X.x = buf.ctypes.data; X.xtype = H.CHOLMOD_REAL
+    E = np.zeros(nrhs * max(1, int(f["maxesize"]))); Ed = ch.dense(E)
+    assert ch.hot("cholmod_l_super_lsolve")(L, C.byref(X), C.byref(Ed), C.byref(ch.cm)) == 1
+    y = oracle.lsolve(f["super"], f["pi"], f["px"], f["s"], f["x"], ref)
+    assert np.abs(buf[:n, :] - y).max() < 1e-10 * np.abs(y).max()
+    assert np.isnan(buf[n:, :]).all()                                   # padding rows untouched
+    assert ch.hot("cholmod_l_super_ltsolve")(L, C.byref(X), C.byref(Ed), C.byref(ch.cm)) == 1
+    y = oracle.lsolve(f["super"], f["pi"], f["px"], f["s"], f["x"], y, transpose=True)
+    assert np.abs(buf[:n, :] - y).max() < 1e-10 * np.abs(y).max()
+    ch.free_factor(L)
+
+
+def test_gpu_resource_functions_and_env_switch(monkeypatch):
+    """cholmod_l_gpu_* (GPU/cholmod_gpu.c:71,170,208,255,364) and CHOLMOD_USE_GPU=0 (no CPU path inside this library)."""
+    from suitesparse_b200 import gen, cholmod_host as H
+    ch = H.Cholmod(gpu=True)
+    lib = ch.b200
+    tot, av = C.c_size_t(0), C.c_size_t(0)
+    lib.cholmod_l_gpu_memorysize.argtypes = [C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.c_void_p]
+    assert lib.cholmod_l_gpu_memorysize(C.byref(tot), C.byref(av), C.byref(ch.cm)) == 0     # 0 = no problem, as in the reference
+    assert tot.value > 100e9 and 0 < av.value <= tot.value
+    lib.cholmod_l_gpu_probe.argtypes = [C.c_void_p]
+    assert lib.cholmod_l_gpu_probe(C.byref(ch.cm)) == 1
+    A, p = gen.make_problem("lap7", 6)
+    S = ch.sparse(A, +1); L = ch.analyze(S, p)
+    assert ch.factorize(S, L) == 1
+    lib.cholmod_l_gpu_deallocate.argtypes = [C.c_void_p]
+    assert lib.cholmod_l_gpu_deallocate(C.byref(ch.cm)) == 0                                # drops the cached plan
+    from suitesparse_b200 import plain
+    assert plain.plan_of_factor(L) is None
+    x = ch.solve(L, np.ones(A.shape[0]))                                                    # plan rebuilt, L->x re-uploaded
+    Af = A + sp.triu(A, 1).T
+    assert np.linalg.norm(Af @ x - 1.0) / np.sqrt(A.shape[0]) < TOL_RESID
+    monkeypatch.setenv("CHOLMOD_USE_GPU", "0")
+    assert ch.factorize(S, L) == 0 and ch.cm.status == H.CHOLMOD_GPU_PROBLEM                # refuses, does not fall back
+    monkeypatch.delenv("CHOLMOD_USE_GPU")
+    assert ch.factorize(S, L) == 1 and ch.cm.status == 0
+    ch.free_factor(L)
