@@ -11,6 +11,7 @@
 #include <numeric>
 #include <cstring>
 #include <cstdlib>
+#include <map>
 
 namespace ssb {
 
@@ -366,6 +367,7 @@ bool build_host_plan(long long n, long long nsuper, const long long *super, cons
     hp.level_launch_begin.assign(hp.nlevels + 1, 0);
     size_t upos = 0;
     std::vector<GemmJob> gs, gb;
+    std::map<std::pair<int, int>, std::vector<GemmJob>> cyc_jobs;   // (panel-cyclic supernode, panel) -> descendant updates of this rank
     std::vector<int> nodes;
     int step_begin = 0;
     // Host streaming: every copy is a host-side call between kernel launches, so only the few supernodes near the root are
@@ -416,7 +418,9 @@ bool build_host_plan(long long n, long long nsuper, const long long *super, cons
                         GemmJob h = g;
                         h.a_off += jlo; h.map_off += jlo; h.nd1 = jhi - jlo; h.nd2 = u.nd2 - jlo;
                         hp.my_flops += 2.0 * ndcol * ((double) h.nd1 * h.nd2 - 0.5 * (double) h.nd1 * (h.nd1 - 1));
-                        route_gemm(h, gs, gb);
+                        // not launched with the level's other updates: the descendant updates of a panel are scheduled just
+                        // in time inside the panel loop, where they fill the ranks' idle time behind the serial panel chain
+                        cyc_jobs[{u.s, blk}].push_back(h);
                     }
                     jlo = jhi;
                 }
@@ -476,7 +480,15 @@ bool build_host_plan(long long n, long long nsuper, const long long *super, cons
                     hp.my_flops += 2.0 * W * ((double) g.nd1 * g.nd2 - 0.5 * (double) g.nd1 * (g.nd1 - 1));
                     route_gemm(g, gs, gb);
                 };
-                // prologue: panel 0
+                auto descendant_updates = [&](int J) {         // this rank's descendant updates into panel J (it owns J)
+                    auto it = cyc_jobs.find({sn, J});
+                    if (it == cyc_jobs.end()) return;
+                    for (const GemmJob &h : it->second) route_gemm(h, gs, gb);
+                    cyc_jobs.erase(it);
+                    emit_update_launches(hp, gs, gb, 0);
+                };
+                // prologue: every rank brings its FIRST panel up to date with the descendants, rank 0 factorizes panel 0
+                if (hp.rank < npan) descendant_updates(hp.rank);
                 if (0 % hp.nranks == hp.rank) factor_panel(0);
                 close_step(step_begin, 0, hp.px[sn], (long long) panel_w(0) * nsrow, l);
                 for (int J = 0; J < npan; J++) {
@@ -485,6 +497,9 @@ bool build_host_plan(long long n, long long nsuper, const long long *super, cons
                     step_mid = (int) hp.launches.size();
                     for (int J1 = J + 2; J1 < npan; J1++) if (J1 % hp.nranks == hp.rank) update_block(J, J1);
                     emit_update_launches(hp, gs, gb, 1);
+                    // the owner of panel J has just finished its turn in the chain: its NEXT panel (J + nranks) gets its
+                    // descendant updates now, nranks-1 steps before it is needed
+                    if (J % hp.nranks == hp.rank && J + hp.nranks < npan) descendant_updates(J + hp.nranks);
                     if (J + 1 < npan) close_step(step_begin, (J + 1) % hp.nranks, hp.px[sn] + (long long) (J + 1) * NB_MID * nsrow, (long long) panel_w(J + 1) * nsrow, l);
                     else close_step(step_begin, -1, 0, 0, l);
                 }

@@ -48,9 +48,11 @@ def test_sharded_schedule_gloo(name, world):
     assert sum(r[3] for r in res) + res[0][4] == len(load_golden([p for p in GOLDEN if os.path.basename(p) == name + ".npz"][0])["super"]) - 1
 
 
-def test_sharded_schedule_with_cyclic_supernode_single_process():
-    """4 ranks emulated in one process on a mesh whose root supernode is wide enough (>= 512 columns) to be shared
-    panel-cyclically; checks load balance numbers and that exactly all of L is broadcast once."""
+@pytest.mark.parametrize("N,nr", [(22, 4), (24, 2)])
+def test_sharded_schedule_with_cyclic_supernode_single_process(N, nr):
+    """Ranks emulated in one process on a mesh whose root supernode is wide enough (>= 512 columns) to be shared
+    panel-cyclically ((24, 2): four panels on two ranks, so the just-in-time descendant updates of a rank's NEXT panel are
+    exercised); checks that exactly all of L is broadcast once and that every rank ends with the oracle's factor."""
     import emulate_plan as E
     from suitesparse_b200 import gen
     from oracle import oracle
@@ -61,14 +63,13 @@ def test_sharded_schedule_with_cyclic_supernode_single_process():
         pytest.skip("reference build (host libcholmod for cholmod_l_analyze) not present")
     from suitesparse_b200.cholmod_host import Cholmod, _np_view
     ch = Cholmod(gpu=False)
-    A, p = gen.make_problem("lap7", 22)
+    A, p = gen.make_problem("lap7", N)
     S = ch.sparse(A, +1); L = ch.analyze(S, p)
     f = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in ch.factor_arrays(L).items()}
     S2 = ch.lower_permuted(S, L); s2 = S2.contents; n = s2.nrow
     Ap = _np_view(s2.p, n + 1, np.int64).copy(); Ai = _np_view(s2.i, int(Ap[n]), np.int64).copy(); Ax = _np_view(s2.x, int(Ap[n]), np.float64).copy()
     Sl = sp.csc_matrix((Ax, Ai, Ap), shape=(n, n))
     st, minor, Lo = oracle.factorize(n, f["super"], f["pi"], f["px"], f["s"], Sl)
-    nr = 4
     os.environ["SSB200_DIST_TAU"] = "0"              # cost model: free panel steps -> dominant supernodes are shared
     try:
         plans = [E.export_plan(n, f["super"], f["pi"], f["px"], f["s"], nr, r) for r in range(nr)]
