@@ -140,40 +140,68 @@ class ShardedFactor:
         self.step_events = [] if dbg or os.environ.get("SSB200_DIST_STEPTIME") else None
         with torch.cuda.stream(self.stream):
             self.plan._check(L.ssb200_dist_begin(h, b))
-            pending = []                                  # broadcasts in flight: (work, off, cnt)
+            pending = []                                  # collectives in flight: work handles
+            deferred = []                                 # finished subtrees whose exchange has not been issued yet
+            batch_subtrees = (self.world > 1 and do_comm and os.environ.get("SSB200_DIST_P2P", "1") != "0"
+                              and (host_out is None or host_shared))
+
+            def flush_deferred():
+                # All finished subtrees change hands in ONE grouped exchange of point-to-point sends: every rank sends its
+                # ranges to every other rank at the same time, so all NVLink ports are busy (a sequence of broadcasts has
+                # one source at a time).
+                if not deferred:
+                    return
+                self.comm_stream.wait_stream(self.stream)
+                with torch.cuda.stream(self.comm_stream):
+                    ops = []
+                    for (src, off, cnt) in deferred:
+                        view = self.Lx[off:off + cnt]
+                        if src == self.rank:
+                            ops += [dist.P2POp(dist.isend, view, peer) for peer in range(self.world) if peer != self.rank]
+                        else:
+                            ops.append(dist.P2POp(dist.irecv, view, src))
+                    pending.extend(dist.batch_isend_irecv(ops))
+                deferred.clear()
+
             for k, (src, off, cnt, wait_remote) in enumerate(self.steps):
                 if self.step_events is not None:
                     ev = torch.cuda.Event(enable_timing=True); ev.record(); self.step_events.append(ev)
                 if wait_remote and self.phase_event is None:
                     self.phase_event = torch.cuda.Event(enable_timing=True); self.phase_event.record()   # subtree phase ends here
+                if wait_remote:
+                    flush_deferred()
                 if wait_remote and pending:
-                    for w, _, _ in pending:
+                    for w in pending:
                         w.wait()                          # stream-level: self.stream waits for the NCCL stream
                     pending = []
                 if do_compute:
                     self.plan._check(L.ssb200_dist_run_step(h, k, 0))
+                w = None
                 if src >= 0:
-                    if self.world > 1 and do_comm:
+                    if batch_subtrees and not wait_remote:
+                        deferred.append((src, off, cnt))  # subtree phase: nobody reads remote data yet
+                    elif self.world > 1 and do_comm:
                         self.comm_stream.wait_stream(self.stream)
                         with torch.cuda.stream(self.comm_stream):
                             w = dist.broadcast(self.Lx[off:off + cnt], src, async_op=True)
-                        pending.append((w, off, cnt))
+                        pending.append(w)
                     if host_out is not None and host_shared:
                         if src == self.rank:              # final here since the launches above: no need to wait for the transfer
                             self._copy_stream.wait_stream(self.stream)
                             with torch.cuda.stream(self._copy_stream):
                                 host_out[off:off + cnt].copy_(self.Lx[off:off + cnt], non_blocking=True)
                     elif host_out is not None:
-                        # the range is final everywhere once its broadcast has landed: stream it to the host
+                        # rank 0 pulls everything: the range is final there once its broadcast has landed
                         with torch.cuda.stream(self._copy_stream):
-                            if self.world > 1 and do_comm:
+                            if w is not None:
                                 w.wait()
                             else:
                                 self._copy_stream.wait_stream(self.stream)
                             host_out[off:off + cnt].copy_(self.Lx[off:off + cnt], non_blocking=True)
                 if do_compute:
                     self.plan._check(L.ssb200_dist_run_step(h, k, 1))
-            for w, _, _ in pending:
+            flush_deferred()
+            for w in pending:
                 w.wait()
             if self.step_events is not None:
                 ev = torch.cuda.Event(enable_timing=True); ev.record(); self.step_events.append(ev)
