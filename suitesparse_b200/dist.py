@@ -142,13 +142,13 @@ class ShardedFactor:
             self.plan._check(L.ssb200_dist_begin(h, b))
             pending = []                                  # collectives in flight: work handles
             deferred = []                                 # finished subtrees whose exchange has not been issued yet
-            batch_subtrees = (self.world > 1 and do_comm and os.environ.get("SSB200_DIST_P2P", "1") != "0"
+            batch_subtrees = (self.world > 1 and do_comm and os.environ.get("SSB200_DIST_P2P", "0") != "0"
                               and (host_out is None or host_shared))
 
             def flush_deferred():
-                # All finished subtrees change hands in ONE grouped exchange of point-to-point sends: every rank sends its
-                # ranges to every other rank at the same time, so all NVLink ports are busy (a sequence of broadcasts has
-                # one source at a time).
+                # Optional (SSB200_DIST_P2P=1): all finished subtrees change hands in ONE grouped exchange of point-to-point
+                # sends instead of one broadcast per subtree.  Measured slower on 8 B200 (308 vs 296 ms at lap7 128^3), so
+                # the default stays with asynchronous broadcasts.
                 if not deferred:
                     return
                 self.comm_stream.wait_stream(self.stream)
