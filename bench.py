@@ -369,7 +369,8 @@ def main():
                             "frac": round(ach / peak_tf, 4) if peak_tf else None, "traffic": None,
                             "peak_source": "cuBLAS DGEMM 8192^3 (torch.matmul fp64) measured in this run; MEASURED_PEAKS.json has no fp64 entry",
                             "kernel_time_share": share, "launches_per_step": [int(v / args.steps) for v in kind_n[:5]],
-                            "whole_step_frac_of_peak": round(fl / t_dev / 1e12 / peak_tf, 4) if peak_tf else None},
+                            "whole_step_frac_of_peak": round(fl / t_dev / 1e12 / peak_tf, 4) if peak_tf else None,
+                            "ncu_capture": "profiles/r1_ncu_full_gemm128_bigK_update.txt: one large-K launch, dram read+write 1.21e9 B, DMMA sub-pipe 87.3 % active"},
                "solve": {"value": round(16.0 * xsize / (solve_ms_v * 1e-3) / 1e9, 1), "unit": "GB/s", "ms": round(solve_ms_v, 3), "launches": int(solve_launches),
                          "hbm_peak_GBps": json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(REPO, "MEASURED_PEAKS.json")) else 6650.0,
                          "e2e_cholmod_l_solve_ms": round(t_solve_e2e * 1e3, 2), "resid_2norm_rel": resid},
