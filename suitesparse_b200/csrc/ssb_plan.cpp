@@ -565,6 +565,9 @@ extern "C" int ssb200_plan_summary(long long n, long long nsuper, const long lon
     out[7] = (double) hp.trsm_jobs.size(); out[8] = (double) hp.trsm_tiles.size(); out[9] = (double) hp.solve_steps.size();
     out[10] = (double) hp.solve_jobs.size(); out[11] = hp.flops_update; out[12] = hp.flops_potrf; out[13] = hp.flops_trsm;
     out[14] = hp.bytes_update_panel; out[15] = hp.bytes_update_scatter;
+    { double c = 0; for (const auto &ct : hp.copy_tasks) c += (double) ct.cnt; out[16] = c; out[17] = (double) hp.copy_tasks.size(); }
+    out[18] = hp.max_winv_slots;
+    { int k = 0; for (const auto &g : hp.gemm_jobs) if (g.map_off < 0) k = std::max(k, g.K); out[19] = k; }
     if (level_of_supernode) for (long long t = 0; t < nsuper; t++) level_of_supernode[t] = hp.level[t];
     return 0;
 }

@@ -9,7 +9,7 @@ from oracle import oracle
 
 def plan_summary(n, super_, pi, px, s):
     lib = C.CDLL(B200_LIB)
-    out = np.zeros(16); lev = np.zeros(len(super_) - 1, dtype=np.int32)
+    out = np.zeros(20); lev = np.zeros(len(super_) - 1, dtype=np.int32)
     a = [np.ascontiguousarray(v, dtype=np.int64) for v in (super_, pi, px, s)]
     rc = lib.ssb200_plan_summary(C.c_int64(n), C.c_int64(len(super_) - 1), *[v.ctypes.data_as(C.c_void_p) for v in a],
                                  out.ctypes.data_as(C.c_void_p), lev.ctypes.data_as(C.c_void_p))
@@ -35,6 +35,8 @@ def test_plan_matches_oracle_enumeration(path):
     ndcol = nscol[up["d"]]
     tri = up["ndrow1"] * up["ndrow2"] - 0.5 * up["ndrow1"] * (up["ndrow1"] - 1)
     assert np.isclose(out[11], (2 * ndcol * tri).sum())
+    # the host-streaming copy tasks cover every entry of Lx exactly once
+    assert int(out[16]) == int(g["px"][-1])
     # one potrf job per 64-column block, one solve job per block
     blocks = np.ceil(nscol / 64).sum()
     assert int(out[6]) == int(blocks) and int(out[10]) == int(blocks)
@@ -65,3 +67,27 @@ def test_generators():
     assert E.shape == (192, 192)
     fullE = (E + __import__("scipy.sparse").sparse.triu(E, 1).T).toarray()
     assert np.linalg.eigvalsh(fullE).min() > 0
+
+
+def test_three_level_blocking_and_copy_cover_on_a_wide_supernode():
+    """A mesh whose root supernode is wider than 1024 columns: the in-supernode trailing updates use K = 64, 256 and 1024,
+    the copy tasks still cover Lx exactly once, and the wide blocks get inverse slots."""
+    import os
+    from conftest import REF_LIB
+    if not os.path.exists(REF_LIB):
+        pytest.skip("reference build (host libcholmod for cholmod_l_analyze) not present")
+    from suitesparse_b200 import gen
+    from suitesparse_b200.cholmod_host import Cholmod
+    ch = Cholmod(gpu=False)
+    A, p = gen.make_problem("lap7", 34)
+    L = ch.analyze(ch.sparse(A, +1), p)
+    f = ch.factor_arrays(L)
+    assert np.diff(f["super"]).max() > 1024
+    rc, out, lev = plan_summary(f["n"], f["super"], f["pi"], f["px"], f["s"])
+    assert rc == 0
+    assert int(out[19]) == 1024
+    assert int(out[16]) == int(f["px"][-1])
+    nscol = np.diff(f["super"]); nsrow = np.diff(f["pi"])
+    wide = (nscol >= 33) & (nsrow > 32)
+    assert int(out[18]) == int(np.ceil(nscol[wide] / 64).sum())
+    ch.free_factor(L)
