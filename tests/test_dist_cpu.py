@@ -48,8 +48,8 @@ def test_sharded_schedule_gloo(name, world):
     assert sum(r[3] for r in res) + res[0][4] == len(load_golden([p for p in GOLDEN if os.path.basename(p) == name + ".npz"][0])["super"]) - 1
 
 
-@pytest.mark.parametrize("N,nr", [(22, 4), (24, 2)])
-def test_sharded_schedule_with_cyclic_supernode_single_process(N, nr):
+@pytest.mark.parametrize("N,nr,jit", [(22, 4, "0"), (24, 2, "1"), (24, 2, "0")])
+def test_sharded_schedule_with_cyclic_supernode_single_process(N, nr, jit):
     """Ranks emulated in one process on a mesh whose root supernode is wide enough (>= 512 columns) to be shared
     panel-cyclically ((24, 2): four panels on two ranks, so the just-in-time descendant updates of a rank's NEXT panel are
     exercised); checks that exactly all of L is broadcast once and that every rank ends with the oracle's factor."""
@@ -71,10 +71,11 @@ def test_sharded_schedule_with_cyclic_supernode_single_process(N, nr):
     Sl = sp.csc_matrix((Ax, Ai, Ap), shape=(n, n))
     st, minor, Lo = oracle.factorize(n, f["super"], f["pi"], f["px"], f["s"], Sl)
     os.environ["SSB200_DIST_TAU"] = "0"              # cost model: free panel steps -> dominant supernodes are shared
+    os.environ["SSB200_DIST_JIT"] = jit              # descendant updates just in time inside the panel loop, or up front
     try:
         plans = [E.export_plan(n, f["super"], f["pi"], f["px"], f["s"], nr, r) for r in range(nr)]
     finally:
-        del os.environ["SSB200_DIST_TAU"]
+        del os.environ["SSB200_DIST_TAU"], os.environ["SSB200_DIST_JIT"]
     assert (plans[0]["owner"] < 0).sum() >= 1                      # a panel-cyclic supernode exists
     assert all(np.array_equal(pl["owner"], plans[0]["owner"]) for pl in plans)
     rel = E.relmap_of(plans[0], f["pi"], f["s"])
