@@ -359,7 +359,10 @@ def main():
                "config": {"workload": workload, "n": n, "nnz_tril_A": int(S2.contents.nzmax), "fl": fl, "lnz": lnz, "nsuper": int(nsuper), "xsize": int(xsize),
                           "levels": st_e2e["nlevels"], "updates": st_e2e["nupdates"], "l2": "inputs_exceed_l2 (L is %.1f GB)" % (xsize * 8 / 1e9),
                           "parallelism": "1 GPU",
-                          "analyze_s_host": round(t_an, 2), "first_call_s": round(t_first, 2)},
+                          "analyze_s_host": round(t_an, 2), "first_call_s": round(t_first, 2),
+                          "hot_path_library": os.path.relpath(ch.b200._name, REPO),
+                          "host_cholmod_for_analyze_only": os.path.relpath(ch.lib._name, REPO),
+                          "reference_blas_calls_during_our_steps": int(ch.cm.cpu_syrk_calls + ch.cm.cpu_gemm_calls + ch.cm.cpu_potrf_calls + ch.cm.cpu_trsm_calls)},
                "e2e": {"value": round(e2e_v, 1), "unit": "GFLOP/s", "h2d_bytes_per_step": a_bytes, "d2h_bytes_per_step": int(xsize) * 8,
                        "ms_per_step": round(t_host * 1e3, 2), "call": "cholmod_l_super_numeric(S,NULL,beta,L,Common) via the interposed C ABI, host buffers, L->x page-locked once",
                        "ms_h2d": round(st_e2e["ms_h2d"], 2), "ms_d2h_exposed": round(st_e2e["ms_d2h"], 2), "ms_device_factorize": round(st_e2e["ms_total"], 2)},

@@ -103,3 +103,28 @@ def test_invalid_arguments_without_gpu():
     # n-by-0 right-hand side returns TRUE immediately (Tcov/raw_factor.c:339-345)
     X.ncol = 0; E.nzmax = 0; cm.status = -1
     assert g(C.byref(L), C.byref(X), C.byref(E), C.byref(cm)) == 1 and cm.status == 0
+
+
+def test_header_is_plain_c_and_example_links(tmp_path):
+    """include/suitesparse_b200.h compiles as C99 and examples/plain_demo.c links against the library (no run: no GPU here)."""
+    exe = tmp_path / "plain_demo"
+    csrc = os.path.join(REPO, "suitesparse_b200", "csrc")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(REPO, "include"),
+                           os.path.join(REPO, "examples", "plain_demo.c"), "-L", csrc, "-lsuitesparse_b200",
+                           f"-Wl,-rpath,{csrc}", "-o", str(exe)])
+    assert exe.exists()
+
+
+@pytest.mark.gpu
+def test_plain_c_example_runs(tmp_path):
+    exe = tmp_path / "plain_demo"
+    csrc = os.path.join(REPO, "suitesparse_b200", "csrc")
+    subprocess.check_call(["gcc", "-std=c99", "-I", os.path.join(REPO, "include"), os.path.join(REPO, "examples", "plain_demo.c"),
+                           "-L", csrc, "-lsuitesparse_b200", f"-Wl,-rpath,{csrc}", "-o", str(exe)])
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    import numpy as np
+    A = np.array([[4, 1, 0], [1, 5, 2], [0, 2, 6]], dtype=float)
+    x = np.linalg.solve(A, np.array([1.0, 2.0, 3.0]))
+    got = [float(v) for v in re.search(r"x = ([-0-9.e]+) ([-0-9.e]+) ([-0-9.e]+)", r.stdout).groups()]
+    assert np.allclose(got, x, atol=1e-5) and "L(0,0)=2.000000" in r.stdout
