@@ -196,7 +196,8 @@ void ssb200_plan_destroy(ssb200_plan *plan);
  *         if (wait) wait for every broadcast started so far;   ssb200_dist_run_step(k, 0);
  *         if (src >= 0) start broadcast(Lx+off, cnt, src) asynchronously, ordered after the launches above;
  *         ssb200_dist_run_step(k, 1);          // look-ahead work that overlaps the broadcast
- *     ssb200_dist_end(&bad);  minor = min over ranks of bad;  if (minor < n) ssb200_dist_zero_from(minor);
+ *     ssb200_dist_end(&bad);  minor = min over ranks of bad;
+ *     if (minor < n) { ssb200_dist_not_posdef(minor, quick, &redo_rank, &off, &cnt); if (redo_rank >= 0) broadcast(Lx+off, cnt, redo_rank); }
  * Kernels go to the stream given by ssb200_set_stream(plan, cudaStream_t); the caller orders its broadcasts against it. */
 ssb200_plan *ssb200_plan_create_dist(ssb_long n, ssb_long nsuper, const ssb_long *super, const ssb_long *pi,
                                      const ssb_long *px, const ssb_long *s, int device, int nranks, int rank);
@@ -207,6 +208,7 @@ int      ssb200_dist_begin(ssb200_plan *plan, const double beta[2]);
 int      ssb200_dist_run_step(ssb200_plan *plan, ssb_long k, int part);
 int      ssb200_dist_end(ssb200_plan *plan, ssb_long *first_bad_column);
 int      ssb200_dist_zero_from(ssb200_plan *plan, ssb_long column);
+int      ssb200_dist_not_posdef(ssb200_plan *plan, ssb_long minor, int quick_return, int *redo_rank, ssb_long *off, ssb_long *cnt);
 int      ssb200_dist_flops(const ssb200_plan *plan, double *mine, double *total);
 int      ssb200_plan_set_owner(ssb200_plan *plan, const int32_t *owner, int rank);   /* superseded by ssb200_plan_create_dist */
 

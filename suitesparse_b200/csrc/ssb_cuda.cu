@@ -92,6 +92,7 @@ struct ssb200_plan {
     int stype = -1;
     double *d_X = nullptr; size_t capX = 0;
     bool factor_on_device = false;
+    double last_beta0 = 0.0;               // beta of the running sharded factorization (not-positive-definite repeat)
     bool winv_valid = false;               // d_winv matches d_Lx (false after ssb200_upload_L or a sharded factorization)
     // the whole solve sequence is replayed as one CUDA graph (thousands of tiny dependent kernels)
     cudaGraphExec_t solve_graph = nullptr; double *sg_X = nullptr; long long sg_nrhs = 0, sg_ldx = 0; int sg_which = -1; bool sg_winv = false;
@@ -282,7 +283,8 @@ extern "C" int ssb200_dist_step_info(const ssb200_plan *p, ssb_long k, int *src,
     return 0;
 }
 
-static int scatter_A(ssb200_plan *p, double beta0, long long kfirst, long long kcount);
+static int scatter_A(ssb200_plan *p, double beta0, long long kfirst, long long kcount, bool ignore_owner);
+static int handle_not_posdef(ssb200_plan *p, int sfail, int info, double beta0, int quick_return, ssb_long *minor_out);
 static int run_launch(ssb200_plan *p, const Launch &L, const DevJobs &dj);
 
 // zero Lx, assemble the columns this rank computes; everything is enqueued on the plan's stream, nothing is synchronized
@@ -296,7 +298,8 @@ extern "C" int ssb200_dist_begin(ssb200_plan *p, const double beta[2])
     CU_TRY(cudaMemsetAsync(p->d_Lx, 0, (size_t) hp.xsize * sizeof(double), p->stream));
     fill_int_kernel<<<(unsigned) ((hp.nsuper + 255) / 256), 256, 0, p->stream>>>(p->d_info, hp.nsuper, INT_MAX);
     p->stats.kernel_launches++;
-    return scatter_A(p, beta ? beta[0] : 0.0, 0, hp.n);
+    p->last_beta0 = beta ? beta[0] : 0.0;
+    return scatter_A(p, p->last_beta0, 0, hp.n, false);
 }
 
 // part 0: the launches before the step's broadcast starts; part 1: the look-ahead launches that overlap it
@@ -339,6 +342,27 @@ extern "C" int ssb200_dist_zero_from(ssb200_plan *p, ssb_long column)
     CU_TRY(cudaMemsetAsync(p->d_Lx + off, 0, (size_t) (p->hp.xsize - off) * sizeof(double), p->stream));
     CU_TRY(cudaStreamSynchronize(p->stream));
     return 0;
+}
+
+// Not positive definite at global column `minor` (the minimum over the ranks): every rank zeroes the failing supernode
+// and everything after it; unless quick_return or the failure is in the supernode's first column, ONE rank - the owner of
+// the failing supernode, rank 0 for a panel-cyclic one; it holds all the descendants - repeats the supernode on its first
+// info-1 columns (t_cholmod_super_numeric.c:944-967).  *redo_rank >= 0: the caller broadcasts Lx[*off, *off+*cnt) from it.
+extern "C" int ssb200_dist_not_posdef(ssb200_plan *p, ssb_long minor, int quick_return, int *redo_rank, ssb_long *off, ssb_long *cnt)
+{
+    if (!p || minor < 0 || minor >= p->hp.n || !redo_rank || !off || !cnt) return SSB_CHOLMOD_INVALID;
+    HostPlan &hp = p->hp;
+    const int sfail = hp.supermap[minor];
+    const int info = (int) (minor - hp.super[sfail]) + 1;
+    *redo_rank = -1; *off = hp.px[sfail]; *cnt = hp.px[sfail + 1] - hp.px[sfail];
+    const bool redo = !(info == 1 || quick_return);
+    const int who = hp.owner[sfail] >= 0 ? hp.owner[sfail] : 0;
+    if (redo) *redo_rank = who;
+    ssb_long m = 0;
+    // the non-repeating ranks only zero (handle_not_posdef with quick_return does exactly that)
+    const int rc = handle_not_posdef(p, sfail, info, p->last_beta0, (redo && who == hp.rank) ? 0 : 1, &m);
+    p->winv_valid = false;
+    return rc;
 }
 
 // dense flops this rank executes in one factorization, and the global total (load balance of the shard)
@@ -456,14 +480,14 @@ static cudaEvent_t get_event(ssb200_plan *p, size_t idx)
     return p->events[idx];
 }
 
-static int scatter_A(ssb200_plan *p, double beta0, long long kfirst, long long kcount)
+static int scatter_A(ssb200_plan *p, double beta0, long long kfirst, long long kcount, bool ignore_owner = false)
 {
     if (kcount <= 0) return 0;
     DevCsc A{p->bufA->p, p->bufA->i, p->bufA->haveNz ? p->bufA->nz : nullptr, p->bufA->x};
     DevCsc F{p->bufF->p, p->bufF->i, p->bufF->haveNz ? p->bufF->nz : nullptr, p->bufF->x};
     const int T = 128;
     const long long g = (kcount + T - 1) / T;
-    scatter_A_kernel<<<(unsigned) g, T, 0, p->stream>>>(dev_sym(p), p->stype, A, F, beta0, p->d_Lx, kfirst, kcount, p->d_owner, p->hp.nranks, p->hp.rank);
+    scatter_A_kernel<<<(unsigned) g, T, 0, p->stream>>>(dev_sym(p), p->stype, A, F, beta0, p->d_Lx, kfirst, kcount, ignore_owner ? nullptr : p->d_owner, p->hp.nranks, p->hp.rank);
     p->stats.kernel_launches++;
     CU_TRY(cudaGetLastError());
     return 0;
@@ -481,7 +505,7 @@ static int handle_not_posdef(ssb200_plan *p, int sfail, int info, double beta0, 
     const int nscol = hp.super[sfail + 1] - hp.super[sfail];
     const int nsrow = (int) (hp.pi[sfail + 1] - hp.pi[sfail]);
     const int ncol_new = info - 1;
-    if (scatter_A(p, beta0, hp.super[sfail], nscol)) return SSB_CHOLMOD_GPU_PROBLEM;
+    if (scatter_A(p, beta0, hp.super[sfail], nscol, /*ignore_owner=*/true)) return SSB_CHOLMOD_GPU_PROBLEM;
     HostPlan tmp;
     {   // descendant updates of sfail
         std::vector<GemmJob> all;

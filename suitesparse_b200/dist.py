@@ -41,6 +41,7 @@ class ShardedFactor:
         L.ssb200_dist_run_step.argtypes = [C.c_void_p, c_long, C.c_int]
         L.ssb200_dist_end.argtypes = [C.c_void_p, C.POINTER(c_long)]
         L.ssb200_dist_zero_from.argtypes = [C.c_void_p, c_long]
+        L.ssb200_dist_not_posdef.argtypes = [C.c_void_p, c_long, C.c_int, C.POINTER(C.c_int), C.POINTER(c_long), C.POINTER(c_long)]
         L.ssb200_dist_flops.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         a = [np.ascontiguousarray(v, dtype=np.int64) for v in (super_, pi, px, s)]
         self.n = int(n)
@@ -123,7 +124,7 @@ class ShardedFactor:
     def upload_A(self, A_lower, F=None):
         return self.plan.upload_A(A_lower, F)
 
-    def factorize_resident(self, beta: float = 0.0, host_out=None, host_shared: bool = False):
+    def factorize_resident(self, beta: float = 0.0, host_out=None, host_shared: bool = False, quick_return: bool = False):
         """Returns (status, minor): status 0 ok, 1 not positive definite (every rank gets the same answer).
         host_out: pinned host tensor of xsize doubles (or None).  A range of L is final on every rank right after its
         broadcast, so it is copied to host_out on a second stream while the factorization continues.
@@ -213,7 +214,13 @@ class ShardedFactor:
                 dist.all_reduce(t, op=dist.ReduceOp.MIN)
                 minor = int(t.item())
             if minor < self.n:
-                self.plan._check(L.ssb200_dist_zero_from(h, minor))
+                # the reference's protocol (t_cholmod_super_numeric.c:905-968): zero from the failing supernode on, then one
+                # rank repeats that supernode on the columns before the failing one and hands the block to the others
+                redo, roff, rcnt = C.c_int(-1), c_long(0), c_long(0)
+                self.plan._check(L.ssb200_dist_not_posdef(h, minor, 1 if quick_return else 0, C.byref(redo), C.byref(roff), C.byref(rcnt)))
+                if redo.value >= 0 and self.world > 1:
+                    dist.broadcast(self.Lx[roff.value:roff.value + rcnt.value], redo.value)
+                    torch.cuda.current_stream().synchronize()
                 if host_out is not None:
                     self._copy_stream.synchronize()
                     if not host_shared or self.rank == 0:

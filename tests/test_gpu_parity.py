@@ -207,13 +207,17 @@ def test_sharded_api_single_rank():
     # not positive definite: every rank reports the same failing column; the failing supernode and the rest are zeroed
     Sbad = Sl.copy().tolil(); kbad = n // 2; Sbad[kbad, kbad] = -1.0; Sbad = Sbad.tocsc(); Sbad.sort_indices()
     sf.upload_A(Sbad)
-    st, minor = sf.factorize_resident()
-    st_o, minor_o, Lo = oracle.factorize(n, f["super"], f["pi"], f["px"], f["s"], Sbad, quick_return=True)
-    assert st == 1 and minor == minor_o
-    Lx = sf.download_L()
-    sbad = int(np.searchsorted(f["super"], minor, side="right") - 1)
-    assert np.all(Lx[int(f["px"][sbad]):] == 0.0)
-    assert persuper_relerr(f["px"][: sbad + 1], Lx, Lo) < TOL_L
+    for quick in (True, False):
+        st, minor = sf.factorize_resident(quick_return=quick)
+        st_o, minor_o, Lo = oracle.factorize(n, f["super"], f["pi"], f["px"], f["s"], Sbad, quick_return=quick)
+        assert st == 1 and minor == minor_o
+        Lx = sf.download_L()
+        sbad = int(np.searchsorted(f["super"], minor, side="right") - 1)
+        assert np.all(Lx[int(f["px"][sbad + 1]):] == 0.0)                      # everything after the failing supernode
+        if quick:
+            assert np.all(Lx[int(f["px"][sbad]):] == 0.0)
+        # supernodes before the failing one, and (repeat protocol) its columns before the failing column, match the oracle
+        assert persuper_relerr(f["px"][: sbad + 2], Lx, Lo) < TOL_L
     sf.close(); ch.free_sparse(S2); ch.free_factor(L)
 
 
