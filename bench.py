@@ -246,7 +246,7 @@ def main():
         sample = f"{args.kind} {Ns}^3 (n={r['n']}, fl={r['fl']:.3e}); the full {args.N}^3 step takes ~180 s on 8 cores"
         out = {"impl": "reference", "metric": "supernodal Cholesky factorize GFLOP/s (fp64)", "value": round(r["gflops"], 2), "unit": "GFLOP/s",
                "n_gpus": 0, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(r["sec"] * 1e3, 2), "higher_is_better": True,
-               "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+               "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                "config": {"workload": workload, "sample": sample},
                "cpu_baseline": {"value": round(r["gflops"], 2), "unit": "GFLOP/s", "cores": cores, "kind": "reference", "sample": sample,
                                 "blas": "OpenBLAS (scipy-bundled), threads = all host cores", "solve_GBps": round(r["solve_gbs"], 2), "resid": r["resid"]},
