@@ -48,7 +48,7 @@ def test_sharded_schedule_gloo(name, world):
     assert sum(r[3] for r in res) + res[0][4] == len(load_golden([p for p in GOLDEN if os.path.basename(p) == name + ".npz"][0])["super"]) - 1
 
 
-@pytest.mark.parametrize("kind,N,nr,jit", [("lap7", 22, 4, "0"), ("lap7", 24, 2, "1"), ("lap7", 24, 2, "0"), ("lap27", 18, 3, "1"), ("elas", 8, 3, "0")])
+@pytest.mark.parametrize("kind,N,nr,jit", [("lap7", 22, 4, "0"), ("lap7", 24, 2, "1"), ("lap7", 24, 2, "0"), ("lap27", 18, 3, "1"), ("elas", 8, 3, "0"), ("lap7", 24, 3, "1")])
 def test_sharded_schedule_with_cyclic_supernode_single_process(kind, N, nr, jit):
     """Ranks emulated in one process on a mesh whose root supernode is wide enough (>= 512 columns) to be shared
     panel-cyclically ((24, 2): four panels on two ranks, so the just-in-time descendant updates of a rank's NEXT panel are
