@@ -11,7 +11,8 @@ already exists (the refactorization loop of a Newton / time-stepping code: analy
           buffers: S is uploaded and L->x (xsize doubles) is copied back inside the timed region, every step
   solve   forward+backward triangular solve GB/s = 16*xsize / t  (extra keys)
   roofline  the dominant kernel (gemm_nt_sub_kernel<128>, DMMA) against a cuBLAS DGEMM peak measured in this run
-  cpu_baseline  the reference library (oracle/_ref) timed on the host cores on a bounded sample
+  cpu_baseline  the unmodified reference library (baseline/_ref/libcholmod.so) on the host cores, bounded sample;
+                `--impl reference` times it on the full workload (fewer steps when a step takes minutes)
 Workload: BASELINE.json configs[1], the 3-D 7-point Laplacian 128^3 (n = 2 097 152, L = 29 GB), geometric nested
 dissection (MESHND) passed as the user permutation.  The other configs are parity-test cases (tests/).
 Multi-GPU (N > 1): ONE factorization sharded over the N GPUs along the elimination tree (suitesparse_b200/dist.py):
@@ -53,33 +54,58 @@ def build_problem(ch, kind, N):
     return A, perm, S, Lp, S2, t_an
 
 
-def cpu_sample_size(steps, warmup, budget_s=150.0):
-    # measured factorize seconds of the reference CPU path on 8 host threads (BASELINE.md §2 and this repo's runs)
-    est = [(32, 0.3), (48, 1.6), (64, 7.0), (80, 28.0), (96, 75.0)]
-    per = budget_s / max(1, steps + warmup)
-    best = 32
-    for n, t in est:
-        if t <= per:
-            best = n
-    return best
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
 
 
-def time_reference_steps(kind, N, steps, warmup):
-    """The reference's own cholmod_l_super_numeric (CPU, BLAS threads = all host cores) on lap7 N^3."""
-    from suitesparse_b200.cholmod_host import Cholmod
+def set_blas_threads(n):
+    """torchrun exports OMP_NUM_THREADS=1, which OpenBLAS honours: set the thread count of the reference's BLAS
+    explicitly (and report what the library says it uses), so the CPU arm always runs on all host cores."""
+    import glob, scipy
+    for k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "GOTO_NUM_THREADS"):
+        os.environ[k] = str(n)
+    libs = sorted(glob.glob(os.path.join(os.path.dirname(scipy.__file__), "..", "scipy.libs", "libscipy_openblas*.so")))
+    ob = C.CDLL(libs[0], mode=C.RTLD_GLOBAL)
+    ob.scipy_openblas_set_num_threads(int(n))
+    return int(ob.scipy_openblas_get_num_threads())
+
+
+def time_reference_steps(kind, N, steps, warmup, budget_s=170.0):
+    """The reference's own cholmod_l_super_numeric (unmodified CHOLMOD built from /root/reference + OpenBLAS on all host
+    cores) on the SAME workload as our arm.  A step = one numeric refactorization into an existing numeric L (L->x is
+    allocated and touched before the timed region, as in our arm).  When steps+warmup full-size steps do not fit the time
+    budget, fewer full-size steps are timed (at least one, then without warm-up) instead of shrinking the matrix."""
+    from suitesparse_b200.cholmod_host import Cholmod, _np_view, CHOLMOD_REAL
+    threads = set_blas_threads(host_cores())
     ch = Cholmod(gpu=False)
     A, perm, S, Lp, S2, t_an = build_problem(ch, kind, N)
     fl = ch.cm.fl
     f = ch.hot("cholmod_l_super_numeric")
     beta = (C.c_double * 2)(0.0, 0.0)
-    for _ in range(warmup):
-        f(S2, None, beta, Lp, C.byref(ch.cm))
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        ok = f(S2, None, beta, Lp, C.byref(ch.cm))
-    dt = (time.perf_counter() - t0) / max(1, steps)
-    assert ok and ch.cm.status == 0
+    # numeric L with its pages touched (the reference allocates L->x inside the first call: cholmod_super_numeric.c:211-223)
+    ch.lib.cholmod_l_change_factor(CHOLMOD_REAL, 1, 1, 1, 1, Lp, C.byref(ch.cm))
     xsize = Lp.contents.xsize
+    _np_view(Lp.contents.x, xsize, np.float64)[:] = 0.0
+    t_begin = time.perf_counter()
+    t0 = time.perf_counter(); ok = f(S2, None, beta, Lp, C.byref(ch.cm)); t1 = time.perf_counter() - t0
+    assert ok and ch.cm.status == 0
+    times = []
+    if t1 * (steps + warmup) <= budget_s:
+        for _ in range(max(0, warmup - 1)):
+            f(S2, None, beta, Lp, C.byref(ch.cm))
+        warm_eff = max(1, warmup)
+        for _ in range(steps):
+            t0 = time.perf_counter(); ok = f(S2, None, beta, Lp, C.byref(ch.cm)); times.append(time.perf_counter() - t0)
+    else:
+        warm_eff = 0
+        times.append(t1)
+        while len(times) < steps and (time.perf_counter() - t_begin) + 1.1 * t1 <= budget_s:
+            t0 = time.perf_counter(); ok = f(S2, None, beta, Lp, C.byref(ch.cm)); times.append(time.perf_counter() - t0)
+    dt = float(np.mean(times))
+    assert ok and ch.cm.status == 0
     # solve sample
     b = np.ones(A.shape[0])
     ts = time.perf_counter(); x = ch.solve(Lp, b); ts = time.perf_counter() - ts
@@ -87,7 +113,8 @@ def time_reference_steps(kind, N, steps, warmup):
     Af = A + sp.triu(A, 1).T
     resid = float(np.linalg.norm(Af @ x - b) / np.linalg.norm(b))
     ch.free_sparse(S2); ch.free_factor(Lp)
-    return dict(gflops=fl / dt / 1e9, sec=dt, fl=fl, xsize=xsize, solve_gbs=16.0 * xsize / ts / 1e9, resid=resid, n=A.shape[0])
+    return dict(gflops=fl / dt / 1e9, sec=dt, fl=fl, xsize=xsize, solve_gbs=16.0 * xsize / ts / 1e9, resid=resid, n=A.shape[0],
+                steps_effective=len(times), warmup_effective=warm_eff, threads=threads, host_lib=os.path.relpath(ch.lib._name, REPO))
 
 
 class ClockSampler:
@@ -240,16 +267,21 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        Ns = args.cpu_sample_N or cpu_sample_size(args.steps, args.warmup)
+        # same workload as our arm (args.kind, args.N) unless a bounded sample is asked for explicitly (--cpu-sample-N:
+        # the in-line cpu_baseline of our arm)
+        Ns = args.cpu_sample_N or args.N
         r = time_reference_steps(args.kind, Ns, args.steps, args.warmup)
-        cores = os.cpu_count()
-        sample = f"{args.kind} {Ns}^3 (n={r['n']}, fl={r['fl']:.3e}); the full {args.N}^3 step takes ~180 s on 8 cores"
+        sample = (f"full workload {args.kind} {Ns}^3" if Ns == args.N else f"bounded sample {args.kind} {Ns}^3 of the {args.N}^3 workload") + \
+                 f" (n={r['n']}, fl={r['fl']:.3e}), {r['steps_effective']} timed full-size step(s) after {r['warmup_effective']} warm-up"
+        cfg = {"workload": workload if Ns == args.N else f"{args.kind} {Ns}^3 (sample of: {workload})", "n": r["n"], "fl": r["fl"], "xsize": int(r["xsize"]),
+               "steps_effective": r["steps_effective"], "warmup_effective": r["warmup_effective"],
+               "host_library": r["host_lib"], "blas": f"OpenBLAS (scipy-bundled), {r['threads']} threads set explicitly"}
         out = {"impl": "reference", "metric": "supernodal Cholesky factorize GFLOP/s (fp64)", "value": round(r["gflops"], 2), "unit": "GFLOP/s",
                "n_gpus": 0, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(r["sec"] * 1e3, 2), "higher_is_better": True,
                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-               "config": {"workload": workload, "sample": sample},
-               "cpu_baseline": {"value": round(r["gflops"], 2), "unit": "GFLOP/s", "cores": cores, "kind": "reference", "sample": sample,
-                                "blas": "OpenBLAS (scipy-bundled), threads = all host cores", "solve_GBps": round(r["solve_gbs"], 2), "resid": r["resid"]},
+               "config": cfg,
+               "cpu_baseline": {"value": round(r["gflops"], 2), "unit": "GFLOP/s", "cores": r["threads"], "kind": "reference", "sample": sample,
+                                "blas": f"OpenBLAS (scipy-bundled), {r['threads']} threads", "solve_GBps": round(r["solve_gbs"], 2), "resid": r["resid"]},
                "e2e": {"value": round(r["gflops"], 2), "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(out), flush=True)
         return
@@ -380,10 +412,12 @@ def main():
                "wall_ms_per_resident_step": round(wall_res * 1e3, 2)}
         out["solve"]["frac_of_hbm"] = round(out["solve"]["value"] / out["solve"]["hbm_peak_GBps"], 4)
         if not args.no_cpu_baseline and world == 1:
-            Ns = args.cpu_sample_N or 64
+            # bounded sample (about 10-30 s of CPU work on this box's cores): one size below the workload; the full-size
+            # reference run is the `--impl reference` arm
+            Ns = args.cpu_sample_N or min(args.N, 80)
             # separate process: the interposed symbols of this process must not be bound there
             try:
-                p = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "2", "--warmup", "1", "--cpu-sample-N", str(Ns),
+                p = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--warmup", "0", "--cpu-sample-N", str(Ns),
                                     "--kind", args.kind, "--N", str(args.N)], capture_output=True, text=True, timeout=600)
                 ref = json.loads(p.stdout.strip().splitlines()[-1])
                 out["cpu_baseline"] = ref["cpu_baseline"]

@@ -167,6 +167,11 @@ int  cholmod_l_gpu_probe     (ssb_cholmod_common *Common);
 int  cholmod_l_gpu_allocate  (ssb_cholmod_common *Common);
 int  cholmod_l_gpu_deallocate(ssb_cholmod_common *Common);
 void cholmod_l_gpu_end       (ssb_cholmod_common *Common);
+/* Core/cholmod_factor.c:152 interposed: drops the cached device plan and the page-lock of L->x, then calls the host
+ * library's own cholmod_l_free_factor (next definition in the symbol search order). */
+int  cholmod_l_free_factor   (ssb_cholmod_factor **L, ssb_cholmod_common *Common);
+/* the caller changed L->x in place: the next solve uploads the host values again.  Returns 1 if L had a cached plan. */
+int  ssb200_invalidate_factor(const ssb_cholmod_factor *L);
 #endif /* SSB200_NO_DROPIN_PROTOTYPES */
 #endif /* SSB200_NO_CHOLMOD_TYPES */
 
@@ -210,7 +215,6 @@ int      ssb200_dist_end(ssb200_plan *plan, ssb_long *first_bad_column);
 int      ssb200_dist_zero_from(ssb200_plan *plan, ssb_long column);
 int      ssb200_dist_not_posdef(ssb200_plan *plan, ssb_long minor, int quick_return, int *redo_rank, ssb_long *off, ssb_long *cnt);
 int      ssb200_dist_flops(const ssb200_plan *plan, double *mine, double *total);
-int      ssb200_plan_set_owner(ssb200_plan *plan, const int32_t *owner, int rank);   /* superseded by ssb200_plan_create_dist */
 
 /* Numeric factorization.  A (and F for stype==0) are HOST CSC arrays with 64-bit indices:
  * Ap[n+1], Ai, Ax and optional Anz (unpacked).  stype<0 symmetric-lower input, stype==0 A*F.
@@ -236,6 +240,9 @@ int ssb200_upload_L(ssb200_plan *plan, const double *Lx_host);
 int ssb200_solve(ssb200_plan *plan, int which, double *X, ssb_long nrhs, ssb_long ldx);
 /* same with X already on the device (device pointer) */
 int ssb200_solve_resident(ssb200_plan *plan, int which, double *dX, ssb_long nrhs, ssb_long ldx);
+
+/* diag_host[k] = L(k,k), k < n, read from the device-resident factor (what Cholesky/cholmod_rcond.c:102-125 scans). */
+int ssb200_factor_diag(ssb200_plan *plan, double *diag_host);
 
 /* Raw device pointers / sizes for callers that manage their own streams or collectives. */
 double  *ssb200_device_Lx(ssb200_plan *plan);

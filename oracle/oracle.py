@@ -9,6 +9,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 PORT_LIB = os.path.join(HERE, "_ref", "libssb_oracle.so")
 REF_LIB = os.path.join(HERE, "_ref", "libcholmod_ref.so")
+HOST_LIB = os.path.join(os.path.dirname(HERE), "baseline", "_ref", "libcholmod.so")   # the application's host library
 
 
 def build(ref: bool = True):
@@ -17,6 +18,8 @@ def build(ref: bool = True):
     if ref and os.path.isdir(os.environ.get("SSB200_REFERENCE", "/root/reference")):
         if not os.path.exists(REF_LIB):
             subprocess.check_call(["make", "-s", "-C", HERE, "ref"])
+        if not os.path.exists(HOST_LIB):
+            subprocess.check_call(["make", "-s", "-C", HERE, "host"])
         if not os.path.exists(os.path.join(HERE, "_ref", "cholmod_l_demo")):
             subprocess.check_call(["make", "-s", "-C", HERE, "demo"])
 

@@ -4,7 +4,7 @@ A CHOLMOD user calls cholmod_l_start / analyze / factorize / solve on a host lib
 (CHOLMOD/Include/cholmod_cholesky.h:89,113,160,216).  This module is that user, in Python: it loads
   1. libsuitesparse_b200.so with RTLD_GLOBAL (optional: the GPU arm), which defines
      cholmod_l_super_numeric / _lsolve / _ltsolve, and then
-  2. the host libcholmod (any build of the reference; on this box oracle/_ref/libcholmod_ref.so),
+  2. the host libcholmod (any build of the reference; on this box baseline/_ref/libcholmod.so),
 so the host library's PLT calls at cholmod_factorize.c:265 and cholmod_solve.c:1568-1577 bind to the
 B200 implementation — the same interposition LD_PRELOAD gives a C program.
 The struct layouts restate include/suitesparse_b200.h (which restates cholmod_core.h).
@@ -112,8 +112,9 @@ B200_LIB = os.path.join(REPO, "suitesparse_b200", "csrc", "libsuitesparse_b200.s
 
 
 def default_host_cholmod() -> str:
-    """The host libcholmod the application links: $SSB200_CHOLMOD_LIB, else this box's reference build."""
-    return os.environ.get("SSB200_CHOLMOD_LIB", os.path.join(REPO, "oracle", "_ref", "libcholmod_ref.so"))
+    """The host libcholmod the application links: $SSB200_CHOLMOD_LIB, else this box's build of the unmodified
+    reference (baseline/_ref/libcholmod.so, built by `make -C oracle host`; never anything under oracle/)."""
+    return os.environ.get("SSB200_CHOLMOD_LIB", os.path.join(REPO, "baseline", "_ref", "libcholmod.so"))
 
 
 _b200_handle = None
@@ -272,7 +273,11 @@ class Cholmod:
 
     def free_factor(self, Lp):
         pp = C.POINTER(Factor)(Lp.contents)
-        self.lib.cholmod_l_free_factor(C.byref(pp), C.byref(self.cm))
+        # a C program resolves cholmod_l_free_factor to the interposed definition (which drops the cached plan and then
+        # calls the host library's); ctypes resolves per handle, so pick the same one explicitly
+        lib = self.b200 if self.gpu else self.lib
+        lib.cholmod_l_free_factor.argtypes = [C.POINTER(C.POINTER(Factor)), C.POINTER(Common)]
+        lib.cholmod_l_free_factor(C.byref(pp), C.byref(self.cm))
 
     def free_sparse(self, Sp):
         pp = C.POINTER(Sparse)(Sp.contents)

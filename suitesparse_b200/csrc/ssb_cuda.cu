@@ -83,6 +83,7 @@ struct ssb200_plan {
     long long *d_pi = nullptr, *d_px = nullptr;
     double *d_Lx = nullptr;
     double *d_winv = nullptr; long long winv_slots = 0;   // inverses of the wide 64x64 diagonal blocks (trsm_tc + solves)
+    double *d_probe = nullptr;               // 8-byte scratch of the host-registration probe
     DevJobs jobs;
     SolveJob *d_solve_jobs = nullptr; int *d_solve_tiles = nullptr;
     int *h_info = nullptr;                 // pinned
@@ -140,7 +141,7 @@ static void plan_free(ssb200_plan *p)
 {
     if (!p) return;
     cudaSetDevice(p->device);
-    void *ptrs[] = {p->d_owner, p->d_super, p->d_ls, p->d_supermap, p->d_relmap, p->d_info, p->d_pi, p->d_px, p->d_Lx, p->d_winv, p->jobs.gemm_jobs,
+    void *ptrs[] = {p->d_probe, p->d_owner, p->d_super, p->d_ls, p->d_supermap, p->d_relmap, p->d_info, p->d_pi, p->d_px, p->d_Lx, p->d_winv, p->jobs.gemm_jobs,
                     p->jobs.gemm_tiles, p->jobs.potrf_jobs, p->jobs.trsm_jobs, p->jobs.trsm_tiles, p->d_solve_jobs, p->d_solve_tiles,
                     p->d_X};
     for (void *q : ptrs) if (q) cudaFree(q);
@@ -193,6 +194,7 @@ static int plan_build_device(ssb200_plan *p)
     p->winv_slots = std::max(1, hp.max_winv_slots);
     const size_t wbytes = (size_t) p->winv_slots * NB_INNER * NB_INNER * sizeof(double);
     CU_TRY(cudaMalloc((void **) &p->d_winv, wbytes)); p->device_bytes += wbytes;
+    CU_TRY(cudaMalloc((void **) &p->d_probe, 64)); p->device_bytes += 64;
     const size_t ibytes = std::max<long long>(hp.nsuper, 1) * sizeof(int);
     CU_TRY(cudaMalloc((void **) &p->d_info, ibytes)); p->device_bytes += ibytes;
     CU_TRY(cudaMallocHost((void **) &p->h_info, ibytes));
@@ -371,13 +373,6 @@ extern "C" int ssb200_dist_flops(const ssb200_plan *p, double *mine, double *tot
     if (!p) return SSB_CHOLMOD_INVALID;
     *mine = p->hp.my_flops; *total = p->hp.flops_update + p->hp.flops_potrf + p->hp.flops_trsm;
     return 0;
-}
-
-extern "C" int ssb200_plan_set_owner(ssb200_plan *plan, const int32_t *owner, int rank)
-{
-    (void) plan; (void) owner; (void) rank;
-    set_error("ssb200_plan_set_owner: use ssb200_plan_create_dist (the shard is computed by the plan builder)");
-    return SSB_CHOLMOD_NOT_INSTALLED;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -850,6 +845,23 @@ extern "C" int ssb200_solve(ssb200_plan *p, int which, double *X, ssb_long nrhs,
     return 0;
 }
 
+// diag_host[k] = L(k,k) of the device-resident factor (n doubles): enough for cholmod_rcond's min/max ratio and for
+// log det A = 2 sum log L(k,k), without moving the factor
+extern "C" int ssb200_factor_diag(ssb200_plan *p, double *diag_host)
+{
+    if (!p || !diag_host) { set_error("null argument"); return SSB_CHOLMOD_INVALID; }
+    if (!p->factor_on_device) { set_error("no numeric factor on the device"); return SSB_CHOLMOD_INVALID; }
+    const long long n = p->hp.n;
+    if (n == 0) return 0;
+    CU_TRY(cudaSetDevice(p->device));
+    if (ensure_cap(p, &p->d_X, &p->capX, (size_t) n)) return SSB_CHOLMOD_GPU_PROBLEM;
+    factor_diag_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, p->stream>>>(dev_sym(p), p->d_Lx, p->d_X);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpyAsync(diag_host, p->d_X, n * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    CU_TRY(cudaStreamSynchronize(p->stream));
+    return 0;
+}
+
 extern "C" double *ssb200_device_Lx(ssb200_plan *p) { return p ? p->d_Lx : nullptr; }
 extern "C" ssb_long ssb200_xsize(const ssb200_plan *p) { return p ? p->hp.xsize : 0; }
 extern "C" void *ssb200_stream(ssb200_plan *p) { return p ? (void *) p->stream : nullptr; }
@@ -924,8 +936,7 @@ static unsigned long long hash_symbolic(const ssb_cholmod_factor *L)
     const long long *super = (const long long *) L->super, *pi = (const long long *) L->pi, *px = (const long long *) L->px, *s = (const long long *) L->s;
     for (size_t t = 0; t <= L->nsuper; t++) { mix(super[t]); mix(pi[t]); mix(px[t]); }
     const size_t ss = L->ssize ? (size_t) pi[L->nsuper] : 0;
-    const size_t step = std::max<size_t>(1, ss / 65536);
-    for (size_t t = 0; t < ss; t += step) mix(s[t]);
+    for (size_t t = 0; t < ss; t++) mix(s[t]);          // every row index: a factor with another pattern at the same address gets a new plan
     return h;
 }
 
@@ -958,13 +969,19 @@ static bool pin_probe(CacheEntry *e, const ssb_cholmod_factor *L)
     volatile double *x = (volatile double *) L->x;
     const size_t idx[3] = {0, L->xsize / 2, L->xsize - 1};
     static const double magic = 0x1.b200b200b200bp+77;
-    if (cudaMemcpyAsync(p->d_winv, &magic, sizeof(double), cudaMemcpyHostToDevice, p->stream) != cudaSuccess) { (void) cudaGetLastError(); return false; }
-    for (size_t t : idx) x[t] = 0.0;
-    for (size_t t : idx)
-        if (cudaMemcpyAsync((void *) &x[t], p->d_winv, sizeof(double), cudaMemcpyDeviceToHost, p->stream) != cudaSuccess) { (void) cudaGetLastError(); return false; }
-    if (cudaStreamSynchronize(p->stream) != cudaSuccess) { (void) cudaGetLastError(); return false; }
-    for (size_t t : idx) { const double v = x[t]; if (memcmp(&v, &magic, sizeof(double)) != 0) return false; }
-    return true;
+    double saved[3];
+    for (int t = 0; t < 3; t++) saved[t] = x[idx[t]];       // a refactorization that fails later must leave L->x as it was
+    bool ok = cudaMemcpyAsync(p->d_probe, &magic, sizeof(double), cudaMemcpyHostToDevice, p->stream) == cudaSuccess;
+    if (ok) {
+        for (size_t t : idx) x[t] = 0.0;
+        for (size_t t : idx)
+            if (cudaMemcpyAsync((void *) &x[t], p->d_probe, sizeof(double), cudaMemcpyDeviceToHost, p->stream) != cudaSuccess) ok = false;
+        if (cudaStreamSynchronize(p->stream) != cudaSuccess) ok = false;
+        if (ok) for (size_t t : idx) { const double v = x[t]; if (memcmp(&v, &magic, sizeof(double)) != 0) ok = false; }
+    }
+    if (!ok) (void) cudaGetLastError();
+    for (int t = 0; t < 3; t++) x[idx[t]] = saved[t];
+    return ok;
 }
 
 static void pin_host_x(CacheEntry *e, const ssb_cholmod_factor *L)
@@ -1085,8 +1102,19 @@ extern "C" int cholmod_l_super_numeric(ssb_cholmod_sparse *A, ssb_cholmod_sparse
         if (verbose < 0) { const char *v = getenv("SSB200_VERBOSE"); verbose = (v && atoi(v)) ? 1 : 0; }
         if (verbose) fprintf(stderr, "[suitesparse_b200] cholmod_l_super_numeric: n=%zu nsuper=%zu xsize=%zu (CUDA path)\n", L->n, L->nsuper, L->xsize);
     }
+    // On failure L is given back in the form it had on input (cholmod_super_numeric.c:235-248): a factor that was symbolic
+    // goes back to CHOLMOD_PATTERN (its freshly allocated L->x holds garbage), the plan and its page-lock are dropped.
+    auto fail = [&](int status, const std::string &msg) {
+        if (CacheEntry *ce = cache_find(L)) { if (ce->plan) { ce->plan->factor_on_device = false; ce->plan->winv_valid = false; } if (symbolic) cache_drop(ce); }
+        if (symbolic) {
+            static change_factor_fn cf2 = (change_factor_fn) host_sym("cholmod_l_change_factor");
+            if (cf2) cf2(SSB_CHOLMOD_PATTERN, 1, 1, 1, 1, L, Common);
+        }
+        raise_error(Common, status, __LINE__, msg.c_str());
+        return 0;
+    };
     CacheEntry *e = cache_get_plan(L);
-    if (!e) { RAISE(Common, SSB_CHOLMOD_GPU_PROBLEM, ssb200_last_error()); return 0; }
+    if (!e) return fail(SSB_CHOLMOD_GPU_PROBLEM, ssb200_last_error());
     pin_host_x(e, L);
     ssb_long minor = (ssb_long) L->n;
     const int rc = ssb200_factorize(e->plan, stype, (const ssb_long *) A->p, (const ssb_long *) A->i, A->packed ? nullptr : (const ssb_long *) A->nz,
@@ -1094,7 +1122,7 @@ extern "C" int cholmod_l_super_numeric(ssb_cholmod_sparse *A, ssb_cholmod_sparse
                                     F ? (const ssb_long *) F->p : nullptr, F ? (const ssb_long *) F->i : nullptr,
                                     (F && !F->packed) ? (const ssb_long *) F->nz : nullptr, F ? (const double *) F->x : nullptr,
                                     beta, Common->quick_return_if_not_posdef, (double *) L->x, &minor);
-    if (rc < 0) { RAISE(Common, rc == SSB_CHOLMOD_INVALID ? SSB_CHOLMOD_INVALID : SSB_CHOLMOD_GPU_PROBLEM, ssb200_last_error()); return 0; }
+    if (rc < 0) return fail(rc == SSB_CHOLMOD_INVALID ? SSB_CHOLMOD_INVALID : SSB_CHOLMOD_GPU_PROBLEM, ssb200_last_error());
     take_value_fingerprint(e, L);
     // statistics the reference keeps in Common (cholmod_core.h:1002-1048)
     const ssb200_stats &st = e->plan->stats;
@@ -1176,9 +1204,12 @@ extern "C" int cholmod_l_gpu_probe(ssb_cholmod_common *Common)
     (void) Common;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return 0;
+    int dev = 0;                    // the device the drop-in layer will use: SSB200_DEVICE, else the current one
+    if (const char *d = getenv("SSB200_DEVICE")) dev = atoi(d); else if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+    if (dev < 0 || dev >= ndev) return 0;
     cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, 0) != cudaSuccess) return 0;
-    return prop.major >= 10;        // the kernels are sm_100a only
+    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return 0;
+    return prop.major == 10;        // the kernels are sm_100a only
 }
 extern "C" int cholmod_l_gpu_allocate(ssb_cholmod_common *Common) { (void) Common; return 0; }      // plans own their memory; nothing to pre-allocate
 extern "C" int cholmod_l_gpu_deallocate(ssb_cholmod_common *Common)
@@ -1189,6 +1220,34 @@ extern "C" int cholmod_l_gpu_deallocate(ssb_cholmod_common *Common)
     return 0;
 }
 extern "C" void cholmod_l_gpu_end(ssb_cholmod_common *Common) { cholmod_l_gpu_deallocate(Common); }
+
+// The device copy of a factor is trusted by the solves when L->x still is the buffer the last factorization wrote and a
+// sampled fingerprint matches.  A caller that edits L->x in place tells the library so with this call (the next solve
+// uploads the host values again); freeing the factor through cholmod_l_free_factor below drops everything.
+extern "C" int ssb200_invalidate_factor(const ssb_cholmod_factor *L)
+{
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    CacheEntry *e = cache_find(L);
+    if (!e) return 0;
+    e->plan->factor_on_device = false; e->plan->winv_valid = false; e->xptr = nullptr;
+    return 1;
+}
+
+// cholmod_l_free_factor (Core/cholmod_factor.c:152) interposed: the plan cache is keyed by the factor's address and holds
+// xsize doubles of HBM plus a page-lock on L->x, so the entry must die with the factor.  Then the host library's own
+// definition (next in the symbol search order) does the real work.
+typedef int (*free_factor_fn)(ssb_cholmod_factor **, ssb_cholmod_common *);
+extern "C" int cholmod_l_free_factor(ssb_cholmod_factor **LHandle, ssb_cholmod_common *Common)
+{
+    if (LHandle && *LHandle) {
+        std::lock_guard<std::mutex> lk(g_cache_mu);
+        if (CacheEntry *e = cache_find(*LHandle)) cache_drop(e);
+    }
+    static free_factor_fn next = (free_factor_fn) dlsym(RTLD_NEXT, "cholmod_l_free_factor");
+    if (!next) next = (free_factor_fn) dlsym(RTLD_NEXT, "cholmod_l_free_factor");
+    if (!next) { if (Common) Common->status = SSB_CHOLMOD_INVALID; return 0; }
+    return next(LHandle, Common);
+}
 
 // plan of a cached factor (tests / bench: statistics of the drop-in path)
 extern "C" ssb200_plan *ssb200_plan_of_factor(const ssb_cholmod_factor *L)

@@ -667,6 +667,17 @@ __global__ void relmap_kernel(const DevUpdate *__restrict__ ups, const int *__re
         relmap[u.map_off + i] = find_row(rows_s, u.nsrow_s, ls[u.ls_d + i]);
 }
 
+// diagonal of L (what cholmod_rcond reads, Cholesky/cholmod_rcond.c:102-125): one thread per column
+__global__ void factor_diag_kernel(DevSym sym, const double *__restrict__ Lx, double *__restrict__ diag)
+{
+    const long long k = blockIdx.x * (long long) blockDim.x + threadIdx.x;
+    if (k >= sym.n) return;
+    const int s = sym.supermap[k];
+    const long long j = k - sym.super[s];
+    const long long nsrow = sym.pi[s + 1] - sym.pi[s];
+    diag[k] = Lx[sym.px[s] + j + j * nsrow];
+}
+
 __global__ void fill_int_kernel(int *p, long long n, int v)
 {
     const long long t = blockIdx.x * (long long) blockDim.x + threadIdx.x;

@@ -277,6 +277,22 @@ bool build_host_plan(long long n, long long nsuper, const long long *super, cons
         for (int t = 0; t < (int) nsuper; t++) first_desc[t] = t;
         for (int t = 0; t < (int) nsuper; t++)
             if (hp.parent[t] >= 0) { sub[hp.parent[t]] += sub[t]; first_desc[hp.parent[t]] = std::min(first_desc[hp.parent[t]], first_desc[t]); }
+        // The shard treats the subtree of r as the index range [first_desc[r], r] and its Lx as one contiguous range: true
+        // only for a postordered supernodal etree (cholmod_analyze.c:855 postorders when Common->postorder is TRUE).
+        {
+            std::vector<int> cnt(nsuper, 1);
+            for (int t = 0; t < (int) nsuper; t++) {
+                if (hp.parent[t] >= 0) {
+                    if (hp.parent[t] <= t) { hp.error = "supernodal elimination tree is not topologically ordered"; return false; }
+                    cnt[hp.parent[t]] += cnt[t];
+                }
+            }
+            for (int t = 0; t < (int) nsuper; t++)
+                if (cnt[t] != t - first_desc[t] + 1) {
+                    hp.error = "supernodal elimination tree is not postordered (analyze with Common->postorder = TRUE for the multi-GPU factorization)";
+                    return false;
+                }
+        }
         std::vector<std::vector<int>> kids(nsuper);
         std::vector<int> cand;                          // roots of the candidate subtrees
         double total = 0;

@@ -178,6 +178,37 @@ def elasticity(N: int, E: float = 1.0, nu: float = 0.3) -> sp.csc_matrix:
     return A
 
 
+def graded_laplacian(N: int, contrast: float = 1e10, seed: int = 42):
+    """Ill-conditioned SPD test matrix: 7-point variable-coefficient diffusion on an N^3 grid, node coefficients
+    c = contrast**u with u graded along x plus a seeded random part, edge weight = harmonic mean of its two nodes,
+    Dirichlet closure (a missing neighbour contributes the node's own coefficient to the diagonal).
+    cond(A) ~ contrast * N^2.  Returns (A_upper_csc, nested-dissection permutation)."""
+    m = n = k = N
+    G = mesh_index(m, n, k)
+    rng = np.random.default_rng(seed)
+    u = np.linspace(0.0, 1.0, m)[:, None, None] * 0.7 + 0.3 * rng.random((m, n, k))
+    c = contrast ** (u - 0.5)
+    nn = m * n * k
+    diag = np.zeros((m, n, k))
+    rows, cols, vals = [], [], []
+    for ax in range(3):
+        sl_a = [slice(None)] * 3; sl_b = [slice(None)] * 3
+        sl_a[ax] = slice(0, -1); sl_b[ax] = slice(1, None)
+        ca, cb = c[tuple(sl_a)], c[tuple(sl_b)]
+        w = 2.0 * ca * cb / (ca + cb)
+        diag[tuple(sl_a)] += w; diag[tuple(sl_b)] += w
+        rows.append(G[tuple(sl_a)].ravel()); cols.append(G[tuple(sl_b)].ravel()); vals.append(-w.ravel())
+        # Dirichlet closure on the two faces of this axis
+        f0 = [slice(None)] * 3; f1 = [slice(None)] * 3
+        f0[ax] = 0; f1[ax] = -1
+        diag[tuple(f0)] += c[tuple(f0)]; diag[tuple(f1)] += c[tuple(f1)]
+    rows.append(np.arange(nn, dtype=np.int64)); cols.append(np.arange(nn, dtype=np.int64)); vals.append(diag.ravel(order="F"))
+    A = sp.csc_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(nn, nn))
+    A.sort_indices()
+    A.indices = A.indices.astype(np.int64); A.indptr = A.indptr.astype(np.int64)
+    return A, meshnd_perm(m, n, k)
+
+
 def expand_perm(p: np.ndarray, ndof: int) -> np.ndarray:
     """Node permutation -> DOF permutation (DOF = ndof*node + c)."""
     return (ndof * p[:, None] + np.arange(ndof, dtype=np.int64)[None, :]).ravel()

@@ -50,6 +50,7 @@ def _lib():
         L.ssb200_xsize.argtypes = [C.c_void_p]
         L.ssb200_debug_relmap.restype = c_long
         L.ssb200_debug_relmap.argtypes = [C.c_void_p, C.c_void_p, c_long]
+        L.ssb200_factor_diag.argtypes = [C.c_void_p, C.c_void_p]
         L.ssb200_plan_of_factor.restype = C.c_void_p
         L.ssb200_plan_of_factor.argtypes = [C.c_void_p]
         L._ssb_typed = True
@@ -131,6 +132,11 @@ class Plan:
 
     def solve_resident(self, dX_ptr: int, nrhs: int, ldx: int, which: int = 2):
         self._check(self.lib.ssb200_solve_resident(self.h, which, C.c_void_p(dX_ptr), nrhs, ldx))
+
+    def factor_diag(self) -> np.ndarray:
+        d = np.empty(self.n, dtype=np.float64)
+        self._check(self.lib.ssb200_factor_diag(self.h, _ptr(d)))
+        return d
 
     def stats(self) -> dict:
         st = Stats()
