@@ -170,6 +170,9 @@ void cholmod_l_gpu_end       (ssb_cholmod_common *Common);
 /* Core/cholmod_factor.c:152 interposed: drops the cached device plan and the page-lock of L->x, then calls the host
  * library's own cholmod_l_free_factor (next definition in the symbol search order). */
 int  cholmod_l_free_factor   (ssb_cholmod_factor **L, ssb_cholmod_common *Common);
+/* The drop-in entry points fan one factorization out over the devices listed in $SSB200_DEVICES ("0,1,2,3" or "all";
+ * two or more -> ssb200_mg_*); this returns the multi-GPU plan cached for L, or NULL. */
+struct ssb200_mg *ssb200_mg_of_factor(const ssb_cholmod_factor *L);
 /* the caller changed L->x in place: the next solve uploads the host values again.  Returns 1 if L had a cached plan. */
 int  ssb200_invalidate_factor(const ssb_cholmod_factor *L);
 #endif /* SSB200_NO_DROPIN_PROTOTYPES */
@@ -216,6 +219,33 @@ int      ssb200_dist_zero_from(ssb200_plan *plan, ssb_long column);
 int      ssb200_dist_not_posdef(ssb200_plan *plan, ssb_long minor, int quick_return, int *redo_rank, ssb_long *off, ssb_long *cnt);
 int      ssb200_dist_flops(const ssb200_plan *plan, double *mine, double *total);
 
+/* ---- Multi-GPU inside ONE process (the reference "can only utilize a single GPU", GPU/cholmod_gpu.c:160-164).
+ * The elimination tree is cut into subtrees owned by one device each, the wide top supernodes are shared panel-cyclically;
+ * the factor is DISTRIBUTED: a device stores its own supernodes, the cyclic ones, and the remote supernodes its updates read,
+ * which it pulls over NVLink (peer-mapped pointers, copy kernel) as soon as their owner has finished them.  One host thread
+ * per device, CUDA events across devices, no NCCL.  devices == NULL: ordinals 0..ndev-1.  Lx_host (optional, xsize doubles,
+ * CHOLMOD's layout) receives every device's share over that device's own PCIe link while the factorization runs
+ * (page-lock it once with ssb200_mg_pin_host).  A matrix that is not positive definite returns 1 with *minor_out set; the
+ * partial refactorization of the failing supernode (t_cholmod_super_numeric.c:944-967) is then left to the single-GPU path. */
+typedef struct ssb200_mg ssb200_mg;
+ssb200_mg *ssb200_mg_create(ssb_long n, ssb_long nsuper, const ssb_long *super, const ssb_long *pi, const ssb_long *px,
+                            const ssb_long *s, int ndev, const int *devices);
+void ssb200_mg_destroy(ssb200_mg *mg);
+int  ssb200_mg_pin_host(ssb200_mg *mg, double *Lx_host);
+int  ssb200_mg_factorize(ssb200_mg *mg, int stype,
+                         const ssb_long *Ap, const ssb_long *Ai, const ssb_long *Anz, const double *Ax, ssb_long ncolA,
+                         const ssb_long *Fp, const ssb_long *Fi, const ssb_long *Fnz, const double *Fx,
+                         const double beta[2], double *Lx_host, ssb_long *minor_out);
+/* X (host, n-by-nrhs, leading dimension ldx) <- L\X, L'\X or both, on the distributed factor: right-hand sides on device
+ * 0, every device solves with its own blocks and reaches X over NVLink. */
+int  ssb200_mg_solve(ssb200_mg *mg, int which, double *X, ssb_long nrhs, ssb_long ldx);
+/* host factor (CHOLMOD layout) -> the devices' local storage (a factor computed elsewhere; the solves then work without
+ * the inverses of the diagonal blocks) */
+int  ssb200_mg_upload_L(ssb200_mg *mg, const double *Lx_host);
+/* out[0] wall ms of the last factorization, out[1] of the last solve, out[2] NVLink bytes pulled per factorization,
+ * out[3+r] HBM bytes held by rank r, out[3+N+r] dense flops of rank r; returns the number of devices. */
+int  ssb200_mg_info(const ssb200_mg *mg, double *out, int cap);
+
 /* Numeric factorization.  A (and F for stype==0) are HOST CSC arrays with 64-bit indices:
  * Ap[n+1], Ai, Ax and optional Anz (unpacked).  stype<0 symmetric-lower input, stype==0 A*F.
  * Lx_host (xsize doubles) receives the factor if not NULL.  *minor_out = n on success, else the
@@ -240,6 +270,11 @@ int ssb200_upload_L(ssb200_plan *plan, const double *Lx_host);
 int ssb200_solve(ssb200_plan *plan, int which, double *X, ssb_long nrhs, ssb_long ldx);
 /* same with X already on the device (device pointer) */
 int ssb200_solve_resident(ssb200_plan *plan, int which, double *dX, ssb_long nrhs, ssb_long ldx);
+
+/* Look-ahead schedule (default on): the latency-bound potrf/trsm chain of the next 1024-column outer panel runs on a
+ * high-priority stream while the main stream applies the previous outer panel to the rest of the supernode.  With it on
+ * only total device times are reported; off = one stream, timing events around every launch (ssb200_stats.ms_kind). */
+int ssb200_set_lookahead(ssb200_plan *plan, int on);
 
 /* diag_host[k] = L(k,k), k < n, read from the device-resident factor (what Cholesky/cholmod_rcond.c:102-125 scans). */
 int ssb200_factor_diag(ssb200_plan *plan, double *diag_host);

@@ -13,6 +13,7 @@
 #include <condition_variable>
 #include <deque>
 #include <atomic>
+#include <chrono>
 #include <string>
 #include <vector>
 #include <algorithm>
@@ -62,7 +63,7 @@ struct Copier {
 };
 
 // parameters baked into the captured factorization graph
-struct FactorGraphKey { double beta0; double *host; int stype; const void *a[4]; const void *f[4]; };
+struct FactorGraphKey { double beta0; double *host; int stype; int two_streams; const void *a[4]; const void *f[4]; };
 
 struct CscBuf { long long *p = nullptr, *i = nullptr, *nz = nullptr; double *x = nullptr; size_t capP = 0, capI = 0, capNz = 0, capX = 0; bool haveNz = false; };
 static void free_cscbuf(CscBuf *b) { if (!b) return; if (b->p) cudaFree(b->p); if (b->i) cudaFree(b->i); if (b->nz) cudaFree(b->nz); if (b->x) cudaFree(b->x); delete b; }
@@ -73,6 +74,12 @@ struct ssb200_plan {
     cudaStream_t stream = nullptr;           // launches go here (the plan's own stream, or the caller's: ssb200_set_stream)
     cudaStream_t own_stream = nullptr;
     int *d_owner = nullptr;                  // sharded plans: owner rank per supernode (-1 = panel-cyclic)
+    cudaStream_t panel_stream = nullptr;     // look-ahead: the potrf/trsm/small-K chain of the next outer panel (high priority)
+    std::vector<cudaEvent_t> la_events;      // cross-stream events of the look-ahead schedule (HostPlan::n_events)
+    int panel_prio = 0;
+    bool capturing = false;                  // a factorization graph is being captured
+    std::vector<cudaGraphNode_t> cap_high_nodes;   // captured kernel nodes of the panel stream (their priority is set on the graph)
+    bool lookahead = true;                   // run the schedule on two streams; false: one stream, per-launch timing events
     cudaStream_t copy_stream = nullptr;      // device-to-host streaming of finished supernodes
     cudaEvent_t copy_gate = nullptr, copy_done = nullptr;
     std::vector<cudaEvent_t> copy_gates;     // one per copy-task group
@@ -82,6 +89,7 @@ struct ssb200_plan {
     int *d_super = nullptr, *d_ls = nullptr, *d_supermap = nullptr, *d_relmap = nullptr, *d_info = nullptr;
     long long *d_pi = nullptr, *d_px = nullptr;
     double *d_Lx = nullptr;
+    long long lx_alloc = 0;                  // doubles behind d_Lx: xsize, or the local share under distributed storage
     double *d_winv = nullptr; long long winv_slots = 0;   // inverses of the wide 64x64 diagonal blocks (trsm_tc + solves)
     double *d_probe = nullptr;               // 8-byte scratch of the host-registration probe
     DevJobs jobs;
@@ -154,6 +162,8 @@ static void plan_free(ssb200_plan *p)
     for (auto e : p->copy_gates) cudaEventDestroy(e);
     if (p->copy_gate) cudaEventDestroy(p->copy_gate);
     if (p->copy_done) cudaEventDestroy(p->copy_done);
+    for (auto e : p->la_events) cudaEventDestroy(e);
+    if (p->panel_stream) cudaStreamDestroy(p->panel_stream);
     if (p->copy_stream) cudaStreamDestroy(p->copy_stream);
     if (p->own_stream) cudaStreamDestroy(p->own_stream);
     delete p;
@@ -181,7 +191,7 @@ static int plan_build_device(ssb200_plan *p)
     if (configure_kernels_once()) return SSB_CHOLMOD_GPU_PROBLEM;
     if (dev_alloc_copy(p, &p->d_super, hp.super)) return SSB_CHOLMOD_GPU_PROBLEM;
     if (dev_alloc_copy(p, &p->d_pi, hp.pi)) return SSB_CHOLMOD_GPU_PROBLEM;
-    if (dev_alloc_copy(p, &p->d_px, hp.px)) return SSB_CHOLMOD_GPU_PROBLEM;
+    if (dev_alloc_copy(p, &p->d_px, hp.compact ? hp.lpx : hp.px)) return SSB_CHOLMOD_GPU_PROBLEM;   // distributed storage: local offsets
     if (dev_alloc_copy(p, &p->d_ls, hp.ls)) return SSB_CHOLMOD_GPU_PROBLEM;
     if (dev_alloc_copy(p, &p->d_supermap, hp.supermap)) return SSB_CHOLMOD_GPU_PROBLEM;
     if (hp.nranks > 1) if (dev_alloc_copy(p, &p->d_owner, hp.owner)) return SSB_CHOLMOD_GPU_PROBLEM;
@@ -189,7 +199,8 @@ static int plan_build_device(ssb200_plan *p)
     if (upload_jobs(p, hp, p->jobs)) return SSB_CHOLMOD_GPU_PROBLEM;
     if (dev_alloc_copy(p, &p->d_solve_jobs, hp.solve_jobs)) return SSB_CHOLMOD_GPU_PROBLEM;
     if (dev_alloc_copy(p, &p->d_solve_tiles, hp.solve_tiles)) return SSB_CHOLMOD_GPU_PROBLEM;
-    const size_t xbytes = std::max<long long>(hp.xsize, 1) * sizeof(double);
+    p->lx_alloc = hp.compact ? hp.lxsize : hp.xsize;
+    const size_t xbytes = std::max<long long>(p->lx_alloc, 1) * sizeof(double);
     CU_TRY(cudaMalloc((void **) &p->d_Lx, xbytes)); p->device_bytes += xbytes;
     p->winv_slots = std::max(1, hp.max_winv_slots);
     const size_t wbytes = (size_t) p->winv_slots * NB_INNER * NB_INNER * sizeof(double);
@@ -229,7 +240,7 @@ static int plan_build_device(ssb200_plan *p)
 }
 
 static ssb200_plan *plan_create_impl(ssb_long n, ssb_long nsuper, const ssb_long *super, const ssb_long *pi, const ssb_long *px,
-                                     const ssb_long *s, int device, int nranks, int rank)
+                                     const ssb_long *s, int device, int nranks, int rank, bool compact = false)
 {
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_error("no CUDA device: the hot path has no CPU fallback"); return nullptr; }
@@ -239,12 +250,20 @@ static ssb200_plan *plan_create_impl(ssb_long n, ssb_long nsuper, const ssb_long
     ssb200_plan *p = new ssb200_plan();
     p->device = device; p->bufA = new CscBuf(); p->bufF = new CscBuf();
     if (!build_host_plan(n, nsuper, (const long long *) super, (const long long *) pi, (const long long *) px, (const long long *) s,
-                         nranks, rank, p->hp)) {
+                         nranks, rank, p->hp, compact)) {
         set_error("invalid symbolic factor: " + p->hp.error); delete p; return nullptr;
     }
     if (cudaStreamCreateWithFlags(&p->own_stream, cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&p->copy_gate, cudaEventDisableTiming) != cudaSuccess || cudaEventCreate(&p->copy_done) != cudaSuccess) { set_error("cudaStreamCreate failed"); delete p; return nullptr; }
     p->stream = p->own_stream;
+    {
+        int lo = 0, hi = 0;                  // numerically lowest value = highest priority
+        if (cudaDeviceGetStreamPriorityRange(&lo, &hi) != cudaSuccess) { lo = 0; hi = 0; }
+        if (cudaStreamCreateWithPriority(&p->panel_stream, cudaStreamNonBlocking, hi) != cudaSuccess) { set_error("cudaStreamCreateWithPriority failed"); plan_free(p); return nullptr; }
+        p->panel_prio = hi;
+        if (const char *e = getenv("SSB200_LOOKAHEAD")) p->lookahead = atoi(e) != 0;
+        if (nranks > 1) p->lookahead = false;            // the sharded path has its own look-ahead (DistStep)
+    }
     if (plan_build_device(p) != 0) { plan_free(p); return nullptr; }
     return p;
 }
@@ -287,7 +306,7 @@ extern "C" int ssb200_dist_step_info(const ssb200_plan *p, ssb_long k, int *src,
 
 static int scatter_A(ssb200_plan *p, double beta0, long long kfirst, long long kcount, bool ignore_owner);
 static int handle_not_posdef(ssb200_plan *p, int sfail, int info, double beta0, int quick_return, ssb_long *minor_out);
-static int run_launch(ssb200_plan *p, const Launch &L, const DevJobs &dj);
+static int run_launch(ssb200_plan *p, const Launch &L, const DevJobs &dj, bool two_streams = false);
 
 // zero Lx, assemble the columns this rank computes; everything is enqueued on the plan's stream, nothing is synchronized
 extern "C" int ssb200_dist_begin(ssb200_plan *p, const double beta[2])
@@ -432,40 +451,69 @@ extern "C" int ssb200_upload_A(ssb200_plan *p, int stype, const ssb_long *Ap, co
 // ---------------------------------------------------------------------------------------------------------------
 // launches
 // ---------------------------------------------------------------------------------------------------------------
-static int run_launch(ssb200_plan *p, const Launch &L, const DevJobs &dj)
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_ex(void (*kern)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t st, bool high, int prio, Args... args)
 {
+    cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributePriority; at[0].val.priority = prio;     // explicit: also recorded in captured graph nodes
+    cfg.attrs = at; cfg.numAttrs = high ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+
+// two_streams: the launch goes to the stream its schedule entry names (panel chain: high priority), after that stream has
+// waited for L.wait_ev; L.rec_ev is recorded behind it.  Otherwise everything runs on the plan's stream in list order.
+static int run_launch(ssb200_plan *p, const Launch &L, const DevJobs &dj, bool two_streams)
+{
+    const bool high = two_streams && L.stream == 1;
+    cudaStream_t st = high ? p->panel_stream : p->stream;
+    const int pr = p->panel_prio;
+    if (two_streams && L.wait_ev >= 0) CU_TRY(cudaStreamWaitEvent(st, p->la_events[L.wait_ev], 0));
+    cudaError_t ce = cudaSuccess;
     switch (L.kind) {
     case L_GEMM_BIG: {
         static int kb32 = -1;
         if (kb32 < 0) { const char *v = getenv("SSB200_KB32"); kb32 = (v && atoi(v)) ? 1 : 0; }
         if (kb32)
-            gemm_nt_sub_kernel<128, 32><<<L.ntiles, gemm_threads<128>(), gemm_smem_bytes<128, 32>(), p->stream>>>(dj.gemm_jobs + L.job0, dj.gemm_tiles + L.tile0, p->d_Lx, p->d_relmap);
+            ce = launch_ex(gemm_nt_sub_kernel<128, 32>, L.ntiles, gemm_threads<128>(), gemm_smem_bytes<128, 32>(), st, high, pr, (const GemmJob *) (dj.gemm_jobs + L.job0), (const int *) (dj.gemm_tiles + L.tile0), p->d_Lx, (const int *) p->d_relmap);
         else
-            gemm_nt_sub_kernel<128, 16><<<L.ntiles, gemm_threads<128>(), gemm_smem_bytes<128, 16>(), p->stream>>>(dj.gemm_jobs + L.job0, dj.gemm_tiles + L.tile0, p->d_Lx, p->d_relmap);
+            ce = launch_ex(gemm_nt_sub_kernel<128, 16>, L.ntiles, gemm_threads<128>(), gemm_smem_bytes<128, 16>(), st, high, pr, (const GemmJob *) (dj.gemm_jobs + L.job0), (const int *) (dj.gemm_tiles + L.tile0), p->d_Lx, (const int *) p->d_relmap);
         break;
     }
     case L_GEMM_SMALL:
-        gemm_nt_sub_kernel<64, 16><<<L.ntiles, gemm_threads<64>(), gemm_smem_bytes<64, 16>(), p->stream>>>(dj.gemm_jobs + L.job0, dj.gemm_tiles + L.tile0, p->d_Lx, p->d_relmap);
+        ce = launch_ex(gemm_nt_sub_kernel<64, 16>, L.ntiles, gemm_threads<64>(), gemm_smem_bytes<64, 16>(), st, high, pr, (const GemmJob *) (dj.gemm_jobs + L.job0), (const int *) (dj.gemm_tiles + L.tile0), p->d_Lx, (const int *) p->d_relmap);
         break;
     case L_POTRF:
     {
-        // version 2 (16-column sub-panels, warp-shuffle diagonal) measured SLOWER on B200 (59 vs 46 ms at lap7 128^3): the
-        // shuffle chains are longer than version 1's one barrier per column.  Kept for experiments: SSB200_POTRF_V2=1.
-        static int v1 = -1;
-        if (v1 < 0) { const char *v = getenv("SSB200_POTRF_V2"); v1 = (v && atoi(v)) ? 0 : 1; }
-        if (v1) potrf_block_kernel<<<L.njobs, POTRF_THREADS, 0, p->stream>>>(dj.potrf_jobs + L.job0, p->d_Lx, p->d_info, p->d_winv);
-        else potrf_block_kernel2<<<L.njobs, POTRF_THREADS, potrf2_smem_bytes(), p->stream>>>(dj.potrf_jobs + L.job0, p->d_Lx, p->d_info, p->d_winv);
+        // version 3 (four columns per barrier) is the default; SSB200_POTRF=1 selects version 1 (one barrier per column),
+        // =2 version 2 (16-column sub-panels with a warp-shuffle diagonal block; measured slower than version 1 on B200)
+        static int ver = -1;
+        if (ver < 0) { const char *v = getenv("SSB200_POTRF"); ver = v ? atoi(v) : 3; if (ver < 1 || ver > 3) ver = 3; }
+        if (ver == 3) ce = launch_ex(potrf_block_kernel3, L.njobs, POTRF_THREADS, 0, st, high, pr, (const PanelJob *) (dj.potrf_jobs + L.job0), p->d_Lx, p->d_info, p->d_winv);
+        else if (ver == 1) ce = launch_ex(potrf_block_kernel, L.njobs, POTRF_THREADS, 0, st, high, pr, (const PanelJob *) (dj.potrf_jobs + L.job0), p->d_Lx, p->d_info, p->d_winv);
+        else ce = launch_ex(potrf_block_kernel2, L.njobs, POTRF_THREADS, potrf2_smem_bytes(), st, high, pr, (const PanelJob *) (dj.potrf_jobs + L.job0), p->d_Lx, p->d_info, p->d_winv);
     }
         break;
     case L_TRSM:
-        trsm_rows_kernel<<<L.ntiles, TRSM_ROWS, 0, p->stream>>>(dj.trsm_jobs + L.job0, dj.trsm_tiles + L.tile0, p->d_Lx);
+        ce = launch_ex(trsm_rows_kernel, L.ntiles, TRSM_ROWS, 0, st, high, pr, (const PanelJob *) (dj.trsm_jobs + L.job0), (const int *) (dj.trsm_tiles + L.tile0), p->d_Lx);
         break;
     case L_TRSM_TC:
-        trsm_tc_kernel<<<L.ntiles, TRSM_ROWS, trsm_tc_smem_bytes(), p->stream>>>(dj.trsm_jobs + L.job0, dj.trsm_tiles + L.tile0, p->d_Lx, p->d_winv);
+        ce = launch_ex(trsm_tc_kernel, L.ntiles, TRSM_ROWS, trsm_tc_smem_bytes(), st, high, pr, (const PanelJob *) (dj.trsm_jobs + L.job0), (const int *) (dj.trsm_tiles + L.tile0), p->d_Lx, (const double *) p->d_winv);
         break;
+    case L_SYNC:
+        break;                                  // only the wait above
     default: set_error("bad launch kind"); return SSB_CHOLMOD_GPU_PROBLEM;
     }
-    p->stats.kernel_launches++;
+    if (ce != cudaSuccess) { set_error(std::string("kernel launch: ") + cudaGetErrorString(ce)); return SSB_CHOLMOD_GPU_PROBLEM; }
+    if (L.kind != L_SYNC) p->stats.kernel_launches++;
+    if (high && p->capturing && L.kind != L_SYNC) {
+        // remember the node: stream priorities do not carry over into a captured graph by themselves on every driver
+        cudaStreamCaptureStatus cs; const cudaGraphNode_t *deps = nullptr; size_t nd = 0;
+        if (cudaStreamGetCaptureInfo(st, &cs, nullptr, nullptr, &deps, &nd) == cudaSuccess && cs == cudaStreamCaptureStatusActive && nd == 1)
+            p->cap_high_nodes.push_back(deps[0]);
+    }
+    if (two_streams && L.rec_ev >= 0) CU_TRY(cudaEventRecord(p->la_events[L.rec_ev], st));
     return 0;
 }
 
@@ -553,12 +601,13 @@ static bool host_is_pinned(const void *ptr)
 // capture == true: the calls are being recorded into a CUDA graph (copies are issued here, the copy stream joins the
 // capture through the gate events and is joined back at the end); otherwise the helper thread issues the copies.
 static int enqueue_factorization(ssb200_plan *p, double beta0, double *Lx_host, bool streaming, bool capture, int stop_level,
-                                 std::vector<std::pair<int, size_t>> &marks, size_t &ev)
+                                 bool two_streams, std::vector<std::pair<int, size_t>> &marks, size_t &ev)
 {
     HostPlan &hp = p->hp;
-    const bool timing = !capture;      // events recorded by graph nodes cannot be used with cudaEventElapsedTime
+    // per-launch events only make sense on one stream; events recorded by graph nodes cannot be used with cudaEventElapsedTime
+    const bool timing = !capture && !two_streams;
     marks.clear(); ev = 0;
-    if (timing) cudaEventRecord(get_event(p, ev), p->stream);                     // 0: start
+    if (!capture) cudaEventRecord(get_event(p, ev), p->stream);                   // 0: start
     ev++;
     // zero all supernodes (:305-317); in pieces, a captured memset node does not take 2^32 bytes or more
     for (size_t off = 0, tot = (size_t) hp.xsize * sizeof(double); off < tot; off += (size_t) 1 << 30)
@@ -569,7 +618,7 @@ static int enqueue_factorization(ssb200_plan *p, double beta0, double *Lx_host, 
         p->stats.kernel_launches++;
     }
     if (scatter_A(p, beta0, 0, hp.n)) return SSB_CHOLMOD_GPU_PROBLEM;
-    if (timing) cudaEventRecord(get_event(p, ev), p->stream);                     // 1: assembled
+    if (!capture) cudaEventRecord(get_event(p, ev), p->stream);                   // 1: assembled
     ev++;
     size_t ctask = 0, cgroup = 0;
     bool copies_captured = false;
@@ -578,11 +627,11 @@ static int enqueue_factorization(ssb200_plan *p, double beta0, double *Lx_host, 
             const Launch &L = hp.launches[t];
             if (timing) cudaEventRecord(get_event(p, ev), p->stream);
             marks.push_back({t, ev}); ev++;
-            if (run_launch(p, L, p->jobs)) return SSB_CHOLMOD_GPU_PROBLEM;
+            if (run_launch(p, L, p->jobs, two_streams)) return SSB_CHOLMOD_GPU_PROBLEM;
             if (streaming && ctask < hp.copy_tasks.size() && hp.copy_tasks[ctask].after_launch == t) {
-                // these ranges of Lx are final: copy them out behind this point of the compute stream
+                // these ranges of Lx are final: copy them out behind this point of the stream that finished them
                 cudaEvent_t gate = p->copy_gates[cgroup++];
-                CU_TRY(cudaEventRecord(gate, p->stream));
+                CU_TRY(cudaEventRecord(gate, (two_streams && L.stream == 1) ? p->panel_stream : p->stream));
                 if (capture) { CU_TRY(cudaStreamWaitEvent(p->copy_stream, gate, 0)); copies_captured = true; }
                 for (bool first = true; ctask < hp.copy_tasks.size() && hp.copy_tasks[ctask].after_launch == t; ctask++, first = false) {
                     const CopyTask &ct = hp.copy_tasks[ctask];
@@ -594,14 +643,19 @@ static int enqueue_factorization(ssb200_plan *p, double beta0, double *Lx_host, 
             }
         }
     }
-    if (timing) cudaEventRecord(get_event(p, ev), p->stream);
+    if (two_streams && stop_level < hp.nlevels) {
+        // debugging stop in the middle of the schedule: join the panel stream by hand
+        cudaEvent_t e = get_event(p, hp.launches.size() + 7);
+        CU_TRY(cudaEventRecord(e, p->panel_stream)); CU_TRY(cudaStreamWaitEvent(p->stream, e, 0));
+    }
+    if (!capture) cudaEventRecord(get_event(p, ev), p->stream);
     marks.push_back({-1, ev}); ev++;                                               // end of the compute chain
     CU_TRY(cudaMemcpyAsync(p->h_info, p->d_info, hp.nsuper * sizeof(int), cudaMemcpyDeviceToHost, p->stream));
     if (capture && copies_captured) {                                              // join the copy stream back into the capture
         CU_TRY(cudaEventRecord(p->copy_gate, p->copy_stream));
         CU_TRY(cudaStreamWaitEvent(p->stream, p->copy_gate, 0));
     }
-    if (timing) cudaEventRecord(get_event(p, ev), p->stream);
+    if (!capture) cudaEventRecord(get_event(p, ev), p->stream);
     ev++;                                                                          // everything, copies included
     CU_TRY(cudaGetLastError());
     return 0;
@@ -629,6 +683,8 @@ static int factorize_impl(ssb200_plan *p, const double beta[2], int quick_return
     // link that the streaming saturates (+24 us per launch otherwise).  Resident factorizations keep the per-launch events
     // (per-kernel statistics) unless SSB200_FACTOR_GRAPH=1.
     const bool graph = stop_level == INT_MAX && (use_graph == 1 || (use_graph == -1 && streaming));
+    const bool two_streams = p->lookahead && hp.n_events > 0 && hp.nranks == 1;
+    while ((int) p->la_events.size() < hp.n_events) { cudaEvent_t e; CU_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); p->la_events.push_back(e); }
     // everything the enqueue needs exists before a capture starts
     while (p->events.size() < hp.launches.size() + 8) { cudaEvent_t e; CU_TRY(cudaEventCreate(&e)); p->events.push_back(e); }
     {
@@ -644,15 +700,30 @@ static int factorize_impl(ssb200_plan *p, const double beta[2], int quick_return
         // The whole factorization is one CUDA graph (thousands of small dependent launches; replaying it also keeps the
         // launch chain off the PCIe link that the host streaming saturates).  Rebuilt when a baked-in parameter changes.
         FactorGraphKey key; memset(&key, 0, sizeof(key));
-        key.beta0 = beta0; key.host = streaming ? Lx_host : nullptr; key.stype = p->stype;
+        key.beta0 = beta0; key.host = streaming ? Lx_host : nullptr; key.stype = p->stype; key.two_streams = two_streams ? 1 : 0;
         key.a[0] = p->bufA->p; key.a[1] = p->bufA->i; key.a[2] = p->bufA->x; key.a[3] = p->bufA->haveNz ? p->bufA->nz : nullptr;
         key.f[0] = p->bufF->p; key.f[1] = p->bufF->i; key.f[2] = p->bufF->x; key.f[3] = p->bufF->haveNz ? p->bufF->nz : nullptr;
         if (!p->fgraph || memcmp(&key, &p->fg_key, sizeof(key)) != 0) {
             if (p->fgraph) { cudaGraphExecDestroy(p->fgraph); p->fgraph = nullptr; }
             CU_TRY(cudaStreamBeginCapture(p->stream, cudaStreamCaptureModeThreadLocal));
-            const int rc = enqueue_factorization(p, beta0, Lx_host, streaming, true, stop_level, marks, ev);
+            p->capturing = true; p->cap_high_nodes.clear();
+            const int rc = enqueue_factorization(p, beta0, Lx_host, streaming, true, stop_level, two_streams, marks, ev);
+            p->capturing = false;
             cudaGraph_t g = nullptr;
             cudaError_t ce = cudaStreamEndCapture(p->stream, &g);
+            if (!rc && ce == cudaSuccess) {
+                int nset = 0, nalready = 0;
+                for (cudaGraphNode_t nd : p->cap_high_nodes) {
+                    cudaLaunchAttributeValue v; memset(&v, 0, sizeof(v));
+                    if (cudaGraphKernelNodeGetAttribute(nd, cudaLaunchAttributePriority, &v) == cudaSuccess && v.priority == p->panel_prio) nalready++;
+                    memset(&v, 0, sizeof(v)); v.priority = p->panel_prio;
+                    if (cudaGraphKernelNodeSetAttribute(nd, cudaLaunchAttributePriority, &v) == cudaSuccess) nset++;
+                }
+                (void) cudaGetLastError();
+                if (getenv("SSB200_VERBOSE") && atoi(getenv("SSB200_VERBOSE")))
+                    fprintf(stderr, "[suitesparse_b200] factorization graph: %zu panel-stream kernel nodes, priority %d set on %d (captured with it: %d)\n",
+                            p->cap_high_nodes.size(), p->panel_prio, nset, nalready);
+            }
             if (rc || ce != cudaSuccess) { if (g) cudaGraphDestroy(g); (void) cudaGetLastError(); if (!rc) set_error(std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce)); return SSB_CHOLMOD_GPU_PROBLEM; }
             ce = cudaGraphInstantiate(&p->fgraph, g, 0);
             cudaGraphDestroy(g);
@@ -664,7 +735,7 @@ static int factorize_impl(ssb200_plan *p, const double beta[2], int quick_return
         CU_TRY(cudaGraphLaunch(p->fgraph, p->stream));
         CU_TRY(cudaEventRecord(p->events[1], p->stream));
     } else {
-        if (enqueue_factorization(p, beta0, Lx_host, streaming, false, stop_level, marks, ev)) return SSB_CHOLMOD_GPU_PROBLEM;
+        if (enqueue_factorization(p, beta0, Lx_host, streaming, false, stop_level, two_streams, marks, ev)) return SSB_CHOLMOD_GPU_PROBLEM;
     }
     CU_TRY(cudaStreamSynchronize(p->stream));
     // timings: events[0] start, [1] assembled, one per launch, end of compute (marks.back()), [ev-1] end of everything
@@ -676,7 +747,12 @@ static int factorize_impl(ssb200_plan *p, const double beta[2], int quick_return
     if (graph) {
         // one replayed graph: only the total is known (copies to the host included)
         cudaEventElapsedTime(&ms, p->events[0], p->events[1]); p->stats.ms_total = ms;
-        for (const Launch &L : hp.launches) { p->stats.flops_kind[L.kind] += L.flops; p->stats.launches_kind[L.kind]++; }
+        for (const Launch &L : hp.launches) if (L.kind != L_SYNC) { p->stats.flops_kind[L.kind] += L.flops; p->stats.launches_kind[L.kind]++; }
+    } else if (two_streams) {
+        // two concurrent streams: only the assembly and the total are meaningful
+        cudaEventElapsedTime(&ms, p->events[0], p->events[1]); p->stats.ms_assemble = ms;
+        cudaEventElapsedTime(&ms, p->events[0], p->events[ev_compute_end]); p->stats.ms_total = ms;
+        for (const Launch &L : hp.launches) if (L.kind != L_SYNC) { p->stats.flops_kind[L.kind] += L.flops; p->stats.launches_kind[L.kind]++; }
     } else {
         cudaEventElapsedTime(&ms, p->events[0], p->events[1]); p->stats.ms_assemble = ms;
         for (size_t t = 0; t + 1 < marks.size(); t++) {
@@ -862,6 +938,15 @@ extern "C" int ssb200_factor_diag(ssb200_plan *p, double *diag_host)
     return 0;
 }
 
+// on (default): two-stream look-ahead schedule, only total device times are reported; off: one stream in list order with
+// timing events around every launch (per-kernel statistics in ssb200_stats.ms_kind)
+extern "C" int ssb200_set_lookahead(ssb200_plan *p, int on)
+{
+    if (!p) return SSB_CHOLMOD_INVALID;
+    p->lookahead = on != 0 && p->hp.nranks == 1;
+    return 0;
+}
+
 extern "C" double *ssb200_device_Lx(ssb200_plan *p) { return p ? p->d_Lx : nullptr; }
 extern "C" ssb_long ssb200_xsize(const ssb200_plan *p) { return p ? p->hp.xsize : 0; }
 extern "C" void *ssb200_stream(ssb200_plan *p) { return p ? (void *) p->stream : nullptr; }
@@ -898,6 +983,449 @@ extern "C" ssb_long ssb200_debug_relmap(ssb200_plan *p, int32_t *out, ssb_long c
 }
 
 // ===============================================================================================================
+// Multi-GPU inside one process: the elimination-tree shard (ssb_plan.cpp) with DISTRIBUTED STORAGE.  One host thread per
+// device walks the rank's step list; a finished range (subtree, whole-owned top supernode, 256-column panel of a cyclic
+// supernode) is PULLED over NVLink by exactly the ranks whose updates read it, with a copy kernel on peer-mapped
+// pointers (mg_pull_kernel) - no NCCL, no host staging.  Cross-device ordering = CUDA events; the host threads only
+// hand-shake on "this event has been recorded" flags.  The reference has no counterpart (GPU/cholmod_gpu.c:160-164:
+// "can only utilize a single GPU").
+// ===============================================================================================================
+struct MgPiece { long long src_off, dst_off, cnt; };
+
+// chunks of <= MG_CHUNK doubles; one CTA per chunk (grid-stride); 16-byte accesses when both sides are aligned
+constexpr int MG_CHUNK = 16384, MG_THREADS = 256;
+__global__ void __launch_bounds__(MG_THREADS) mg_pull_kernel(const MgPiece *__restrict__ chunks, int nchunks,
+                                                            const double *__restrict__ src, double *__restrict__ dst)
+{
+    for (int c = blockIdx.x; c < nchunks; c += gridDim.x) {
+        const MgPiece pc = chunks[c];
+        const double *__restrict__ sp = src + pc.src_off;
+        double *__restrict__ dp = dst + pc.dst_off;
+        if (((pc.src_off | pc.dst_off | pc.cnt) & 1) == 0) {
+            const double2 *__restrict__ s2 = reinterpret_cast<const double2 *>(sp);
+            double2 *__restrict__ d2 = reinterpret_cast<double2 *>(dp);
+            const long long n2 = pc.cnt >> 1;
+            for (long long i = threadIdx.x; i < n2; i += MG_THREADS * 8) {
+                double2 v[8];
+#pragma unroll
+                for (int q = 0; q < 8; q++) { const long long t = i + (long long) q * MG_THREADS; v[q] = t < n2 ? s2[t] : make_double2(0.0, 0.0); }
+#pragma unroll
+                for (int q = 0; q < 8; q++) { const long long t = i + (long long) q * MG_THREADS; if (t < n2) d2[t] = v[q]; }
+            }
+        } else {
+            for (long long i = threadIdx.x; i < pc.cnt; i += MG_THREADS * 8) {
+                double v[8];
+#pragma unroll
+                for (int q = 0; q < 8; q++) { const long long t = i + (long long) q * MG_THREADS; v[q] = t < pc.cnt ? sp[t] : 0.0; }
+#pragma unroll
+                for (int q = 0; q < 8; q++) { const long long t = i + (long long) q * MG_THREADS; if (t < pc.cnt) dp[t] = v[q]; }
+            }
+        }
+    }
+}
+
+struct MgDev {
+    ssb200_plan *plan = nullptr;
+    int device = 0;
+    cudaStream_t comm = nullptr, d2h = nullptr;          // pulls (high priority), copies to the host factor
+    cudaEvent_t ev_begin = nullptr, ev_done = nullptr;
+    std::vector<cudaEvent_t> ev_arrived;                  // per step: this device's pull of the step's range has landed
+    MgPiece *d_chunks = nullptr;                          // all chunks of all steps, device array
+    std::vector<long long> chunk0; std::vector<int> nchunk;   // per step
+    std::vector<cudaEvent_t> ev_solve;                    // per solve step (sync steps): this device's part of the step is done
+    int rc = 0; std::string err; ssb_long bad = 0;
+    double ms = 0;
+};
+
+struct ssb200_mg {
+    int N = 0;
+    long long n = 0, xsize = 0;
+    std::vector<MgDev> d;
+    std::vector<cudaEvent_t> ev_ready;                    // per step: the step's range is final on its source device
+    std::vector<std::atomic<long long>> ready_epoch;      // host hand-shake: ev_ready[k] has been recorded in this epoch
+    std::vector<std::atomic<long long>> arrived_epoch;    // [r * nsteps + k]
+    std::vector<std::atomic<long long>> solve_epoch;      // [r * nsolve + t]
+    long long epoch = 0;
+    double *d_X = nullptr; size_t capX = 0;               // right-hand sides, on device 0 (peers reach it over NVLink)
+    cudaEvent_t ev_x = nullptr;
+    void *pinned_ptr = nullptr; size_t pinned_bytes = 0;  // host L->x registered for all devices (ssb200_mg_pin_host)
+    bool factor_on_devices = false;
+    double last_ms = 0, last_solve_ms = 0;
+    long long pulled_bytes = 0;                           // NVLink bytes per factorization (sum over ranks)
+};
+
+static void mg_free(ssb200_mg *m)
+{
+    if (!m) return;
+    for (auto &dv : m->d) {
+        if (!dv.plan) continue;
+        cudaSetDevice(dv.device);
+        for (auto e : dv.ev_arrived) if (e) cudaEventDestroy(e);
+        for (auto e : dv.ev_solve) if (e) cudaEventDestroy(e);
+        if (dv.ev_begin) cudaEventDestroy(dv.ev_begin);
+        if (dv.ev_done) cudaEventDestroy(dv.ev_done);
+        if (dv.d_chunks) cudaFree(dv.d_chunks);
+        if (dv.comm) cudaStreamDestroy(dv.comm);
+        if (dv.d2h) cudaStreamDestroy(dv.d2h);
+    }
+    for (size_t k = 0; k < m->ev_ready.size(); k++) if (m->ev_ready[k]) { cudaEventDestroy(m->ev_ready[k]); }
+    if (m->d_X) { cudaSetDevice(m->d[0].device); cudaFree(m->d_X); }
+    if (m->ev_x) cudaEventDestroy(m->ev_x);
+    if (m->pinned_ptr) { if (cudaHostUnregister(m->pinned_ptr) != cudaSuccess) (void) cudaGetLastError(); }
+    for (auto &dv : m->d) plan_free(dv.plan);
+    delete m;
+}
+
+extern "C" void ssb200_mg_destroy(ssb200_mg *m) { mg_free(m); }
+
+extern "C" ssb200_mg *ssb200_mg_create(ssb_long n, ssb_long nsuper, const ssb_long *super, const ssb_long *pi, const ssb_long *px,
+                                       const ssb_long *s, int ndev, const int *devices)
+{
+    int have = 0;
+    if (cudaGetDeviceCount(&have) != cudaSuccess || have == 0) { set_error("no CUDA device: the hot path has no CPU fallback"); return nullptr; }
+    if (ndev < 2 || ndev > have) { set_error("ssb200_mg_create: need 2 <= ndev <= number of devices"); return nullptr; }
+    std::vector<int> devs(ndev);
+    for (int r = 0; r < ndev; r++) { devs[r] = devices ? devices[r] : r; if (devs[r] < 0 || devs[r] >= have) { set_error("device ordinal out of range"); return nullptr; } }
+    // every device maps every other device's memory (NVLink / NVSwitch peer access)
+    for (int a = 0; a < ndev; a++) {
+        cudaSetDevice(devs[a]);
+        for (int b = 0; b < ndev; b++) {
+            if (a == b) continue;
+            int can = 0; cudaDeviceCanAccessPeer(&can, devs[a], devs[b]);
+            if (!can) { set_error("devices cannot access each other's memory (no NVLink/PCIe peer access)"); return nullptr; }
+            cudaError_t e = cudaDeviceEnablePeerAccess(devs[b], 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { set_error(std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e)); return nullptr; }
+            (void) cudaGetLastError();
+        }
+    }
+    ssb200_mg *m = new ssb200_mg();
+    m->N = ndev; m->n = n; m->xsize = nsuper > 0 ? px[nsuper] : 0;
+    m->d.resize(ndev);
+    {   // one plan per device, built in parallel (the host plan builder is single-threaded per rank)
+        std::vector<std::thread> th;
+        std::vector<std::string> errs(ndev);
+        for (int r = 0; r < ndev; r++)
+            th.emplace_back([&, r] {
+                m->d[r].device = devs[r];
+                m->d[r].plan = plan_create_impl(n, nsuper, super, pi, px, s, devs[r], ndev, r, /*compact=*/true);
+                if (!m->d[r].plan) errs[r] = g_last_error;
+            });
+        for (auto &t : th) t.join();
+        for (int r = 0; r < ndev; r++) if (!m->d[r].plan) { set_error("rank " + std::to_string(r) + ": " + errs[r]); mg_free(m); return nullptr; }
+    }
+    const size_t ns = m->d[0].plan->hp.steps.size();
+    for (int r = 1; r < ndev; r++) {
+        const auto &a = m->d[0].plan->hp.steps, &b = m->d[r].plan->hp.steps;
+        bool same = a.size() == b.size();
+        for (size_t k = 0; same && k < ns; k++) same = a[k].bcast_src == b[k].bcast_src && a[k].off == b[k].off && a[k].cnt == b[k].cnt && a[k].wait_remote == b[k].wait_remote;
+        if (!same) { set_error("internal: the ranks disagree on the step list"); mg_free(m); return nullptr; }
+    }
+    m->ev_ready.assign(ns, nullptr);
+    m->ready_epoch = std::vector<std::atomic<long long>>(ns);
+    m->arrived_epoch = std::vector<std::atomic<long long>>(ns * ndev);
+    for (auto &a : m->ready_epoch) a.store(0);
+    for (auto &a : m->arrived_epoch) a.store(0);
+    const size_t nsolve = m->d[0].plan->hp.solve_steps.size();
+    m->solve_epoch = std::vector<std::atomic<long long>>(nsolve * ndev);
+    for (auto &a : m->solve_epoch) a.store(0);
+    for (size_t k = 0; k < ns; k++) {
+        const DistStep &st = m->d[0].plan->hp.steps[k];
+        if (st.bcast_src < 0) continue;
+        cudaSetDevice(devs[st.bcast_src]);
+        if (cudaEventCreateWithFlags(&m->ev_ready[k], cudaEventDisableTiming) != cudaSuccess) { set_error("cudaEventCreate failed"); mg_free(m); return nullptr; }
+    }
+    for (int r = 0; r < ndev; r++) {
+        MgDev &dv = m->d[r];
+        HostPlan &hp = dv.plan->hp;
+        cudaSetDevice(dv.device);
+        int lo = 0, hi = 0; cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        if (cudaStreamCreateWithPriority(&dv.comm, cudaStreamNonBlocking, hi) != cudaSuccess || cudaStreamCreateWithFlags(&dv.d2h, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&dv.ev_begin, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&dv.ev_done, cudaEventDisableTiming) != cudaSuccess) {
+            set_error("stream/event creation failed"); mg_free(m); return nullptr; }
+        dv.ev_arrived.assign(ns, nullptr); dv.chunk0.assign(ns, 0); dv.nchunk.assign(ns, 0);
+        dv.ev_solve.assign(nsolve, nullptr);
+        for (size_t t = 0; t < nsolve; t++) if (hp.solve_steps[t].njobs > 0) cudaEventCreateWithFlags(&dv.ev_solve[t], cudaEventDisableTiming);
+        std::vector<MgPiece> chunks;
+        for (size_t k = 0; k < ns; k++) {
+            if (hp.step_recv[k].empty()) continue;
+            const int src = hp.steps[k].bcast_src;
+            const HostPlan &sp = m->d[src].plan->hp;
+            cudaEventCreateWithFlags(&dv.ev_arrived[k], cudaEventDisableTiming);
+            dv.chunk0[k] = (long long) chunks.size();
+            for (const HostPlan::Piece &pc : hp.step_recv[k]) {
+                // the piece starts inside supernode t; both ranks store the run [t ..] contiguously with the same inner offsets
+                const int t = (int) (std::upper_bound(hp.px.begin(), hp.px.end(), pc.home_off) - hp.px.begin()) - 1;
+                if (sp.lpx[t] < 0 || hp.lpx[t] < 0) { set_error("internal: transfer of a supernode that one side does not store"); mg_free(m); return nullptr; }
+                const long long so = sp.lpx[t] + (pc.home_off - hp.px[t]), dn = hp.lpx[t] + (pc.home_off - hp.px[t]);
+                for (long long o = 0; o < pc.cnt; o += MG_CHUNK) chunks.push_back(MgPiece{so + o, dn + o, std::min<long long>(MG_CHUNK, pc.cnt - o)});
+                m->pulled_bytes += pc.cnt * 8;
+            }
+            dv.nchunk[k] = (int) (chunks.size() - dv.chunk0[k]);
+        }
+        if (!chunks.empty()) {
+            if (cudaMalloc((void **) &dv.d_chunks, chunks.size() * sizeof(MgPiece)) != cudaSuccess ||
+                cudaMemcpy(dv.d_chunks, chunks.data(), chunks.size() * sizeof(MgPiece), cudaMemcpyHostToDevice) != cudaSuccess) { set_error("chunk list upload failed"); mg_free(m); return nullptr; }
+        }
+    }
+    cudaSetDevice(devs[0]);
+    cudaEventCreateWithFlags(&m->ev_x, cudaEventDisableTiming);
+    return m;
+}
+
+// Page-lock the host factor for ALL devices (every device copies its own share out over its own PCIe link).
+extern "C" int ssb200_mg_pin_host(ssb200_mg *m, double *Lx_host)
+{
+    if (!m) return SSB_CHOLMOD_INVALID;
+    const size_t bytes = (size_t) m->xsize * sizeof(double);
+    if (m->pinned_ptr == Lx_host && m->pinned_bytes == bytes) return 0;
+    if (m->pinned_ptr) { if (cudaHostUnregister(m->pinned_ptr) != cudaSuccess) (void) cudaGetLastError(); m->pinned_ptr = nullptr; }
+    if (!Lx_host || bytes == 0) return 0;
+    if (cudaHostRegister(Lx_host, bytes, cudaHostRegisterPortable) != cudaSuccess) { (void) cudaGetLastError(); return 1; }   // best effort
+    m->pinned_ptr = Lx_host; m->pinned_bytes = bytes;
+    return 0;
+}
+
+static void mg_spin_until(const std::atomic<long long> &a, long long epoch, const std::atomic<int> &abort_flag)
+{
+    while (a.load(std::memory_order_acquire) != epoch) { if (abort_flag.load(std::memory_order_relaxed)) return; std::this_thread::yield(); }
+}
+
+// One factorization over all devices.  Host arrays as in ssb200_factorize.  Lx_host (may be NULL) receives the factor: every
+// device copies the ranges it finished.  Returns 0 ok, 1 not positive definite (*minor_out = failing column; the factor on
+// the devices is then NOT usable - see ssb200_mg_factorize's comment in the header), < 0 error.
+extern "C" int ssb200_mg_factorize(ssb200_mg *m, int stype, const ssb_long *Ap, const ssb_long *Ai, const ssb_long *Anz, const double *Ax,
+                                   ssb_long ncolA, const ssb_long *Fp, const ssb_long *Fi, const ssb_long *Fnz, const double *Fx,
+                                   const double beta[2], double *Lx_host, ssb_long *minor_out)
+{
+    if (!m) { set_error("null plan"); return SSB_CHOLMOD_INVALID; }
+    const int N = m->N;
+    const size_t ns = m->d[0].plan->hp.steps.size();
+    const long long epoch = ++m->epoch;
+    const double beta0 = beta ? beta[0] : 0.0;
+    const bool host_pinned = Lx_host && host_is_pinned(Lx_host);
+    std::atomic<int> abort_flag{0};
+    m->factor_on_devices = false;
+    if (minor_out) *minor_out = m->n;
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto worker = [&](int r) {
+        MgDev &dv = m->d[r];
+        ssb200_plan *p = dv.plan;
+        HostPlan &hp = p->hp;
+        dv.rc = 0; dv.err.clear(); dv.bad = hp.n;
+        auto fail = [&](const std::string &msg) { dv.rc = SSB_CHOLMOD_GPU_PROBLEM; dv.err = msg; abort_flag.store(1); };
+#define MG_TRY(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { fail(std::string(#expr) + ": " + cudaGetErrorString(_e)); return; } } while (0)
+        MG_TRY(cudaSetDevice(dv.device));
+        if (ssb200_upload_A(p, stype, Ap, Ai, Anz, Ax, ncolA, Fp, Fi, Fnz, Fx)) { fail(g_last_error); return; }
+        p->stats.kernel_launches = 0; p->factor_on_device = false;
+        if (hp.nsuper == 0) return;
+        // zero the local storage, assemble the columns this rank computes
+        for (size_t off = 0, tot = (size_t) p->lx_alloc * sizeof(double); off < tot; off += (size_t) 1 << 30)
+            MG_TRY(cudaMemsetAsync((char *) p->d_Lx + off, 0, std::min<size_t>((size_t) 1 << 30, tot - off), p->stream));
+        fill_int_kernel<<<(unsigned) ((hp.nsuper + 255) / 256), 256, 0, p->stream>>>(p->d_info, hp.nsuper, INT_MAX);
+        p->stats.kernel_launches++;
+        p->last_beta0 = beta0;
+        if (scatter_A(p, beta0, 0, hp.n, false)) { fail(g_last_error); return; }
+        MG_TRY(cudaEventRecord(dv.ev_begin, p->stream));
+        MG_TRY(cudaStreamWaitEvent(dv.comm, dv.ev_begin, 0));
+        std::vector<cudaEvent_t> outstanding;
+        for (size_t k = 0; k < ns; k++) {
+            if (abort_flag.load()) return;
+            const DistStep &st = hp.steps[k];
+            if (st.wait_remote && !outstanding.empty()) {
+                for (cudaEvent_t e : outstanding) MG_TRY(cudaStreamWaitEvent(p->stream, e, 0));
+                outstanding.clear();
+            }
+            for (int t = st.launch_begin; t < st.launch_mid; t++) if (run_launch(p, hp.launches[t], p->jobs)) { fail(g_last_error); return; }
+            if (st.bcast_src == r) {
+                MG_TRY(cudaEventRecord(m->ev_ready[k], p->stream));
+                m->ready_epoch[k].store(epoch, std::memory_order_release);
+                if (Lx_host && host_pinned && st.cnt > 0) {
+                    // final here: this device's share of the factor goes to the host while the factorization continues
+                    const int t0 = (int) (std::upper_bound(hp.px.begin(), hp.px.end(), st.off) - hp.px.begin()) - 1;
+                    MG_TRY(cudaStreamWaitEvent(dv.d2h, m->ev_ready[k], 0));
+                    MG_TRY(cudaMemcpyAsync(Lx_host + st.off, p->d_Lx + hp.lpx[t0] + (st.off - hp.px[t0]), (size_t) st.cnt * sizeof(double), cudaMemcpyDeviceToHost, dv.d2h));
+                }
+            } else if (st.bcast_src >= 0 && dv.nchunk[k] > 0) {
+                mg_spin_until(m->ready_epoch[k], epoch, abort_flag);
+                if (abort_flag.load()) return;
+                MG_TRY(cudaStreamWaitEvent(dv.comm, m->ev_ready[k], 0));
+                const int nxt = hp.step_next[k];
+                if (nxt >= 0 && nxt != r) {
+                    // the owner of the next panel pulls first: it is the one on the critical path
+                    mg_spin_until(m->arrived_epoch[(size_t) nxt * ns + k], epoch, abort_flag);
+                    if (abort_flag.load()) return;
+                    MG_TRY(cudaStreamWaitEvent(dv.comm, m->d[nxt].ev_arrived[k], 0));
+                }
+                const int grid = std::min(dv.nchunk[k], 148 * 4);
+                mg_pull_kernel<<<grid, MG_THREADS, 0, dv.comm>>>(dv.d_chunks + dv.chunk0[k], dv.nchunk[k], m->d[st.bcast_src].plan->d_Lx, p->d_Lx);
+                p->stats.kernel_launches++;
+                MG_TRY(cudaEventRecord(dv.ev_arrived[k], dv.comm));
+                m->arrived_epoch[(size_t) r * ns + k].store(epoch, std::memory_order_release);
+                outstanding.push_back(dv.ev_arrived[k]);
+            }
+            for (int t = st.launch_mid; t < st.launch_end; t++) if (run_launch(p, hp.launches[t], p->jobs)) { fail(g_last_error); return; }
+        }
+        for (cudaEvent_t e : outstanding) MG_TRY(cudaStreamWaitEvent(p->stream, e, 0));
+        MG_TRY(cudaMemcpyAsync(p->h_info, p->d_info, hp.nsuper * sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+        MG_TRY(cudaStreamSynchronize(p->stream));
+        MG_TRY(cudaStreamSynchronize(dv.comm));
+        MG_TRY(cudaStreamSynchronize(dv.d2h));
+        MG_TRY(cudaGetLastError());
+        for (long long sn = 0; sn < hp.nsuper; sn++) if (p->h_info[sn] != INT_MAX) { dv.bad = hp.super[sn] + p->h_info[sn] - 1; break; }
+        p->stats.kernel_launches_total += p->stats.kernel_launches;
+        p->factor_on_device = true; p->winv_valid = true;      // the inverses of the blocks THIS rank factorized (what its solve jobs use)
+#undef MG_TRY
+    };
+    {
+        std::vector<std::thread> th;
+        for (int r = 0; r < N; r++) th.emplace_back(worker, r);
+        for (auto &t : th) t.join();
+    }
+    m->last_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+    ssb_long minor = m->n;
+    for (int r = 0; r < N; r++) {
+        if (m->d[r].rc) { set_error("rank " + std::to_string(r) + ": " + m->d[r].err); return m->d[r].rc; }
+        minor = std::min(minor, m->d[r].bad);
+    }
+    if (minor < m->n) { if (minor_out) *minor_out = minor; return SSB_CHOLMOD_NOT_POSDEF; }
+    if (Lx_host && !host_pinned) {
+        // pageable host memory: plain copies of every device's share at the end
+        for (int r = 0; r < N; r++) {
+            MgDev &dv = m->d[r]; HostPlan &hp = dv.plan->hp;
+            cudaSetDevice(dv.device);
+            for (size_t k = 0; k < ns; k++) {
+                const DistStep &st = hp.steps[k];
+                if (st.bcast_src != r || st.cnt <= 0) continue;
+                const int t0 = (int) (std::upper_bound(hp.px.begin(), hp.px.end(), st.off) - hp.px.begin()) - 1;
+                CU_TRY(cudaMemcpy(Lx_host + st.off, dv.plan->d_Lx + hp.lpx[t0] + (st.off - hp.px[t0]), (size_t) st.cnt * sizeof(double), cudaMemcpyDeviceToHost));
+            }
+        }
+    }
+    m->factor_on_devices = true;
+    return 0;
+}
+
+// Triangular solves on the distributed factor: every device solves with the blocks it factorized (same kernels as the
+// single-GPU path), the right-hand sides live on device 0 and are read / atomically updated by the peers over NVLink
+// (n doubles per right-hand side against 16*xsize bytes of local factor reads).  Steps below the subtree cut need no
+// cross-device ordering; above it, before a step a device waits for the latest step of every other device (streams are
+// in order, so that is a full barrier; a wait is skipped when nothing new happened on that device since the last one).
+extern "C" int ssb200_mg_solve(ssb200_mg *m, int which, double *X, ssb_long nrhs, ssb_long ldx)
+{
+    if (!m || (!X && m->n > 0 && nrhs > 0)) { set_error("null argument"); return SSB_CHOLMOD_INVALID; }
+    if (!m->factor_on_devices) { set_error("no numeric factor on the devices"); return SSB_CHOLMOD_INVALID; }
+    if (which < 0 || which > 2) { set_error("which must be 0 (L), 1 (L') or 2 (both)"); return SSB_CHOLMOD_INVALID; }
+    const long long n = m->n;
+    if (n == 0 || nrhs == 0) return 0;
+    if (ldx < n) { set_error("X and L dimensions must match"); return SSB_CHOLMOD_INVALID; }
+    const int N = m->N;
+    MgDev &d0 = m->d[0];
+    CU_TRY(cudaSetDevice(d0.device));
+    if ((size_t) n * nrhs > m->capX) { if (m->d_X) cudaFree(m->d_X); m->d_X = nullptr; m->capX = (size_t) n * nrhs; CU_TRY(cudaMalloc((void **) &m->d_X, m->capX * sizeof(double))); }
+    CU_TRY(cudaMemcpy2DAsync(m->d_X, n * sizeof(double), X, ldx * sizeof(double), n * sizeof(double), nrhs, cudaMemcpyHostToDevice, d0.plan->stream));
+    CU_TRY(cudaStreamSynchronize(d0.plan->stream));
+    const long long T = (long long) d0.plan->hp.solve_steps.size();
+    std::atomic<int> abort_flag{0};
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto run_pass = [&](int r, int dir, long long ep) {
+        MgDev &dv = m->d[r];
+        ssb200_plan *p = dv.plan;
+        const HostPlan &hp = p->hp;
+        auto fail = [&](const std::string &msg) { dv.rc = SSB_CHOLMOD_GPU_PROBLEM; dv.err = msg; abort_flag.store(1); };
+        if (cudaSetDevice(dv.device) != cudaSuccess) { fail("cudaSetDevice failed"); return; }
+        const double *winv = p->winv_valid ? p->d_winv : nullptr;
+        std::vector<long long> last_waited(N, -1);
+        bool was_sync = false;          // backward pass: the first step below the cut still waits for the top
+        long long launches = 0;
+        for (long long q = 0; q < T; q++) {
+            if (abort_flag.load()) return;
+            const long long t = dir > 0 ? q : T - 1 - q;
+            const SolveStep &st = hp.solve_steps[t];
+            const bool barrier = st.sync || (dir < 0 && was_sync);
+            if (st.sync) was_sync = true;
+            if (st.njobs == 0) continue;
+            if (barrier) {
+                for (int o = 0; o < N; o++) {
+                    if (o == r) continue;
+                    long long tw = t - dir;                                     // the other device's latest non-empty step before t
+                    const auto &os = m->d[o].plan->hp.solve_steps;
+                    while (tw >= 0 && tw < T && os[tw].njobs == 0) tw -= dir;
+                    if (tw < 0 || tw >= T || tw == last_waited[o]) continue;
+                    mg_spin_until(m->solve_epoch[(size_t) o * T + tw], ep, abort_flag);
+                    if (abort_flag.load()) return;
+                    if (cudaStreamWaitEvent(p->stream, m->d[o].ev_solve[tw], 0) != cudaSuccess) { fail("cudaStreamWaitEvent failed"); return; }
+                    last_waited[o] = tw;
+                }
+                if (!st.sync) was_sync = false;                                  // below the cut from here on: no more waits
+            }
+            if (dir > 0) {
+                lsolve_diag_kernel<<<st.njobs, SOLVE_THREADS, 0, p->stream>>>(p->d_solve_jobs + st.job0, p->d_Lx, winv, m->d_X, (int) nrhs, n);
+                if (st.ntiles > 0)
+                    lsolve_update_kernel<<<st.ntiles, SOLVE_THREADS, 0, p->stream>>>(p->d_solve_jobs + st.job0, p->d_solve_tiles + st.tile0, p->d_Lx, p->d_ls, m->d_X, (int) nrhs, n);
+            } else {
+                if (st.ntiles > 0)
+                    ltsolve_update_kernel<<<st.ntiles, SOLVE_THREADS, 0, p->stream>>>(p->d_solve_jobs + st.job0, p->d_solve_tiles + st.tile0, p->d_Lx, p->d_ls, m->d_X, (int) nrhs, n);
+                ltsolve_diag_kernel<<<st.njobs, SOLVE_THREADS, 0, p->stream>>>(p->d_solve_jobs + st.job0, p->d_Lx, winv, m->d_X, (int) nrhs, n);
+            }
+            launches += 1 + (st.ntiles > 0 ? 1 : 0);
+            if (cudaEventRecord(dv.ev_solve[t], p->stream) != cudaSuccess) { fail("cudaEventRecord failed"); return; }
+            m->solve_epoch[(size_t) r * T + t].store(ep, std::memory_order_release);
+        }
+        if (cudaStreamSynchronize(p->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess) { fail("solve kernels failed"); return; }
+        p->stats.kernel_launches = launches;
+    };
+    const int dirs[2] = {which == 1 ? -1 : +1, -1};
+    const int npass = which == 2 ? 2 : 1;
+    for (int ps = 0; ps < npass; ps++) {
+        const long long ep = ++m->epoch;                 // a fresh hand-shake epoch per pass; the join below is the barrier between passes
+        for (int r = 0; r < N; r++) { m->d[r].rc = 0; m->d[r].err.clear(); }
+        std::vector<std::thread> th;
+        for (int r = 0; r < N; r++) th.emplace_back(run_pass, r, dirs[ps], ep);
+        for (auto &t : th) t.join();
+        for (int r = 0; r < N; r++) if (m->d[r].rc) { set_error("rank " + std::to_string(r) + ": " + m->d[r].err); return m->d[r].rc; }
+    }
+    m->last_solve_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+    CU_TRY(cudaSetDevice(d0.device));
+    CU_TRY(cudaMemcpy2DAsync(X, ldx * sizeof(double), m->d_X, n * sizeof(double), n * sizeof(double), nrhs, cudaMemcpyDeviceToHost, d0.plan->stream));
+    CU_TRY(cudaStreamSynchronize(d0.plan->stream));
+    return 0;
+}
+
+// Host factor (CHOLMOD layout) -> every device's local storage: each device takes the supernodes it stores.  The inverses
+// of the diagonal blocks are not rebuilt: the solves then substitute inside the 64-column blocks.
+extern "C" int ssb200_mg_upload_L(ssb200_mg *m, const double *Lx_host)
+{
+    if (!m || !Lx_host) { set_error("null argument"); return SSB_CHOLMOD_INVALID; }
+    for (int r = 0; r < m->N; r++) {
+        MgDev &dv = m->d[r]; const HostPlan &hp = dv.plan->hp;
+        CU_TRY(cudaSetDevice(dv.device));
+        long long run_home = -1, run_loc = -1, run_cnt = 0;
+        for (long long t = 0; t <= hp.nsuper; t++) {
+            const bool present = t < hp.nsuper && hp.lpx[t] >= 0;
+            if (present && run_home >= 0 && hp.px[t] == run_home + run_cnt && hp.lpx[t] == run_loc + run_cnt) { run_cnt += hp.px[t + 1] - hp.px[t]; continue; }
+            if (run_home >= 0) CU_TRY(cudaMemcpyAsync(dv.plan->d_Lx + run_loc, Lx_host + run_home, (size_t) run_cnt * sizeof(double), cudaMemcpyHostToDevice, dv.plan->stream));
+            run_home = -1;
+            if (present) { run_home = hp.px[t]; run_loc = hp.lpx[t]; run_cnt = hp.px[t + 1] - hp.px[t]; }
+        }
+        CU_TRY(cudaStreamSynchronize(dv.plan->stream));
+        dv.plan->factor_on_device = true; dv.plan->winv_valid = false;
+    }
+    m->factor_on_devices = true;
+    return 0;
+}
+
+// out[0] = wall ms of the last factorization (threads started -> all devices idle), out[1] = last solve ms,
+// out[2] = bytes pulled over NVLink per factorization (all ranks), out[3 + r] = HBM bytes held by rank r,
+// out[3 + N + r] = dense flops executed by rank r
+extern "C" int ssb200_mg_info(const ssb200_mg *m, double *out, int cap)
+{
+    if (!m || !out || cap < 3 + 2 * m->N) return SSB_CHOLMOD_INVALID;
+    out[0] = m->last_ms; out[1] = m->last_solve_ms; out[2] = (double) m->pulled_bytes;
+    for (int r = 0; r < m->N; r++) { out[3 + r] = (double) m->d[r].plan->device_bytes; out[3 + m->N + r] = m->d[r].plan->hp.my_flops; }
+    return m->N;
+}
+
+// ===============================================================================================================
 // CHOLMOD drop-in layer
 // ===============================================================================================================
 typedef int (*change_factor_fn)(int, int, int, int, int, ssb_cholmod_factor *, ssb_cholmod_common *);
@@ -918,7 +1446,8 @@ static int raise_error(ssb_cholmod_common *cm, int status, int line, const char 
 // plan cache keyed by the factor object, validated by a fingerprint of its symbolic structure
 struct CacheEntry {
     const ssb_cholmod_factor *L = nullptr;
-    ssb200_plan *plan = nullptr;
+    ssb200_plan *plan = nullptr;           // single-GPU plan, or
+    ssb200_mg *mg = nullptr;               // the multi-GPU plan (SSB200_DEVICES lists two or more devices)
     size_t n = 0, nsuper = 0, ssize = 0, xsize = 0;
     unsigned long long sym_hash = 0;
     std::vector<long long> sample_idx; std::vector<double> sample_val;   // fingerprint of the numeric values last written to L->x
@@ -955,7 +1484,18 @@ static CacheEntry *cache_find(const ssb_cholmod_factor *L)
 
 static void unpin(CacheEntry *e) { if (e->plan && e->plan->fgraph) { cudaGraphExecDestroy(e->plan->fgraph); e->plan->fgraph = nullptr; }   // its copy nodes point into this registration
     if (e->pinned_ptr) { if (cudaHostUnregister(e->pinned_ptr) != cudaSuccess) (void) cudaGetLastError(); e->pinned_ptr = nullptr; e->pinned_bytes = 0; } }
-static void cache_drop(CacheEntry *e) { unpin(e); plan_free(e->plan); g_cache.erase(g_cache.begin() + (e - g_cache.data())); }
+static void cache_drop(CacheEntry *e) { unpin(e); plan_free(e->plan); mg_free(e->mg); g_cache.erase(g_cache.begin() + (e - g_cache.data())); }
+
+// SSB200_DEVICES = "0,1,2,3" | "all": the devices one factorization fans out over (two or more -> ssb200_mg_*)
+static std::vector<int> devices_from_env()
+{
+    std::vector<int> v;
+    const char *e = getenv("SSB200_DEVICES");
+    if (!e || !*e) return v;
+    if (!strcmp(e, "all")) { int n = ssb200_device_count(); for (int i = 0; i < n; i++) v.push_back(i); return v; }
+    for (const char *q = e; *q;) { char *end = nullptr; long d = strtol(q, &end, 10); if (end == q) break; v.push_back((int) d); q = (*end == ',') ? end + 1 : end; if (*end && *end != ',') break; }
+    return v;
+}
 
 // Page-lock the caller's L->x so the factor streams back at PCIe speed.  Best effort: a failure only costs bandwidth.
 // SSB200_PIN_HOST=0 disables it.  The registration is dropped when the plan is evicted, when L->x moves, or by
@@ -966,6 +1506,7 @@ static void cache_drop(CacheEntry *e) { unpin(e); plan_free(e->plan); g_cache.er
 static bool pin_probe(CacheEntry *e, const ssb_cholmod_factor *L)
 {
     ssb200_plan *p = e->plan;
+    if (!p) return true;
     volatile double *x = (volatile double *) L->x;
     const size_t idx[3] = {0, L->xsize / 2, L->xsize - 1};
     static const double magic = 0x1.b200b200b200bp+77;
@@ -989,6 +1530,7 @@ static void pin_host_x(CacheEntry *e, const ssb_cholmod_factor *L)
     static int enabled = -1;
     if (enabled < 0) { const char *v = getenv("SSB200_PIN_HOST"); enabled = (v && atoi(v) == 0) ? 0 : 1; }
     if (!enabled) return;
+    if (e->mg) { ssb200_mg_pin_host(e->mg, (double *) L->x); return; }
     const size_t bytes = L->xsize * sizeof(double);
     if (e->pinned_ptr == L->x && e->pinned_bytes == bytes) {
         if (pin_probe(e, L)) return;
@@ -1013,19 +1555,29 @@ static void pin_host_x(CacheEntry *e, const ssb_cholmod_factor *L)
 }
 
 // returns the (possibly new) entry for L; nullptr on failure
-static CacheEntry *cache_get_plan(ssb_cholmod_factor *L)
+static CacheEntry *cache_get_plan(ssb_cholmod_factor *L, bool single_gpu_only = false)
 {
     const unsigned long long h = hash_symbolic(L);
     CacheEntry *e = cache_find(L);
+    if (e && single_gpu_only && e->mg) { cache_drop(e); e = nullptr; }
     if (e && (e->n != L->n || e->nsuper != L->nsuper || e->ssize != L->ssize || e->xsize != L->xsize || e->sym_hash != h)) { cache_drop(e); e = nullptr; }
     if (e) return e;
     while (g_cache.size() >= cache_capacity()) cache_drop(&g_cache.front());
     int dev = -1;
     if (const char *d = getenv("SSB200_DEVICE")) dev = atoi(d);
-    ssb200_plan *plan = ssb200_plan_create((ssb_long) L->n, (ssb_long) L->nsuper, (const ssb_long *) L->super, (const ssb_long *) L->pi,
-                                           (const ssb_long *) L->px, (const ssb_long *) L->s, dev);
-    if (!plan) return nullptr;
-    CacheEntry ne; ne.L = L; ne.plan = plan; ne.n = L->n; ne.nsuper = L->nsuper; ne.ssize = L->ssize; ne.xsize = L->xsize; ne.sym_hash = h;
+    ssb200_plan *plan = nullptr; ssb200_mg *mg = nullptr;
+    const std::vector<int> devs = devices_from_env();
+    if (devs.size() >= 2 && !single_gpu_only) {
+        mg = ssb200_mg_create((ssb_long) L->n, (ssb_long) L->nsuper, (const ssb_long *) L->super, (const ssb_long *) L->pi,
+                              (const ssb_long *) L->px, (const ssb_long *) L->s, (int) devs.size(), devs.data());
+        if (!mg) return nullptr;
+    } else {
+        if (devs.size() >= 1 && dev < 0) dev = devs[0];
+        plan = ssb200_plan_create((ssb_long) L->n, (ssb_long) L->nsuper, (const ssb_long *) L->super, (const ssb_long *) L->pi,
+                                  (const ssb_long *) L->px, (const ssb_long *) L->s, dev);
+        if (!plan) return nullptr;
+    }
+    CacheEntry ne; ne.L = L; ne.plan = plan; ne.mg = mg; ne.n = L->n; ne.nsuper = L->nsuper; ne.ssize = L->ssize; ne.xsize = L->xsize; ne.sym_hash = h;
     g_cache.push_back(ne);
     return &g_cache.back();
 }
@@ -1041,7 +1593,7 @@ static void take_value_fingerprint(CacheEntry *e, const ssb_cholmod_factor *L)
 }
 static bool value_fingerprint_ok(const CacheEntry *e, const ssb_cholmod_factor *L)
 {
-    if (!e->plan->factor_on_device || e->xptr != L->x) return false;
+    if (!(e->mg ? e->mg->factor_on_devices : e->plan->factor_on_device) || e->xptr != L->x) return false;
     const double *x = (const double *) L->x;
     for (size_t t = 0; t < e->sample_idx.size(); t++)
         if (memcmp(&x[e->sample_idx[t]], &e->sample_val[t], sizeof(double)) != 0) return false;
@@ -1105,7 +1657,11 @@ extern "C" int cholmod_l_super_numeric(ssb_cholmod_sparse *A, ssb_cholmod_sparse
     // On failure L is given back in the form it had on input (cholmod_super_numeric.c:235-248): a factor that was symbolic
     // goes back to CHOLMOD_PATTERN (its freshly allocated L->x holds garbage), the plan and its page-lock are dropped.
     auto fail = [&](int status, const std::string &msg) {
-        if (CacheEntry *ce = cache_find(L)) { if (ce->plan) { ce->plan->factor_on_device = false; ce->plan->winv_valid = false; } if (symbolic) cache_drop(ce); }
+        if (CacheEntry *ce = cache_find(L)) {
+            if (ce->plan) { ce->plan->factor_on_device = false; ce->plan->winv_valid = false; }
+            if (ce->mg) ce->mg->factor_on_devices = false;
+            if (symbolic) cache_drop(ce);
+        }
         if (symbolic) {
             static change_factor_fn cf2 = (change_factor_fn) host_sym("cholmod_l_change_factor");
             if (cf2) cf2(SSB_CHOLMOD_PATTERN, 1, 1, 1, 1, L, Common);
@@ -1117,15 +1673,32 @@ extern "C" int cholmod_l_super_numeric(ssb_cholmod_sparse *A, ssb_cholmod_sparse
     if (!e) return fail(SSB_CHOLMOD_GPU_PROBLEM, ssb200_last_error());
     pin_host_x(e, L);
     ssb_long minor = (ssb_long) L->n;
-    const int rc = ssb200_factorize(e->plan, stype, (const ssb_long *) A->p, (const ssb_long *) A->i, A->packed ? nullptr : (const ssb_long *) A->nz,
-                                    (const double *) A->x, (ssb_long) A->ncol,
-                                    F ? (const ssb_long *) F->p : nullptr, F ? (const ssb_long *) F->i : nullptr,
-                                    (F && !F->packed) ? (const ssb_long *) F->nz : nullptr, F ? (const double *) F->x : nullptr,
-                                    beta, Common->quick_return_if_not_posdef, (double *) L->x, &minor);
+    const ssb_long *Anz_ = A->packed ? nullptr : (const ssb_long *) A->nz;
+    const ssb_long *Fp_ = F ? (const ssb_long *) F->p : nullptr, *Fi_ = F ? (const ssb_long *) F->i : nullptr, *Fnz_ = (F && !F->packed) ? (const ssb_long *) F->nz : nullptr;
+    const double *Fx_ = F ? (const double *) F->x : nullptr;
+    int rc;
+    if (e->mg) {
+        rc = ssb200_mg_factorize(e->mg, stype, (const ssb_long *) A->p, (const ssb_long *) A->i, Anz_, (const double *) A->x, (ssb_long) A->ncol,
+                                 Fp_, Fi_, Fnz_, Fx_, beta, (double *) L->x, &minor);
+        if (rc == SSB_CHOLMOD_NOT_POSDEF) {
+            // the reference's protocol for a matrix that is not positive definite (zero the tail, repeat the failing supernode
+            // on its leading columns, t_cholmod_super_numeric.c:905-968) is implemented by the single-GPU path: run it there
+            e = cache_get_plan(L, /*single_gpu_only=*/true);
+            if (!e) return fail(SSB_CHOLMOD_GPU_PROBLEM, ssb200_last_error());
+            pin_host_x(e, L);
+        }
+    }
+    if (!e->mg)
+        rc = ssb200_factorize(e->plan, stype, (const ssb_long *) A->p, (const ssb_long *) A->i, Anz_, (const double *) A->x, (ssb_long) A->ncol,
+                              Fp_, Fi_, Fnz_, Fx_, beta, Common->quick_return_if_not_posdef, (double *) L->x, &minor);
     if (rc < 0) return fail(rc == SSB_CHOLMOD_INVALID ? SSB_CHOLMOD_INVALID : SSB_CHOLMOD_GPU_PROBLEM, ssb200_last_error());
     take_value_fingerprint(e, L);
     // statistics the reference keeps in Common (cholmod_core.h:1002-1048)
-    const ssb200_stats &st = e->plan->stats;
+    ssb200_stats st = e->mg ? e->mg->d[0].plan->stats : e->plan->stats;
+    if (e->mg) {
+        st.kernel_launches = 0; st.ms_total = e->mg->last_ms;
+        for (auto &dv : e->mg->d) st.kernel_launches += dv.plan->stats.kernel_launches;
+    }
     Common->gpu_syrk_calls = (size_t) st.nupdates; Common->gpu_gemm_calls = (size_t) st.nupdates;
     Common->gpu_potrf_calls = (size_t) st.nsuper; Common->gpu_trsm_calls = (size_t) st.nsuper;
     Common->cpu_syrk_calls = Common->cpu_gemm_calls = Common->cpu_potrf_calls = Common->cpu_trsm_calls = 0;
@@ -1169,10 +1742,11 @@ static int super_solve_common(ssb_cholmod_factor *L, ssb_cholmod_dense *X, ssb_c
     if (!e) { RAISE(Common, SSB_CHOLMOD_GPU_PROBLEM, ssb200_last_error()); return 0; }
     if (!value_fingerprint_ok(e, L)) {
         // L->x was produced or modified elsewhere: bring it to the device (still the GPU path, just slower)
-        if (ssb200_upload_L(e->plan, (const double *) L->x)) { RAISE(Common, SSB_CHOLMOD_GPU_PROBLEM, ssb200_last_error()); return 0; }
+        if (e->mg ? ssb200_mg_upload_L(e->mg, (const double *) L->x) : ssb200_upload_L(e->plan, (const double *) L->x)) { RAISE(Common, SSB_CHOLMOD_GPU_PROBLEM, ssb200_last_error()); return 0; }
         take_value_fingerprint(e, L);
     }
-    const int rc = ssb200_solve(e->plan, which, (double *) X->x, (ssb_long) X->ncol, (ssb_long) X->d);
+    const int rc = e->mg ? ssb200_mg_solve(e->mg, which, (double *) X->x, (ssb_long) X->ncol, (ssb_long) X->d)
+                         : ssb200_solve(e->plan, which, (double *) X->x, (ssb_long) X->ncol, (ssb_long) X->d);
     if (rc) { RAISE(Common, rc == SSB_CHOLMOD_INVALID ? SSB_CHOLMOD_INVALID : SSB_CHOLMOD_GPU_PROBLEM, ssb200_last_error()); return 0; }
     return 1;
 }
@@ -1229,7 +1803,9 @@ extern "C" int ssb200_invalidate_factor(const ssb_cholmod_factor *L)
     std::lock_guard<std::mutex> lk(g_cache_mu);
     CacheEntry *e = cache_find(L);
     if (!e) return 0;
-    e->plan->factor_on_device = false; e->plan->winv_valid = false; e->xptr = nullptr;
+    if (e->plan) { e->plan->factor_on_device = false; e->plan->winv_valid = false; }
+    if (e->mg) e->mg->factor_on_devices = false;
+    e->xptr = nullptr;
     return 1;
 }
 
@@ -1255,4 +1831,10 @@ extern "C" ssb200_plan *ssb200_plan_of_factor(const ssb_cholmod_factor *L)
     std::lock_guard<std::mutex> lk(g_cache_mu);
     CacheEntry *e = cache_find(L);
     return e ? e->plan : nullptr;
+}
+extern "C" ssb200_mg *ssb200_mg_of_factor(const ssb_cholmod_factor *L)
+{
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    CacheEntry *e = cache_find(L);
+    return e ? e->mg : nullptr;
 }

@@ -58,9 +58,10 @@ struct SolveJob {
     int winv_slot;       // >= 0: the inverse of the diagonal block is in winv[slot] (diagonal solve = 64x64 mat-vec)
 };
 constexpr int SOLVE_ROWS = 128;     // rows per solve-update tile
-struct SolveStep { long long job0; int njobs; long long tile0; int ntiles; };
+struct SolveStep { long long job0; int njobs; long long tile0; int ntiles; int level = 0; int sync = 0; };   // sync: multi-GPU solve - a step above the subtree cut (all devices pass it in lock step)
 
-enum LaunchKind : int { L_GEMM_BIG = 0, L_GEMM_SMALL = 1, L_POTRF = 2, L_TRSM = 3, L_TRSM_TC = 4, L_NKINDS = 5 };
+enum LaunchKind : int { L_GEMM_BIG = 0, L_GEMM_SMALL = 1, L_POTRF = 2, L_TRSM = 3, L_TRSM_TC = 4, L_NKINDS = 5,
+                        L_SYNC = 5 };   // L_SYNC: no kernel, only the launch's wait (joins the panel stream into the main stream)
 constexpr int TRSM_TC_MIN_W = 33;   // panels wider than 32 columns use the tensor-core trsm (inverse of the diagonal block)
 
 struct Launch {
@@ -71,6 +72,11 @@ struct Launch {
     long long tile0;     // first entry in the flat tile->job array of that kind (gemm, trsm)
     int ntiles;
     double flops;        // algorithmic flops of the launch
+    // Look-ahead schedule: stream 0 = main (descendant updates, big trailing updates), stream 1 = panel stream (the
+    // latency-bound potrf / trsm / small-K chain of the NEXT outer panel, high priority).  wait_ev: event the launch's
+    // stream waits for before the launch (-1 none); rec_ev: event recorded on its stream after the launch (-1 none).
+    // The launch list stays a valid serial order: with look-ahead off everything runs on one stream in list order.
+    int stream = 0, wait_ev = -1, rec_ev = -1;
 };
 
 // Device-to-host streaming of the factor: the Lx range [off, off+cnt) is final once launch `after_launch` has run.
@@ -108,11 +114,22 @@ struct HostPlan {
     std::vector<Launch> launches;    // in execution order
     std::vector<int> level_launch_begin; // nlevels+1
     std::vector<CopyTask> copy_tasks;    // sorted by after_launch
+    int n_events = 0;                    // cross-stream events of the look-ahead schedule
     // ---- elimination-tree shard over several GPUs (one process per GPU) -------------------------------------
     int nranks = 1, rank = 0;
     std::vector<int> owner;              // per supernode: rank that computes it, or -1 = its 256-column panels are cyclic over ranks
     std::vector<DistStep> steps;         // launches [begin,end) of this rank, then an optional broadcast of a finished Lx range
     double my_flops = 0;                 // dense flops this rank executes
+    // ---- distributed storage (multi-GPU inside one process): a rank stores only the supernodes it owns, the panel-cyclic
+    // supernodes (all of them: it computes some of their panels and reads the others) and the remote supernodes its
+    // updates read.  Present supernodes get consecutive local offsets in index order; every job offset is relocated.
+    bool compact = false;
+    std::vector<long long> lpx;          // local offset of supernode t in this rank's storage, -1 = not stored here
+    long long lxsize = 0;                // doubles of local factor storage
+    struct Piece { long long home_off, cnt; };
+    std::vector<std::vector<Piece>> step_recv;   // per step: the parts of the step's finished range this rank reads (home offsets)
+    std::vector<int> step_next;          // per step: for a finished panel of a cyclic supernode, the owner of the next panel (-1 none)
+    int top_min_level = 0;               // lowest etree level that holds a supernode above the subtree cut
     // solve schedule: supernodes ordered by level
     std::vector<int> level_ptr;      // nlevels+1
     std::vector<int> level_nodes;    // supernodes sorted by level
@@ -126,15 +143,17 @@ struct HostPlan {
 
 // Builds everything above from the symbolic factor.  Returns false (plan.error set) on invalid structure.
 bool build_host_plan(long long n, long long nsuper, const long long *super, const long long *pi, const long long *px,
-                     const long long *s, int nranks, int rank, HostPlan &plan);
+                     const long long *s, int nranks, int rank, HostPlan &plan, bool compact = false);
 
 // Job lists for factorizing ONE supernode restricted to its first ncol_limit columns (not-positive-definite repeat,
 // t_cholmod_super_numeric.c:944-967).  Appends launches to `out`.
 // slot of the inverse of the 64-column diagonal block starting at column j0 of supernode s (-1: none kept)
 int winv_slot_of(const HostPlan &hp, int s, int j0);
 
+// lookahead (whole supernodes only): the factorization of outer panel O+1 runs on the panel stream while the main stream
+// applies outer panel O to everything behind panel O+1; after_ev = event the first panel has to wait for (-1 none)
 void append_factor_jobs(const HostPlan &hp, const std::vector<int> &snodes, int ncol_limit, HostPlan &out, bool panel_copies = false,
-                        int only_panel_J0 = -1);
+                        int only_panel_J0 = -1, bool lookahead = false, int after_ev = -1);
 
 int gemm_tile_size(int kind);       // 128 for L_GEMM_BIG, 64 for L_GEMM_SMALL
 

@@ -328,6 +328,157 @@ __global__ void __launch_bounds__(POTRF_THREADS) potrf_block_kernel(const PanelJ
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// diagonal block Cholesky, version 3 (default): FOUR columns per barrier.  Same register layout as version 1 (thread
+// (ti,tk) keeps T(ti+16a, tk+16b) and Y(ti+16a, tk+16b)); per step the owners publish the four panel columns (and the four
+// panel rows of Y) as they are BEFORE the panel is factorized, one barrier, then EVERY thread factorizes the 4x4 diagonal
+// block redundantly (four dependent rsqrt instead of four barrier round trips), forward-substitutes the panel entries of
+// the 8 rows it needs, and applies a rank-4 update to its registers.  16 barriers per 64 columns instead of 64.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(POTRF_THREADS) potrf_block_kernel3(const PanelJob *__restrict__ jobs, double *__restrict__ Lx,
+                                                                    int *__restrict__ info, double *__restrict__ winv)
+{
+    __shared__ double cbuf[2][4][NB_INNER];
+    __shared__ double rbuf[2][4][NB_INNER];
+    const PanelJob job = jobs[blockIdx.x];
+    const int w = job.w, tid = threadIdx.x;
+    const int ti = tid & 15, tk = tid >> 4;
+    const long long lda = job.lda;
+    const bool want_inv = job.winv_slot >= 0;
+    double *__restrict__ A = Lx + job.x_off;
+    double t[4][4], y[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            const int i = ti + 16 * a, k = tk + 16 * b;
+            t[a][b] = (i < w && k < w && i >= k) ? A[i + k * lda] : 0.0;
+            y[a][b] = (i == k) ? 1.0 : 0.0;
+        }
+    for (int j = 0, it = 0; j < w; j += 4, it++) {
+        double (*cb)[NB_INNER] = cbuf[it & 1];
+        double (*rb)[NB_INNER] = rbuf[it & 1];
+        const int jb = j >> 4, jq = j & 15;            // the four columns share the 16-block jb; their owners have tk = jq..jq+3
+        if (tk >= jq && tk < jq + 4) {
+            const int c = tk - jq;
+#pragma unroll
+            for (int a = 0; a < 4; a++) {
+                double v = 0.0;
+#pragma unroll
+                for (int bb = 0; bb < 4; bb++) if (bb == jb) v = t[a][bb];
+                cb[c][ti + 16 * a] = v;
+            }
+        }
+        if (want_inv && ti >= jq && ti < jq + 4) {
+            const int c = ti - jq;
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                double v = 0.0;
+#pragma unroll
+                for (int aa = 0; aa < 4; aa++) if (aa == jb) v = y[aa][b];
+                rb[c][tk + 16 * b] = v;
+            }
+        }
+        __syncthreads();
+        // 4x4 diagonal block, factorized by every thread (identical arithmetic everywhere: uniform control flow)
+        double l[4][4], rinv[4];
+        int failc = -1;
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            double dcc = cb[c][j + c];
+#pragma unroll
+            for (int q = 0; q < c; q++) dcc -= l[c][q] * l[c][q];
+            if (j + c >= w) dcc = 1.0;                 // padding beyond the block: identity
+            if (!(dcc > 0.0)) { if (failc < 0) failc = c; dcc = 1.0; }
+            const double ri = rsqrt(dcc);
+            rinv[c] = ri; l[c][c] = dcc * ri;
+#pragma unroll
+            for (int r = c + 1; r < 4; r++) {
+                double v = cb[c][j + r];
+#pragma unroll
+                for (int q = 0; q < c; q++) v -= l[r][q] * l[c][q];
+                l[r][c] = v * ri;
+            }
+        }
+        if (failc >= 0) {                               // first non-positive (or NaN) pivot: LAPACK's info
+            if (tid == 0) atomicMin(&info[job.snode], job.col0 + j + failc + 1);
+            break;
+        }
+        // panel entries L(i, j..j+3) of the rows this thread needs: i = ti+16a (Li) and i = tk+16b (Lk).  Rows at or above
+        // the panel give values that are never used (updates touch k > j+3 only, stores i >= column only).
+        double Li[4][4], Lk[4][4];
+#pragma unroll
+        for (int a = 0; a < 4; a++) {
+            const int i = ti + 16 * a;
+            const double x0 = cb[0][i] * rinv[0];
+            const double x1 = (cb[1][i] - x0 * l[1][0]) * rinv[1];
+            const double x2 = (cb[2][i] - x0 * l[2][0] - x1 * l[2][1]) * rinv[2];
+            const double x3 = (cb[3][i] - x0 * l[3][0] - x1 * l[3][1] - x2 * l[3][2]) * rinv[3];
+            Li[a][0] = x0; Li[a][1] = x1; Li[a][2] = x2; Li[a][3] = x3;
+        }
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            const int k = tk + 16 * b;
+            const double x0 = cb[0][k] * rinv[0];
+            const double x1 = (cb[1][k] - x0 * l[1][0]) * rinv[1];
+            const double x2 = (cb[2][k] - x0 * l[2][0] - x1 * l[2][1]) * rinv[2];
+            const double x3 = (cb[3][k] - x0 * l[3][0] - x1 * l[3][1] - x2 * l[3][2]) * rinv[3];
+            Lk[b][0] = x0; Lk[b][1] = x1; Lk[b][2] = x2; Lk[b][3] = x3;
+        }
+        // the finished panel columns go to global memory: threads tk < 4 write column j+tk, rows ti+16a
+        if (tk < 4 && j + tk < w) {
+#pragma unroll
+            for (int a = 0; a < 4; a++) {
+                const int i = ti + 16 * a;
+                double v = 0.0;
+#pragma unroll
+                for (int c = 0; c < 4; c++) if (c == tk) v = Li[a][c];
+                if (i >= j + tk && i < w) A[i + (long long) (j + tk) * lda] = v;
+            }
+        }
+        // rank-4 update of the trailing part
+#pragma unroll
+        for (int a = 0; a < 4; a++)
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                const int i = ti + 16 * a, k = tk + 16 * b;
+                if (k > j + 3 && i >= k)
+                    t[a][b] -= Li[a][0] * Lk[b][0] + Li[a][1] * Lk[b][1] + Li[a][2] * Lk[b][2] + Li[a][3] * Lk[b][3];
+            }
+        if (want_inv) {
+            // rows j..j+3 of Y = L^{-1} become final (4-step forward substitution), then Y(i,:) -= L(i,panel) * Y(panel,:)
+            double Yf[4][4];
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                const int k = tk + 16 * b;
+                const double y0 = rb[0][k] * rinv[0];
+                const double y1 = (rb[1][k] - l[1][0] * y0) * rinv[1];
+                const double y2 = (rb[2][k] - l[2][0] * y0 - l[2][1] * y1) * rinv[2];
+                const double y3 = (rb[3][k] - l[3][0] * y0 - l[3][1] * y1 - l[3][2] * y2) * rinv[3];
+                Yf[0][b] = y0; Yf[1][b] = y1; Yf[2][b] = y2; Yf[3][b] = y3;
+            }
+#pragma unroll
+            for (int a = 0; a < 4; a++)
+#pragma unroll
+                for (int b = 0; b < 4; b++) {
+                    const int i = ti + 16 * a;
+                    if (i > j + 3) y[a][b] -= Li[a][0] * Yf[0][b] + Li[a][1] * Yf[1][b] + Li[a][2] * Yf[2][b] + Li[a][3] * Yf[3][b];
+                    else if (i >= j) {
+#pragma unroll
+                        for (int c = 0; c < 4; c++) if (i == j + c) y[a][b] = Yf[c][b];
+                    }
+                }
+        }
+    }
+    if (want_inv) {
+        double *__restrict__ W = winv + (long long) job.winv_slot * (NB_INNER * NB_INNER);
+#pragma unroll
+        for (int a = 0; a < 4; a++)
+#pragma unroll
+            for (int b = 0; b < 4; b++) W[(ti + 16 * a) + NB_INNER * (tk + 16 * b)] = y[a][b];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // diagonal block Cholesky, version 2: blocked by 16-column sub-panels so that the column-by-column part has NO block
 // barriers.  Per sub-panel: (1) ONE warp factorizes the 16x16 diagonal sub-block in registers with shuffles - lanes 0..15
 // hold its rows, lanes 16..31 hold the rows of its inverse, built by the same elimination; (2) all threads bring the rows

@@ -84,7 +84,7 @@ inline void route_gemm(const GemmJob &j, std::vector<GemmJob> &small, std::vecto
 // Blocked factorization steps for a set of mutually independent supernodes (one etree level, or one repeated
 // supernode with ncol_limit >= 0).  Appends to out.{potrf_jobs,trsm_jobs,trsm_tiles,gemm_jobs,gemm_tiles,launches}.
 void append_factor_jobs(const HostPlan &hp, const std::vector<int> &snodes, int ncol_limit, HostPlan &out, bool panel_copies,
-                        int only_panel_J0)
+                        int only_panel_J0, bool lookahead, int after_ev)
 {
     int maxcol = 0;
     for (int s : snodes) {
@@ -92,11 +92,14 @@ void append_factor_jobs(const HostPlan &hp, const std::vector<int> &snodes, int 
         if (ncol_limit >= 0) nscol = std::min(nscol, ncol_limit);
         maxcol = std::max(maxcol, nscol);
     }
+    int NB_OUTER = ssb::NB_OUTER;           // tests shrink the outer panel so that small meshes exercise the look-ahead schedule
+    if (const char *e = getenv("SSB200_NB_OUTER")) { const int v = atoi(e); if (v >= NB_MID && v % NB_MID == 0) NB_OUTER = v; }
+    if (ncol_limit >= 0 || only_panel_J0 >= 0 || maxcol <= NB_OUTER) lookahead = false;   // nothing to overlap
     std::vector<GemmJob> gs, gb;
-    // trailing update of one supernode: columns [c0, c1) of the tall block, with the finished panel [p0, p0+W) (K = W)
-    auto trailing = [&](int s, int p0, int W, int c1) {
+    // trailing update of one supernode with the finished panel [p0, p0+W) (K = W): columns [c0, c1) of the tall block, rows
+    // from c0 down (c0 >= p0+W)
+    auto trailing_cols = [&](int s, int p0, int W, int c0, int c1) {
         const int nsrow = (int) (hp.pi[s + 1] - hp.pi[s]);
-        const int c0 = p0 + W;
         if (c1 - c0 <= 0) return;
         GemmJob g{};
         g.a_off = hp.px[s] + c0 + (long long) p0 * nsrow;
@@ -104,10 +107,14 @@ void append_factor_jobs(const HostPlan &hp, const std::vector<int> &snodes, int 
         g.map_off = -1; g.lda = nsrow; g.ldc = nsrow; g.K = W; g.nd1 = c1 - c0; g.nd2 = nsrow - c0; g.atomic = 1;
         route_gemm(g, gs, gb);
     };
+    auto trailing = [&](int s, int p0, int W, int c1) { trailing_cols(s, p0, W, p0 + W, c1); };
     auto ncols = [&](int s) { const int c = hp.super[s + 1] - hp.super[s]; return ncol_limit >= 0 ? std::min(c, ncol_limit) : c; };
     const int O_first = only_panel_J0 >= 0 ? (only_panel_J0 / NB_OUTER) * NB_OUTER : 0;
+    int ev_before_panel = after_ev;         // look-ahead: what the panel stream waits for before it touches the next outer panel
+    int ev_last_panel = -1;
     for (int O0 = O_first; O0 < maxcol; O0 += NB_OUTER) {
         const int O1 = std::min(O0 + NB_OUTER, maxcol);
+        const size_t panel_first = out.launches.size();
         for (int M0 = (only_panel_J0 >= 0 ? only_panel_J0 : O0); M0 < O1; M0 += NB_MID) {
             const int M1 = std::min(M0 + NB_MID, maxcol);
             for (int j0 = M0; j0 < M1; j0 += NB_INNER) {
@@ -174,20 +181,58 @@ void append_factor_jobs(const HostPlan &hp, const std::vector<int> &snodes, int 
             }
             emit_update_launches(out, gs, gb, 1);
         }
-        // K = 1024 update of everything behind the outer panel
+        if (!lookahead) {
+            // K = 1024 update of everything behind the outer panel
+            for (int s : snodes) {
+                const int nscol = ncols(s);
+                if (nscol <= O0) continue;
+                trailing(s, O0, std::min(NB_OUTER, nscol - O0), nscol);
+            }
+            emit_update_launches(out, gs, gb, 1);
+            continue;
+        }
+        // ---- look-ahead: this outer panel was factorized on the panel stream ------------------------------------------
+        const size_t panel_end = out.launches.size();
+        for (size_t t = panel_first; t < panel_end; t++) out.launches[t].stream = 1;
+        if (panel_end > panel_first) {
+            out.launches[panel_first].wait_ev = ev_before_panel;
+            ev_last_panel = out.n_events++;
+            out.launches[panel_end - 1].rec_ev = ev_last_panel;
+        }
+        // main stream, part 1: bring the NEXT outer panel's columns up to date (K = 1024) - the panel stream is waiting for it
+        const size_t next_first = out.launches.size();
         for (int s : snodes) {
             const int nscol = ncols(s);
-            if (nscol <= O0) continue;
-            trailing(s, O0, std::min(NB_OUTER, nscol - O0), nscol);
+            if (nscol <= O0 + NB_OUTER) continue;
+            trailing_cols(s, O0, NB_OUTER, O0 + NB_OUTER, std::min(O0 + 2 * NB_OUTER, nscol));
         }
         emit_update_launches(out, gs, gb, 1);
+        ev_before_panel = -1;
+        if (out.launches.size() > next_first) {
+            out.launches[next_first].wait_ev = ev_last_panel;
+            ev_before_panel = out.n_events++;
+            out.launches.back().rec_ev = ev_before_panel;
+        }
+        // main stream, part 2: everything behind the next outer panel; overlaps the factorization of the next outer panel
+        for (int s : snodes) {
+            const int nscol = ncols(s);
+            if (nscol <= O0 + 2 * NB_OUTER) continue;
+            trailing_cols(s, O0, NB_OUTER, O0 + 2 * NB_OUTER, nscol);
+        }
+        emit_update_launches(out, gs, gb, 1);
+    }
+    if (lookahead && ev_last_panel >= 0) {
+        // the main stream joins the panel stream before anything else reads these supernodes
+        Launch J{}; J.kind = L_SYNC; J.phase = 1; J.stream = 0; J.wait_ev = ev_last_panel;
+        out.launches.push_back(J);
     }
 }
 
 bool build_host_plan(long long n, long long nsuper, const long long *super, const long long *pi, const long long *px,
-                     const long long *s, int nranks, int rank, HostPlan &hp)
+                     const long long *s, int nranks, int rank, HostPlan &hp, bool compact)
 {
     hp = HostPlan();
+    hp.compact = compact && nranks > 1;
     if (n < 0 || nsuper < 0 || (nsuper > 0 && (!super || !pi || !px || !s))) { hp.error = "null symbolic arrays"; return false; }
     if (n >= (1LL << 31) - 1 || nsuper >= (1LL << 31) - 1) { hp.error = "n too large for 32-bit device row indices"; return false; }
     hp.n = n; hp.nsuper = nsuper;
@@ -371,10 +416,13 @@ bool build_host_plan(long long n, long long nsuper, const long long *super, cons
         for (int t = 0; t < (int) nsuper; t++) if (in_top[t] && hp.owner[t] >= 0) first_desc[t] = -1 - t;
     }
     auto mine_whole = [&](int sn) { return hp.owner[sn] == hp.rank; };
+    bool lookahead_enabled = true;
+    if (const char *e = getenv("SSB200_LOOKAHEAD")) lookahead_enabled = atoi(e) != 0;
     // lowest etree level that holds a supernode above the subtree cut: from there on a step may read remote data
     int top_min_level = hp.nlevels;
     if (hp.nranks > 1)
         for (int t = 0; t < (int) nsuper; t++) if (hp.owner[t] < 0 || first_desc[t] == -1 - t) top_min_level = std::min(top_min_level, hp.level[t]);
+    hp.top_min_level = top_min_level;
     int step_mid = -1;                                  // >= 0: launch index where the current step's post-range starts
     auto close_step = [&](int &step_begin, int src, long long off, long long cnt, int level) {
         const int end = (int) hp.launches.size();
@@ -387,6 +435,7 @@ bool build_host_plan(long long n, long long nsuper, const long long *super, cons
     std::vector<GemmJob> gs, gb;
     std::map<std::pair<int, int>, std::vector<GemmJob>> cyc_jobs;   // (panel-cyclic supernode, panel) -> descendant updates of this rank
     std::vector<int> nodes;
+    std::vector<char> need(nsuper, 0);      // supernodes whose values this rank's updates read
     int step_begin = 0;
     // Host streaming: every copy is a host-side call between kernel launches, so only the few supernodes near the root are
     // streamed panel by panel; everything up to the `flush` level goes out in merged contiguous ranges right after that
@@ -421,6 +470,7 @@ bool build_host_plan(long long n, long long nsuper, const long long *super, cons
             if (hp.owner[u.s] >= 0) {
                 if (!mine_whole(u.s)) continue;
                 hp.my_flops += 2.0 * ndcol * tri;
+                need[u.d] = 1;
                 route_gemm(g, gs, gb);
             } else {
                 // panel-cyclic target: cut the update where its target column crosses a 256-column panel boundary; a cut
@@ -436,6 +486,7 @@ bool build_host_plan(long long n, long long nsuper, const long long *super, cons
                         GemmJob h = g;
                         h.a_off += jlo; h.map_off += jlo; h.nd1 = jhi - jlo; h.nd2 = u.nd2 - jlo;
                         hp.my_flops += 2.0 * ndcol * ((double) h.nd1 * h.nd2 - 0.5 * (double) h.nd1 * (h.nd1 - 1));
+                        need[u.d] = 1;
                         // not launched with the level's other updates: the descendant updates of a panel are scheduled just
                         // in time inside the panel loop, where they fill the ranks' idle time behind the serial panel chain
                         cyc_jobs[{u.s, blk}].push_back(h);
@@ -455,7 +506,22 @@ bool build_host_plan(long long n, long long nsuper, const long long *super, cons
             nodes.push_back(sn);
             hp.my_flops += nscol * nscol * nscol / 3.0 + nscol * nscol * (nsrow - nscol);
         }
-        if (!nodes.empty()) append_factor_jobs(hp, nodes, -1, hp, /*panel_copies=*/hp.nranks == 1 && l > flush);
+        if (!nodes.empty()) {
+            // single GPU: look-ahead inside the level's supernodes; the panel stream first waits for the level's descendant
+            // updates (everything launched so far on the main stream)
+            int after_ev = -1;
+            const bool la = hp.nranks == 1 && lookahead_enabled;
+            if (la && !hp.launches.empty()) {
+                int maxcol = 0;
+                for (int sn : nodes) maxcol = std::max(maxcol, hp.super[sn + 1] - hp.super[sn]);
+                {
+                    Launch &last = hp.launches.back();
+                    if (last.rec_ev < 0) last.rec_ev = hp.n_events++;
+                    after_ev = last.rec_ev;
+                }
+            }
+            append_factor_jobs(hp, nodes, -1, hp, /*panel_copies=*/hp.nranks == 1 && l > flush, -1, la, after_ev);
+        }
         if (hp.nranks == 1 && l == flush && !hp.launches.empty()) {
             // every supernode of level <= flush is final: merge consecutive indices into contiguous Lx ranges
             const int after = (int) hp.launches.size() - 1;
@@ -551,6 +617,8 @@ bool build_host_plan(long long n, long long nsuper, const long long *super, cons
     close_step(step_begin, -1, 0, 0, hp.nlevels);
     if (hp.nranks == 1) hp.my_flops = hp.flops_update + hp.flops_potrf + hp.flops_trsm;
     // ---- solve schedule: per level, per 64-column block index ------------------------------------------------
+    // Distributed storage: a rank solves with the blocks it factorized (its supernodes, its panels of the cyclic ones);
+    // every rank walks the same step list, steps above the subtree cut are passed in lock step.
     for (int l = 0; l < hp.nlevels; l++) {
         int maxcol = 0;
         for (int t = hp.level_ptr[l]; t < hp.level_ptr[l + 1]; t++) {
@@ -559,10 +627,15 @@ bool build_host_plan(long long n, long long nsuper, const long long *super, cons
         }
         for (int j0 = 0; j0 < maxcol; j0 += NB_INNER) {
             SolveStep st{(long long) hp.solve_jobs.size(), 0, (long long) hp.solve_tiles.size(), 0};
+            st.level = l; st.sync = (hp.compact && l >= top_min_level) ? 1 : 0;
             for (int t = hp.level_ptr[l]; t < hp.level_ptr[l + 1]; t++) {
                 const int sn = hp.level_nodes[t];
                 const int nscol = hp.super[sn + 1] - hp.super[sn];
                 if (nscol <= j0) continue;
+                if (hp.compact) {
+                    const int o = hp.owner[sn];
+                    if (o >= 0 ? (o != hp.rank) : ((j0 / NB_MID) % hp.nranks != hp.rank)) continue;
+                }
                 const int nsrow = (int) (hp.pi[sn + 1] - hp.pi[sn]);
                 SolveJob sj{};
                 sj.w = std::min(NB_INNER, nscol - j0);
@@ -577,7 +650,54 @@ bool build_host_plan(long long n, long long nsuper, const long long *super, cons
                 hp.solve_jobs.push_back(sj);
                 st.njobs++;
             }
-            if (st.njobs) hp.solve_steps.push_back(st);
+            if (st.njobs || hp.compact) hp.solve_steps.push_back(st);
+        }
+    }
+    // ---- distributed storage: local layout, relocation of every offset, receive lists ---------------------------------
+    if (hp.compact) {
+        hp.lpx.assign(nsuper + 1, -1);
+        long long pos = 0;
+        for (int t = 0; t < (int) nsuper; t++) {
+            const bool present = hp.owner[t] == hp.rank || hp.owner[t] < 0 || need[t];
+            if (!present) continue;
+            hp.lpx[t] = pos;
+            pos += hp.px[t + 1] - hp.px[t];            // no padding: a run of consecutive supernodes keeps its internal offsets on every rank
+        }
+        hp.lxsize = pos; hp.lpx[nsuper] = pos;
+        auto loc = [&](long long home) -> long long {
+            const int t = (int) (std::upper_bound(hp.px.begin(), hp.px.end(), home) - hp.px.begin()) - 1;
+            if (t < 0 || t >= (int) nsuper || hp.lpx[t] < 0) { hp.error = "internal: job reads a supernode that is not stored on this rank"; return -1; }
+            return hp.lpx[t] + (home - hp.px[t]);
+        };
+        for (auto &g : hp.gemm_jobs) { g.a_off = loc(g.a_off); g.c_off = loc(g.c_off); }
+        for (auto &j : hp.potrf_jobs) j.x_off = loc(j.x_off);
+        for (auto &j : hp.trsm_jobs) j.x_off = loc(j.x_off);
+        for (auto &j : hp.solve_jobs) j.x_off = loc(j.x_off);
+        if (!hp.error.empty()) return false;
+        // what this rank pulls out of every finished range: maximal runs of consecutive needed supernodes
+        hp.step_recv.assign(hp.steps.size(), {});
+        hp.step_next.assign(hp.steps.size(), -1);
+        for (size_t k = 0; k < hp.steps.size(); k++) {
+            const DistStep &st = hp.steps[k];
+            if (st.bcast_src < 0 || st.bcast_src == hp.rank || st.cnt <= 0) continue;
+            const int t0 = (int) (std::upper_bound(hp.px.begin(), hp.px.end(), st.off) - hp.px.begin()) - 1;
+            if (hp.owner[t0] < 0) {                      // a panel of a cyclic supernode: always read by everybody
+                hp.step_recv[k].push_back(HostPlan::Piece{st.off, st.cnt});
+                // the owner of the NEXT panel is on the critical path: it pulls first
+                const long long nsrow = hp.pi[t0 + 1] - hp.pi[t0];
+                const int nscol = hp.super[t0 + 1] - hp.super[t0];
+                const int J = (int) ((st.off - hp.px[t0]) / ((long long) NB_MID * nsrow));
+                if ((J + 1) * NB_MID < nscol) hp.step_next[k] = (J + 1) % hp.nranks;
+                continue;
+            }
+            long long run_off = -1, run_end = -1;
+            for (int t = t0; t < (int) nsuper && hp.px[t] < st.off + st.cnt; t++) {
+                if (need[t]) {
+                    if (run_off < 0) run_off = hp.px[t];
+                    run_end = hp.px[t + 1];
+                } else if (run_off >= 0) { hp.step_recv[k].push_back(HostPlan::Piece{run_off, run_end - run_off}); run_off = -1; }
+            }
+            if (run_off >= 0) hp.step_recv[k].push_back(HostPlan::Piece{run_off, run_end - run_off});
         }
     }
     return true;
@@ -622,14 +742,50 @@ extern "C" int ssb200_export_begin(long long n, long long nsuper, const long lon
     return 0;
 }
 
-// launches[nl*4] = kind, job0, njobs, phase; gemm[ng*8] = a_off,c_off,map_off,lda,ldc,K,nd1,nd2; panel arrays [..*6] = x_off,lda,w,
+// distributed-storage variant of ssb200_export_begin: same, with the compact per-rank layout (local offsets in every job)
+extern "C" int ssb200_export_begin_compact(long long n, long long nsuper, const long long *super, const long long *pi, const long long *px,
+                                           const long long *s, int nranks, int rank, long long *sizes /*[8]*/, long long *csizes /*[2]: lxsize, pieces*/)
+{
+    delete g_export; g_export = new ssb::HostPlan();
+    if (!ssb::build_host_plan(n, nsuper, super, pi, px, s, nranks, rank, *g_export, true)) { delete g_export; g_export = nullptr; return -4; }
+    sizes[0] = (long long) g_export->launches.size(); sizes[1] = (long long) g_export->gemm_jobs.size();
+    sizes[2] = (long long) g_export->potrf_jobs.size(); sizes[3] = (long long) g_export->trsm_jobs.size();
+    sizes[4] = (long long) g_export->steps.size(); sizes[5] = (long long) g_export->updates.size();
+    sizes[6] = g_export->relmap_size; sizes[7] = g_export->nlevels;
+    long long np = 0;
+    for (const auto &v : g_export->step_recv) np += (long long) v.size();
+    csizes[0] = g_export->lxsize; csizes[1] = np;
+    return 0;
+}
+
+// lpx[nsuper+1]; pieces[np*3] = step, home_off, cnt; step_next[nsteps]; solve[nsolvejobs*4] = x_off (local), w, xcol0, rows_below.
+// Call before ssb200_export_fetch (which releases the plan).
+extern "C" long long ssb200_export_compact_fetch(long long *lpx, long long *pieces, int *step_next, long long *solve, long long solve_cap)
+{
+    if (!g_export || !g_export->compact) return -4;
+    const ssb::HostPlan &hp = *g_export;
+    for (size_t t = 0; t < hp.lpx.size(); t++) lpx[t] = hp.lpx[t];
+    long long q = 0;
+    for (size_t k = 0; k < hp.step_recv.size(); k++)
+        for (const auto &pc : hp.step_recv[k]) { pieces[3 * q] = (long long) k; pieces[3 * q + 1] = pc.home_off; pieces[3 * q + 2] = pc.cnt; q++; }
+    for (size_t k = 0; k < hp.step_next.size(); k++) step_next[k] = hp.step_next[k];
+    const long long nsj = (long long) hp.solve_jobs.size();
+    if (solve && solve_cap >= nsj)
+        for (long long t = 0; t < nsj; t++) { solve[4 * t] = hp.solve_jobs[t].x_off; solve[4 * t + 1] = hp.solve_jobs[t].w; solve[4 * t + 2] = hp.solve_jobs[t].xcol0; solve[4 * t + 3] = hp.solve_jobs[t].rows_below; }
+    return nsj;
+}
+
+// launches[nl*7] = kind, job0, njobs, phase, stream, wait_ev, rec_ev; gemm[ng*8] = a_off,c_off,map_off,lda,ldc,K,nd1,nd2; panel arrays [..*6] = x_off,lda,w,
 // rows_below,col0,snode; steps[ns*7] = launch_begin,launch_mid,launch_end,src,off,cnt,wait_remote; updates[nu*6] = d,s,p0,nd1,nd2,map_off; owner[nsuper]
 extern "C" int ssb200_export_fetch(long long *launches, long long *gemm, long long *potrf, long long *trsm, long long *steps,
                                    long long *updates, int *owner)
 {
     if (!g_export) return -4;
     const ssb::HostPlan &hp = *g_export;
-    for (size_t t = 0; t < hp.launches.size(); t++) { const auto &L = hp.launches[t]; launches[4 * t] = L.kind; launches[4 * t + 1] = L.job0; launches[4 * t + 2] = L.njobs; launches[4 * t + 3] = L.phase; }
+    for (size_t t = 0; t < hp.launches.size(); t++) {
+        const auto &L = hp.launches[t]; long long *o = launches + 7 * t;
+        o[0] = L.kind; o[1] = L.job0; o[2] = L.njobs; o[3] = L.phase; o[4] = L.stream; o[5] = L.wait_ev; o[6] = L.rec_ev;
+    }
     for (size_t t = 0; t < hp.gemm_jobs.size(); t++) { const auto &g = hp.gemm_jobs[t]; long long *o = gemm + 8 * t; o[0] = g.a_off; o[1] = g.c_off; o[2] = g.map_off; o[3] = g.lda; o[4] = g.ldc; o[5] = g.K; o[6] = g.nd1; o[7] = g.nd2; }
     auto panel = [](const std::vector<ssb::PanelJob> &v, long long *out) { for (size_t t = 0; t < v.size(); t++) { long long *o = out + 6 * t; o[0] = v[t].x_off; o[1] = v[t].lda; o[2] = v[t].w; o[3] = v[t].rows_below; o[4] = v[t].col0; o[5] = v[t].snode; } };
     panel(hp.potrf_jobs, potrf); panel(hp.trsm_jobs, trsm);

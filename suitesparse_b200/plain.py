@@ -133,6 +133,10 @@ class Plan:
     def solve_resident(self, dX_ptr: int, nrhs: int, ldx: int, which: int = 2):
         self._check(self.lib.ssb200_solve_resident(self.h, which, C.c_void_p(dX_ptr), nrhs, ldx))
 
+    def set_lookahead(self, on: bool):
+        self.lib.ssb200_set_lookahead.argtypes = [C.c_void_p, C.c_int]
+        self._check(self.lib.ssb200_set_lookahead(self.h, 1 if on else 0))
+
     def factor_diag(self) -> np.ndarray:
         d = np.empty(self.n, dtype=np.float64)
         self._check(self.lib.ssb200_factor_diag(self.h, _ptr(d)))
@@ -148,6 +152,75 @@ class Plan:
         out = np.empty(max(nrel, 1), dtype=np.int32)
         self.lib.ssb200_debug_relmap(self.h, _ptr(out), nrel)
         return out[:nrel]
+
+
+class MultiGpu:
+    """One factorization over several GPUs of this process (ssb200_mg_*): distributed storage, pulls over NVLink."""
+
+    def __init__(self, n, super_, pi, px, s, devices=None, ndev: int | None = None, handle=None):
+        self.lib = L = _lib()
+        L.ssb200_mg_create.restype = C.c_void_p
+        L.ssb200_mg_create.argtypes = [c_long, c_long, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.ssb200_mg_destroy.argtypes = [C.c_void_p]
+        L.ssb200_mg_pin_host.argtypes = [C.c_void_p, C.c_void_p]
+        L.ssb200_mg_factorize.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, c_long,
+                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(c_long)]
+        L.ssb200_mg_solve.argtypes = [C.c_void_p, C.c_int, C.c_void_p, c_long, c_long]
+        L.ssb200_mg_upload_L.argtypes = [C.c_void_p, C.c_void_p]
+        L.ssb200_mg_info.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        self.n = int(n)
+        self.owned = handle is None
+        if handle is None:
+            self.super, self.pi, self.px, self.s = _i64(super_), _i64(pi), _i64(px), _i64(s)
+            if devices is None:
+                devices = list(range(ndev if ndev else L.ssb200_device_count()))
+            dv = np.ascontiguousarray(devices, dtype=np.int32)
+            handle = L.ssb200_mg_create(self.n, self.super.size - 1, _ptr(self.super), _ptr(self.pi), _ptr(self.px), _ptr(self.s), len(dv), _ptr(dv))
+            if not handle:
+                raise SsbError(L.ssb200_last_error().decode())
+            self.ndev = len(dv); self.xsize = int(self.px[-1])
+        self.h = C.c_void_p(handle)
+
+    def _check(self, rc):
+        if rc < 0:
+            raise SsbError(f"status {rc}: {self.lib.ssb200_last_error().decode()}")
+        return rc
+
+    def pin_host(self, Lx: np.ndarray):
+        return self.lib.ssb200_mg_pin_host(self.h, _ptr(Lx))
+
+    def factorize(self, A_lower, beta: float = 0.0, Lx_host: np.ndarray | None = None, F=None):
+        """Returns (status, minor).  Lx_host (xsize doubles) receives the factor when given."""
+        Ap, Ai, Ax = _i64(A_lower.indptr), _i64(A_lower.indices), np.ascontiguousarray(A_lower.data, dtype=np.float64)
+        b = (C.c_double * 2)(beta, 0.0)
+        minor = c_long(0)
+        if F is None:
+            st = self.lib.ssb200_mg_factorize(self.h, -1, _ptr(Ap), _ptr(Ai), None, _ptr(Ax), A_lower.shape[1], None, None, None, None,
+                                              b, _ptr(Lx_host), C.byref(minor))
+        else:
+            Fp, Fi, Fx = _i64(F.indptr), _i64(F.indices), np.ascontiguousarray(F.data, dtype=np.float64)
+            st = self.lib.ssb200_mg_factorize(self.h, 0, _ptr(Ap), _ptr(Ai), None, _ptr(Ax), A_lower.shape[1], _ptr(Fp), _ptr(Fi), None, _ptr(Fx),
+                                              b, _ptr(Lx_host), C.byref(minor))
+        return self._check(st), minor.value
+
+    def solve(self, X: np.ndarray, which: int = 2) -> np.ndarray:
+        X = np.array(X, dtype=np.float64, order="F", copy=True)
+        X2 = X.reshape(X.shape[0], -1, order="F")
+        self._check(self.lib.ssb200_mg_solve(self.h, which, _ptr(X2), X2.shape[1], X2.shape[0]))
+        return X
+
+    def upload_L(self, Lx: np.ndarray):
+        self._check(self.lib.ssb200_mg_upload_L(self.h, _ptr(np.ascontiguousarray(Lx, dtype=np.float64))))
+
+    def info(self) -> dict:
+        out = np.zeros(3 + 2 * 16)
+        N = self.lib.ssb200_mg_info(self.h, _ptr(out), out.size)
+        return dict(ndev=N, ms_factorize=out[0], ms_solve=out[1], nvlink_bytes=out[2], device_bytes=out[3:3 + N].tolist(), rank_flops=out[3 + N:3 + 2 * N].tolist())
+
+    def close(self):
+        if self.h and self.owned:
+            self.lib.ssb200_mg_destroy(self.h)
+        self.h = None
 
 
 def plan_of_factor(Lp) -> Plan | None:

@@ -17,12 +17,108 @@ def export_plan(n, super_, pi, px, s, nranks=1, rank=0):
     rc = lib.ssb200_export_begin(C.c_int64(n), C.c_int64(len(super_) - 1), *[P(v) for v in a], C.c_int(nranks), C.c_int(rank), P(sizes))
     assert rc == 0, rc
     nl, ng, npo, nt, ns, nu = [int(v) for v in sizes[:6]]
-    out = dict(launches=np.zeros((nl, 4), np.int64), gemm=np.zeros((ng, 8), np.int64), potrf=np.zeros((npo, 6), np.int64),
+    out = dict(launches=np.zeros((nl, 7), np.int64), gemm=np.zeros((ng, 8), np.int64), potrf=np.zeros((npo, 6), np.int64),
                trsm=np.zeros((nt, 6), np.int64), steps=np.zeros((ns, 7), np.int64), updates=np.zeros((nu, 6), np.int64),
                owner=np.zeros(len(super_) - 1, np.int32))
     rc = lib.ssb200_export_fetch(*[P(out[k]) for k in ("launches", "gemm", "potrf", "trsm", "steps", "updates", "owner")])
     assert rc == 0
     out.update(relmap_size=int(sizes[6]), nlevels=int(sizes[7]), nranks=nranks, rank=rank)
+    return out
+
+
+def export_plan_compact(n, super_, pi, px, s, nranks, rank):
+    """Distributed-storage plan of one rank: job offsets are LOCAL; extra keys lpx, lxsize, pieces (step, home_off, cnt)."""
+    lib = C.CDLL(B200_LIB)
+    a = [np.ascontiguousarray(v, dtype=np.int64) for v in (super_, pi, px, s)]
+    sizes = np.zeros(8, dtype=np.int64); cs = np.zeros(2, dtype=np.int64)
+    P = lambda v: v.ctypes.data_as(C.c_void_p)
+    rc = lib.ssb200_export_begin_compact(C.c_int64(n), C.c_int64(len(super_) - 1), *[P(v) for v in a], C.c_int(nranks), C.c_int(rank), P(sizes), P(cs))
+    assert rc == 0, rc
+    nl, ng, npo, nt, ns, nu = [int(v) for v in sizes[:6]]
+    lpx = np.zeros(len(super_), np.int64); pieces = np.zeros((max(int(cs[1]), 1), 3), np.int64); nxt = np.zeros(max(ns, 1), np.int32)
+    lib.ssb200_export_compact_fetch.restype = C.c_int64
+    nsj = lib.ssb200_export_compact_fetch(P(lpx), P(pieces), P(nxt), None, C.c_int64(0))
+    solve = np.zeros((max(int(nsj), 1), 4), np.int64)
+    lib.ssb200_export_compact_fetch(P(lpx), P(pieces), P(nxt), P(solve), C.c_int64(nsj))
+    out = dict(launches=np.zeros((nl, 7), np.int64), gemm=np.zeros((ng, 8), np.int64), potrf=np.zeros((npo, 6), np.int64),
+               trsm=np.zeros((nt, 6), np.int64), steps=np.zeros((ns, 7), np.int64), updates=np.zeros((nu, 6), np.int64),
+               owner=np.zeros(len(super_) - 1, np.int32))
+    rc = lib.ssb200_export_fetch(*[P(out[k]) for k in ("launches", "gemm", "potrf", "trsm", "steps", "updates", "owner")])
+    assert rc == 0
+    out.update(relmap_size=int(sizes[6]), nlevels=int(sizes[7]), nranks=nranks, rank=rank, lpx=lpx, lxsize=int(cs[0]),
+               pieces=pieces[:int(cs[1])], step_next=nxt[:ns], solve=solve[:int(nsj)])
+    return out
+
+
+def assemble_compact(plan, super_, pi, px, s, S_lower, Lx):
+    """scatter_A_kernel under distributed storage: a rank assembles the columns it computes, at their LOCAL offsets."""
+    nsuper = len(super_) - 1
+    Sp, Si, Sx = S_lower.indptr, S_lower.indices, S_lower.data
+    lpx = plan["lpx"]
+    for sn in range(nsuper):
+        k1, k2 = int(super_[sn]), int(super_[sn + 1])
+        rows = s[pi[sn]: pi[sn + 1]]; nsrow = len(rows)
+        o = plan["owner"][sn]
+        for k in range(k1, k2):
+            if (o != plan["rank"]) if o >= 0 else (((k - k1) // NB_MID) % plan["nranks"] != plan["rank"]):
+                continue
+            assert lpx[sn] >= 0
+            for p in range(Sp[k], Sp[k + 1]):
+                i = Si[p]
+                if i >= k:
+                    pos = np.searchsorted(rows, i)
+                    if pos < nsrow and rows[pos] == i:
+                        Lx[lpx[sn] + pos + (k - k1) * nsrow] = Sx[p]
+
+
+def run_lockstep_compact(plans, rel, Lx, px):
+    """Distributed storage, all ranks in one process, asynchronous pulls: a pull snapshots the source's range when the step's
+    range becomes final and is delivered at the next wait_remote step (or the end).  Returns doubles pulled per rank."""
+    nr = len(plans)
+    pending = []
+    pulled = [0] * nr
+    loc = lambda pl, home: int(pl["lpx"][np.searchsorted(px, home, side="right") - 1] + home - px[np.searchsorted(px, home, side="right") - 1])
+    by_step = [dict() for _ in range(nr)]
+    for r in range(nr):
+        for k, ho, cnt in plans[r]["pieces"]:
+            by_step[r].setdefault(int(k), []).append((int(ho), int(cnt)))
+    for k in range(len(plans[0]["steps"])):
+        if plans[0]["steps"][k][6]:
+            for r, dst, data in pending:
+                Lx[r][dst: dst + len(data)] = data
+            pending = []
+        srcs = set()
+        for r in range(nr):
+            lo, mid, hi, src, off, cnt, wait = plans[r]["steps"][k]
+            run_launches(plans[r], rel, Lx[r], lo, mid)
+            srcs.add((int(src), int(off), int(cnt)))
+        assert len(srcs) == 1
+        src = srcs.pop()[0]
+        for r in range(nr):
+            for ho, cnt in by_step[r].get(k, []):
+                assert src >= 0 and r != src
+                so = loc(plans[src], ho); dn = loc(plans[r], ho)
+                pending.append((r, dn, Lx[src][so: so + cnt].copy())); pulled[r] += cnt
+        for r in range(nr):
+            lo, mid, hi = plans[r]["steps"][k][:3]
+            run_launches(plans[r], rel, Lx[r], mid, hi)
+    for r, dst, data in pending:
+        Lx[r][dst: dst + len(data)] = data
+    return pulled
+
+
+def gather_compact(plans, Lx, px, xsize):
+    """The host factor: every step's range copied out by its source rank (what ssb200_mg_factorize does with Lx_host)."""
+    out = np.full(xsize, np.nan)
+    for k in range(len(plans[0]["steps"])):
+        lo, mid, hi, src, off, cnt, wait = plans[0]["steps"][k]
+        if src < 0 or cnt <= 0:
+            continue
+        t = np.searchsorted(px, off, side="right") - 1
+        so = int(plans[src]["lpx"][t] + off - px[t])
+        assert np.isnan(out[off: off + cnt]).all()              # every entry exactly once
+        out[off: off + cnt] = Lx[src][so: so + cnt]
+    assert not np.isnan(out).any()
     return out
 
 
@@ -59,7 +155,7 @@ def assemble(plan, super_, pi, px, s, S_lower, Lx, beta=0.0):
 
 
 def run_launches(plan, rel, Lx, lo, hi):
-    for kind, job0, njobs, _ in plan["launches"][lo:hi]:
+    for kind, job0, njobs in plan["launches"][lo:hi, :3]:
         if kind in (L_GEMM_BIG, L_GEMM_SMALL):
             for a_off, c_off, moff, lda, ldc, K, nd1, nd2 in plan["gemm"][job0: job0 + njobs]:
                 idx = a_off + np.arange(nd2)[:, None] + np.arange(K)[None, :] * lda
@@ -84,6 +180,35 @@ def run_launches(plan, rel, Lx, lo, hi):
                 L11 = np.tril(Lx[idx])
                 bidx = x_off + w + np.arange(rows_below)[:, None] + np.arange(w)[None, :] * lda
                 Lx[bidx] = np.linalg.solve(L11, Lx[bidx].T).T
+
+
+def run_two_streams(plan, rel, Lx, prefer):
+    """Look-ahead schedule on two in-order streams with events (stream 0 = main, 1 = panel chain): a launch runs when its
+    stream has reached it and its wait event has been recorded.  `prefer` picks which stream advances whenever both can -
+    the two extremes (main stream as early as possible / as late as possible) expose a missing dependency as a wrong
+    factor.  Returns the number of launches that ran while the OTHER stream still had earlier list entries pending
+    (i.e. how much reordering the schedule allowed)."""
+    L = plan["launches"]
+    queues = [[t for t in range(len(L)) if L[t, 4] == st] for st in (0, 1)]
+    pos = [0, 0]; recorded = set(); reordered = 0
+    while pos[0] < len(queues[0]) or pos[1] < len(queues[1]):
+        ready = []
+        for st in (0, 1):
+            if pos[st] < len(queues[st]):
+                t = queues[st][pos[st]]
+                if L[t, 5] < 0 or int(L[t, 5]) in recorded:
+                    ready.append(st)
+        assert ready, "deadlock in the look-ahead schedule"
+        st = prefer if prefer in ready else ready[0]
+        t = queues[st][pos[st]]
+        other = 1 - st
+        if pos[other] < len(queues[other]) and queues[other][pos[other]] < t:
+            reordered += 1
+        run_launches(plan, rel, Lx, t, t + 1)
+        if L[t, 6] >= 0:
+            recorded.add(int(L[t, 6]))
+        pos[st] += 1
+    return reordered
 
 
 def factorize_emulated(n, super_, pi, px, s, S_lower, nranks=1, rank=0, bcast=None, beta=0.0):

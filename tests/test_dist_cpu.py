@@ -88,3 +88,51 @@ def test_sharded_schedule_with_cyclic_supernode_single_process(kind, N, nr, jit)
     for r in range(nr):
         assert persuper_relerr(f["px"], Lx[r], Lo) < 1e-11
     ch.free_sparse(S2); ch.free_factor(L)
+
+
+@pytest.mark.parametrize("kind,N,nr", [("lap7", 22, 4), ("lap7", 24, 2), ("lap27", 18, 3), ("elas", 8, 3), ("lap7", 26, 8)])
+def test_distributed_storage_schedule_single_process(kind, N, nr):
+    """The in-process multi-GPU path (ssb200_mg_*): every rank stores only its supernodes, the cyclic ones and the remote
+    supernodes its updates read; finished ranges are pulled piecewise by the ranks that read them.  Emulated ranks with
+    asynchronous pulls must reproduce the oracle's factor in the gathered host copy; local storage is smaller than L;
+    every solve block belongs to exactly one rank."""
+    import emulate_plan as E
+    from suitesparse_b200 import gen
+    from oracle import oracle
+    from conftest import REF_LIB
+    if not os.path.exists(REF_LIB):
+        pytest.skip("reference build (host libcholmod for cholmod_l_analyze) not present")
+    from suitesparse_b200.cholmod_host import Cholmod, _np_view
+    ch = Cholmod(gpu=False)
+    A, p = gen.make_problem(kind, N)
+    S = ch.sparse(A, +1); L = ch.analyze(S, p)
+    f = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in ch.factor_arrays(L).items()}
+    S2 = ch.lower_permuted(S, L); s2 = S2.contents; n = s2.nrow
+    Ap = _np_view(s2.p, n + 1, np.int64).copy(); Ai = _np_view(s2.i, int(Ap[n]), np.int64).copy(); Ax = _np_view(s2.x, int(Ap[n]), np.float64).copy()
+    Sl = sp.csc_matrix((Ax, Ai, Ap), shape=(n, n))
+    st, minor, Lo = oracle.factorize(n, f["super"], f["pi"], f["px"], f["s"], Sl)
+    os.environ["SSB200_DIST_TAU"] = "0"
+    try:
+        plans = [E.export_plan_compact(n, f["super"], f["pi"], f["px"], f["s"], nr, r) for r in range(nr)]
+    finally:
+        del os.environ["SSB200_DIST_TAU"]
+    xsize = int(f["px"][-1])
+    rel = E.relmap_of(plans[0], f["pi"], f["s"])
+    Lx = [np.zeros(max(pl["lxsize"], 1)) for pl in plans]
+    for r in range(nr):
+        E.assemble_compact(plans[r], f["super"], f["pi"], f["px"], f["s"], Sl, Lx[r])
+    pulled = E.run_lockstep_compact(plans, rel, Lx, f["px"])
+    host = E.gather_compact(plans, Lx, f["px"], xsize)
+    assert persuper_relerr(f["px"], host, Lo) < 1e-11
+    # distributed: the ranks together pull less than a full replication would move, nobody stores everything (nr > 2)
+    assert sum(pulled) < (nr - 1) * xsize
+    if nr > 2:
+        assert max(pl["lxsize"] for pl in plans) < xsize
+    # solve blocks: each 64-column block of each supernode on exactly one rank, at a valid local offset
+    nscol = np.diff(f["super"])
+    blocks = int(np.ceil(nscol / 64).sum())
+    cols = np.concatenate([pl["solve"][:, 2] for pl in plans])
+    assert len(cols) == blocks and len(set(cols.tolist())) == blocks
+    for pl in plans:
+        assert (pl["solve"][:, 0] >= 0).all() and (pl["solve"][:, 0] < max(pl["lxsize"], 1)).all()
+    ch.free_sparse(S2); ch.free_factor(L)

@@ -405,3 +405,108 @@ def test_baseline_configs_full_size_resident(kind, N):
     assert r["resid"] < TOL_RESID
     assert r["linearity"] < 1e-9
     assert r["min_diag"] > 0 and r["finite"]
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# multi-GPU inside the library (ssb200_mg_*, and the drop-in symbols with SSB200_DEVICES): needs two or more B200s
+# ---------------------------------------------------------------------------------------------------------------------
+def _ndev():
+    from suitesparse_b200 import plain
+    return plain._lib().ssb200_device_count()
+
+
+def _mesh_problem(ch, kind, N):
+    from suitesparse_b200 import gen, cholmod_host as H
+    A, p = gen.make_problem(kind, N)
+    S = ch.sparse(A, +1); L = ch.analyze(S, p)
+    f = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in ch.factor_arrays(L).items()}
+    S2 = ch.lower_permuted(S, L); s2 = S2.contents; n = s2.nrow
+    Ap = H._np_view(s2.p, n + 1, np.int64).copy(); Ai = H._np_view(s2.i, int(Ap[n]), np.int64).copy(); Ax = H._np_view(s2.x, int(Ap[n]), np.float64).copy()
+    ch.free_sparse(S2)
+    return A, f, sp.csc_matrix((Ax, Ai, Ap), shape=(n, n)), L
+
+
+@pytest.mark.parametrize("kind,N,tau", [("lap7", 24, "0"), ("lap27", 18, "0"), ("elas", 9, "0"), ("lap7", 40, None)])
+def test_multi_gpu_plain_layer_vs_oracle(kind, N, tau, monkeypatch):
+    """ssb200_mg_factorize / ssb200_mg_solve on all visible devices (>= 2): host factor equal to the oracle's, distributed
+    solve equal to the oracle's solve.  tau = "0" forces panel-cyclic sharing of the wide supernodes on these small meshes."""
+    nd = _ndev()
+    if nd < 2:
+        pytest.skip("needs two or more GPUs")
+    from suitesparse_b200 import cholmod_host as H, plain
+    from oracle import oracle
+    if tau is not None:
+        monkeypatch.setenv("SSB200_DIST_TAU", tau)
+    ch = H.Cholmod(gpu=True)
+    A, f, Sl, L = _mesh_problem(ch, kind, N)
+    n = f["n"]
+    mg = plain.MultiGpu(n, f["super"], f["pi"], f["px"], f["s"], ndev=min(nd, 8))
+    host = np.full(mg.xsize, np.nan)
+    st, minor = mg.factorize(Sl, Lx_host=host)                                  # pageable host buffer: copies at the end
+    assert (st, minor) == (0, n)
+    st_o, minor_o, Lo = oracle.factorize(n, f["super"], f["pi"], f["px"], f["s"], Sl)
+    assert persuper_relerr(f["px"], host, Lo) < TOL_L
+    rng = np.random.default_rng(42)
+    B = rng.standard_normal((n, 3))
+    Y = mg.solve(B, which=0)
+    Yo = oracle.lsolve(f["super"], f["pi"], f["px"], f["s"], Lo, B)
+    assert np.abs(Y - Yo).max() < 1e-10 * np.abs(Yo).max()
+    Z = mg.solve(B, which=2)
+    Zo = oracle.lsolve(f["super"], f["pi"], f["px"], f["s"], Lo, Yo, transpose=True)
+    assert np.abs(Z - Zo).max() < 1e-10 * np.abs(Zo).max()
+    assert np.abs(mg.solve(Y, which=1) - Z).max() < 1e-12 * np.abs(Z).max()
+    # refactorization into a page-locked host buffer (streamed by every device), reproducible to rounding
+    host2 = np.full(mg.xsize, np.nan)
+    mg.pin_host(host2)
+    st, minor = mg.factorize(Sl, Lx_host=host2)
+    assert st == 0 and persuper_relerr(f["px"], host2, Lo) < TOL_L
+    info = mg.info()
+    assert info["ndev"] == min(nd, 8) and info["nvlink_bytes"] > 0
+    # a factor computed elsewhere, uploaded in pieces: the solves work without the inverses of the diagonal blocks
+    mg.upload_L(Lo)
+    Z2 = mg.solve(B, which=2)
+    assert np.abs(Z2 - Zo).max() < 1e-10 * np.abs(Zo).max()
+    # not positive definite: status and column reported
+    Sbad = Sl.copy().tolil(); kbad = n // 2; Sbad[kbad, kbad] = -1.0; Sbad = Sbad.tocsc(); Sbad.sort_indices()
+    st, minor = mg.factorize(Sbad)
+    st_o, minor_o, _ = oracle.factorize(n, f["super"], f["pi"], f["px"], f["s"], Sbad)
+    assert st == 1 and minor == minor_o
+    mg.close(); ch.free_factor(L)
+
+
+def test_multi_gpu_dropin_symbols(monkeypatch):
+    """cholmod_l_factorize / cholmod_l_solve through the host library with SSB200_DEVICES=all: the interposed symbols fan
+    out over every device; a matrix that is not positive definite falls back to the single-GPU protocol."""
+    nd = _ndev()
+    if nd < 2:
+        pytest.skip("needs two or more GPUs")
+    from suitesparse_b200 import gen, cholmod_host as H, plain
+    from oracle import oracle
+    monkeypatch.setenv("SSB200_DEVICES", "all")
+    monkeypatch.setenv("SSB200_DIST_TAU", "0")
+    ch = H.Cholmod(gpu=True)
+    A, p = gen.make_problem("lap7", 30)
+    S = ch.sparse(A, +1); L = ch.analyze(S, p)
+    assert ch.factorize(S, L) == 1 and ch.cm.status == 0 and ch.cm.gpuNumKernelLaunches > 0
+    ch.b200.ssb200_mg_of_factor.restype = C.c_void_p; ch.b200.ssb200_mg_of_factor.argtypes = [C.c_void_p]
+    assert ch.b200.ssb200_mg_of_factor(L)                                        # the multi-GPU plan was used
+    f = ch.factor_arrays(L); n = f["n"]
+    S2 = ch.lower_permuted(S, L); s2 = S2.contents
+    Ap = H._np_view(s2.p, n + 1, np.int64); Ai = H._np_view(s2.i, int(Ap[n]), np.int64); Ax = H._np_view(s2.x, int(Ap[n]), np.float64)
+    Sl = sp.csc_matrix((Ax.copy(), Ai.copy(), Ap.copy()), shape=(n, n))
+    st, minor, Lo = oracle.factorize(n, f["super"], f["pi"], f["px"], f["s"], Sl)
+    assert persuper_relerr(f["px"], f["x"], Lo) < TOL_L
+    b = np.ones(n)
+    x = ch.solve(L, b)
+    Af = A + sp.triu(A, 1).T
+    assert np.linalg.norm(Af @ x - b) / np.linalg.norm(b) < TOL_RESID
+    # not positive definite through the same entry point
+    Ab = A.copy().tolil(); Ab[n // 3, n // 3] = -5.0; Ab = Ab.tocsc(); Ab.sort_indices()
+    Sb = ch.sparse(Ab, +1)
+    assert ch.factorize(Sb, L) == 1 and ch.cm.status == H.CHOLMOD_NOT_POSDEF
+    S2b = ch.lower_permuted(Sb, L); s2b = S2b.contents
+    Apb = H._np_view(s2b.p, n + 1, np.int64); Aib = H._np_view(s2b.i, int(Apb[n]), np.int64); Axb = H._np_view(s2b.x, int(Apb[n]), np.float64)
+    st_o, minor_o, Lob = oracle.factorize(n, f["super"], f["pi"], f["px"], f["s"], sp.csc_matrix((Axb, Aib, Apb), shape=(n, n)))
+    fb = ch.factor_arrays(L)
+    assert fb["minor"] == minor_o and persuper_relerr(f["px"], fb["x"], Lob) < TOL_L
+    ch.free_sparse(S2); ch.free_sparse(S2b); ch.free_factor(L)

@@ -91,3 +91,48 @@ def test_three_level_blocking_and_copy_cover_on_a_wide_supernode():
     wide = (nscol >= 33) & (nsrow > 32)
     assert int(out[18]) == int(np.ceil(nscol[wide] / 64).sum())
     ch.free_factor(L)
+
+
+@pytest.mark.parametrize("prefer", [0, 1])
+def test_lookahead_schedule_two_streams(prefer, monkeypatch):
+    """The single-GPU look-ahead schedule (outer panel O+1 factorized on the panel stream while the main stream applies
+    panel O to the rest): replayed on two emulated in-order streams with events, in both extreme interleavings, it must
+    give the oracle's factor; in list order (look-ahead off) as well."""
+    import scipy.sparse as sp
+    from conftest import REF_LIB, persuper_relerr
+    if not os.path.exists(REF_LIB):
+        pytest.skip("reference build (host libcholmod for cholmod_l_analyze) not present")
+    import emulate_plan as E
+    from suitesparse_b200 import gen
+    from suitesparse_b200.cholmod_host import Cholmod, _np_view
+    monkeypatch.setenv("SSB200_NB_OUTER", "256")          # three or more outer panels on a 24^3 mesh (root > 576 columns)
+    ch = Cholmod(gpu=False)
+    A, p = gen.make_problem("lap7", 24)
+    S = ch.sparse(A, +1); L = ch.analyze(S, p)
+    f = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in ch.factor_arrays(L).items()}
+    assert np.diff(f["super"]).max() > 3 * 256
+    S2 = ch.lower_permuted(S, L); s2 = S2.contents; n = s2.nrow
+    Ap = _np_view(s2.p, n + 1, np.int64).copy(); Ai = _np_view(s2.i, int(Ap[n]), np.int64).copy(); Ax = _np_view(s2.x, int(Ap[n]), np.float64).copy()
+    Sl = sp.csc_matrix((Ax, Ai, Ap), shape=(n, n))
+    st, minor, Lo = oracle.factorize(n, f["super"], f["pi"], f["px"], f["s"], Sl)
+    plan = E.export_plan(n, f["super"], f["pi"], f["px"], f["s"])
+    Ln = plan["launches"]
+    assert (Ln[:, 4] == 1).any() and (Ln[:, 0] == 5).any()           # a panel stream and its joins exist
+    # every event is recorded exactly once, before (in list order) the launch that waits for it
+    rec = {int(e): t for t, e in enumerate(Ln[:, 6]) if e >= 0}
+    assert len(rec) == (Ln[:, 6] >= 0).sum()
+    for t, e in enumerate(Ln[:, 5]):
+        if e >= 0:
+            assert rec[int(e)] < t
+    rel = E.relmap_of(plan, f["pi"], f["s"])
+    Lx = np.zeros(int(f["px"][-1]))
+    E.assemble(plan, f["super"], f["pi"], f["px"], f["s"], Sl, Lx)
+    reordered = E.run_two_streams(plan, rel, Lx, prefer)
+    assert persuper_relerr(f["px"], Lx, Lo) < 1e-11
+    if prefer == 1:
+        assert reordered > 0                                          # the panel chain really ran ahead of main-stream work
+    Lx2 = np.zeros(int(f["px"][-1]))
+    E.assemble(plan, f["super"], f["pi"], f["px"], f["s"], Sl, Lx2)
+    E.run_launches(plan, rel, Lx2, 0, len(Ln))
+    assert persuper_relerr(f["px"], Lx2, Lo) < 1e-11
+    ch.free_sparse(S2); ch.free_factor(L)
