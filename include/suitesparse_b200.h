@@ -227,6 +227,7 @@ int      ssb200_dist_flops(const ssb200_plan *plan, double *mine, double *total)
  * CHOLMOD's layout) receives every device's share over that device's own PCIe link while the factorization runs
  * (page-lock it once with ssb200_mg_pin_host).  A matrix that is not positive definite returns 1 with *minor_out set; the
  * partial refactorization of the failing supernode (t_cholmod_super_numeric.c:944-967) is then left to the single-GPU path. */
+/* Ap == NULL in ssb200_mg_factorize: factorize the matrix uploaded by the previous call again (resident refactorization). */
 typedef struct ssb200_mg ssb200_mg;
 ssb200_mg *ssb200_mg_create(ssb_long n, ssb_long nsuper, const ssb_long *super, const ssb_long *pi, const ssb_long *px,
                             const ssb_long *s, int ndev, const int *devices);
@@ -243,8 +244,12 @@ int  ssb200_mg_solve(ssb200_mg *mg, int which, double *X, ssb_long nrhs, ssb_lon
  * the inverses of the diagonal blocks) */
 int  ssb200_mg_upload_L(ssb200_mg *mg, const double *Lx_host);
 /* out[0] wall ms of the last factorization, out[1] of the last solve, out[2] NVLink bytes pulled per factorization,
- * out[3+r] HBM bytes held by rank r, out[3+N+r] dense flops of rank r; returns the number of devices. */
+ * out[3+r] HBM bytes held by rank r, out[3+N+r] dense flops of rank r, out[3+2N] device ms of the last factorization (CUDA
+ * events, max over the devices); returns the number of devices. */
 int  ssb200_mg_info(const ssb200_mg *mg, double *out, int cap);
+ssb_long ssb200_mg_launches(const ssb200_mg *mg);      /* kernels launched by the last call, all devices */
+/* tuning aid ($SSB200_MG_TRACE=1): device time at which every rank reached every step of the last factorization */
+ssb_long ssb200_mg_trace(const ssb200_mg *mg, float *out, ssb_long cap, ssb_long *steps, ssb_long steps_cap);
 
 /* Numeric factorization.  A (and F for stype==0) are HOST CSC arrays with 64-bit indices:
  * Ap[n+1], Ai, Ax and optional Anz (unpacked).  stype<0 symmetric-lower input, stype==0 A*F.

@@ -35,12 +35,20 @@ ms = []
 for _ in range(steps):
     t0 = time.perf_counter(); st, minor = mg.factorize(Sl, Lx_host=host); ms.append((time.perf_counter() - t0) * 1e3)
 info = mg.info()
+if os.environ.get("SSB200_MG_TRACE"):
+    tr, stp = mg.trace()
+    np.savez(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", f"mg_trace_{kind}{N}_n{ndev}.npz"), t=tr, steps=stp)
+    # compact summary: where the ranks are when the top phase starts, and the end
+    first_top = int(np.argmax(stp[:, 1] > 0))
+    print("trace: first top step", first_top, "reached at ms", [round(float(v), 1) for v in tr[:, first_top]], "end", [round(float(v), 1) for v in tr[:, -1]], flush=True)
 b = np.ones(n)
+y = mg.solve(b[f["Perm"]], which=2)
 t0 = time.perf_counter(); y = mg.solve(b[f["Perm"]], which=2); t_solve = (time.perf_counter() - t0) * 1e3
+info["ms_solve"] = mg.info()["ms_solve"]
 x = np.empty(n); x[f["Perm"]] = y
 Af = A + sp.triu(A, 1).T
 resid = float(np.linalg.norm(Af @ x - b) / np.linalg.norm(b))
-out = {"kind": kind, "N": N, "ndev": ndev, "host_copy": with_host, "ms_wall": [round(v, 1) for v in ms], "ms_internal": round(info["ms_factorize"], 1),
+out = {"kind": kind, "N": N, "ndev": ndev, "host_copy": with_host, "ms_wall": [round(v, 1) for v in ms], "ms_internal": round(info["ms_factorize"], 1), "ms_device": round(info["ms_device"], 1),
        "tflops": round(fl / min(ms) / 1e9, 2), "resid": resid, "solve_ms_wall": round(t_solve, 1), "solve_ms_internal": round(info["ms_solve"], 1),
        "nvlink_GB": round(info["nvlink_bytes"] / 1e9, 2), "device_GB": [round(v / 1e9, 1) for v in info["device_bytes"]],
        "flop_share": [round(v / sum(info["rank_flops"]), 3) for v in info["rank_flops"]], "xsize_GB": round(mg.xsize * 8 / 1e9, 1),

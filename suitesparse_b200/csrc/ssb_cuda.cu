@@ -262,7 +262,7 @@ static ssb200_plan *plan_create_impl(ssb_long n, ssb_long nsuper, const ssb_long
         if (cudaStreamCreateWithPriority(&p->panel_stream, cudaStreamNonBlocking, hi) != cudaSuccess) { set_error("cudaStreamCreateWithPriority failed"); plan_free(p); return nullptr; }
         p->panel_prio = hi;
         if (const char *e = getenv("SSB200_LOOKAHEAD")) p->lookahead = atoi(e) != 0;
-        if (nranks > 1) p->lookahead = false;            // the sharded path has its own look-ahead (DistStep)
+        if (nranks > 1 && !compact) p->lookahead = false;   // the multi-process sharded path drives the launches from outside, on one stream
     }
     if (plan_build_device(p) != 0) { plan_free(p); return nullptr; }
     return p;
@@ -620,6 +620,11 @@ static int enqueue_factorization(ssb200_plan *p, double beta0, double *Lx_host, 
     if (scatter_A(p, beta0, 0, hp.n)) return SSB_CHOLMOD_GPU_PROBLEM;
     if (!capture) cudaEventRecord(get_event(p, ev), p->stream);                   // 1: assembled
     ev++;
+    if (two_streams) {
+        // the panel stream never runs ahead of the assembly (its first launch may have no other event to wait for)
+        CU_TRY(cudaEventRecord(p->copy_gate, p->stream));
+        CU_TRY(cudaStreamWaitEvent(p->panel_stream, p->copy_gate, 0));
+    }
     size_t ctask = 0, cgroup = 0;
     bool copies_captured = false;
     for (int l = 0; l < hp.nlevels && l < stop_level; l++) {
@@ -943,7 +948,7 @@ extern "C" int ssb200_factor_diag(ssb200_plan *p, double *diag_host)
 extern "C" int ssb200_set_lookahead(ssb200_plan *p, int on)
 {
     if (!p) return SSB_CHOLMOD_INVALID;
-    p->lookahead = on != 0 && p->hp.nranks == 1;
+    p->lookahead = on != 0 && (p->hp.nranks == 1 || p->hp.compact);
     return 0;
 }
 
@@ -1034,7 +1039,10 @@ struct MgDev {
     std::vector<long long> chunk0; std::vector<int> nchunk;   // per step
     std::vector<cudaEvent_t> ev_solve;                    // per solve step (sync steps): this device's part of the step is done
     int rc = 0; std::string err; ssb_long bad = 0;
-    double ms = 0;
+    double ms = 0;                                        // device time of the last factorization (assembly .. last kernel / pull)
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;         // timing
+    std::vector<cudaEvent_t> ev_trace;                    // SSB200_MG_TRACE=1: one timing event per step on the compute stream
+    std::vector<float> trace_ms;                          // per step: device time from the start of the factorization
 };
 
 struct ssb200_mg {
@@ -1064,6 +1072,9 @@ static void mg_free(ssb200_mg *m)
         for (auto e : dv.ev_solve) if (e) cudaEventDestroy(e);
         if (dv.ev_begin) cudaEventDestroy(dv.ev_begin);
         if (dv.ev_done) cudaEventDestroy(dv.ev_done);
+        if (dv.ev_t0) cudaEventDestroy(dv.ev_t0);
+        if (dv.ev_t1) cudaEventDestroy(dv.ev_t1);
+        for (auto e : dv.ev_trace) if (e) cudaEventDestroy(e);
         if (dv.d_chunks) cudaFree(dv.d_chunks);
         if (dv.comm) cudaStreamDestroy(dv.comm);
         if (dv.d2h) cudaStreamDestroy(dv.d2h);
@@ -1140,7 +1151,8 @@ extern "C" ssb200_mg *ssb200_mg_create(ssb_long n, ssb_long nsuper, const ssb_lo
         cudaSetDevice(dv.device);
         int lo = 0, hi = 0; cudaDeviceGetStreamPriorityRange(&lo, &hi);
         if (cudaStreamCreateWithPriority(&dv.comm, cudaStreamNonBlocking, hi) != cudaSuccess || cudaStreamCreateWithFlags(&dv.d2h, cudaStreamNonBlocking) != cudaSuccess ||
-            cudaEventCreateWithFlags(&dv.ev_begin, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&dv.ev_done, cudaEventDisableTiming) != cudaSuccess) {
+            cudaEventCreateWithFlags(&dv.ev_begin, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&dv.ev_done, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreate(&dv.ev_t0) != cudaSuccess || cudaEventCreate(&dv.ev_t1) != cudaSuccess) {
             set_error("stream/event creation failed"); mg_free(m); return nullptr; }
         dv.ev_arrived.assign(ns, nullptr); dv.chunk0.assign(ns, 0); dv.nchunk.assign(ns, 0);
         dv.ev_solve.assign(nsolve, nullptr);
@@ -1215,9 +1227,16 @@ extern "C" int ssb200_mg_factorize(ssb200_mg *m, int stype, const ssb_long *Ap, 
         auto fail = [&](const std::string &msg) { dv.rc = SSB_CHOLMOD_GPU_PROBLEM; dv.err = msg; abort_flag.store(1); };
 #define MG_TRY(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { fail(std::string(#expr) + ": " + cudaGetErrorString(_e)); return; } } while (0)
         MG_TRY(cudaSetDevice(dv.device));
-        if (ssb200_upload_A(p, stype, Ap, Ai, Anz, Ax, ncolA, Fp, Fi, Fnz, Fx)) { fail(g_last_error); return; }
+        if (Ap) { if (ssb200_upload_A(p, stype, Ap, Ai, Anz, Ax, ncolA, Fp, Fi, Fnz, Fx)) { fail(g_last_error); return; } }
+        else if (!p->haveA) { fail("no matrix on the devices yet"); return; }      // Ap == NULL: the matrix of the previous call
         p->stats.kernel_launches = 0; p->factor_on_device = false;
         if (hp.nsuper == 0) return;
+        static int trace = -1;
+        if (trace < 0) { const char *v = getenv("SSB200_MG_TRACE"); trace = (v && atoi(v)) ? 1 : 0; }
+        if (trace) while (dv.ev_trace.size() < ns + 1) { cudaEvent_t e; MG_TRY(cudaEventCreate(&e)); dv.ev_trace.push_back(e); }
+        const bool two = p->lookahead && hp.n_events > 0;
+        while ((int) p->la_events.size() < hp.n_events) { cudaEvent_t e; MG_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); p->la_events.push_back(e); }
+        MG_TRY(cudaEventRecord(dv.ev_t0, p->stream));
         // zero the local storage, assemble the columns this rank computes
         for (size_t off = 0, tot = (size_t) p->lx_alloc * sizeof(double); off < tot; off += (size_t) 1 << 30)
             MG_TRY(cudaMemsetAsync((char *) p->d_Lx + off, 0, std::min<size_t>((size_t) 1 << 30, tot - off), p->stream));
@@ -1227,15 +1246,17 @@ extern "C" int ssb200_mg_factorize(ssb200_mg *m, int stype, const ssb_long *Ap, 
         if (scatter_A(p, beta0, 0, hp.n, false)) { fail(g_last_error); return; }
         MG_TRY(cudaEventRecord(dv.ev_begin, p->stream));
         MG_TRY(cudaStreamWaitEvent(dv.comm, dv.ev_begin, 0));
+        if (two) MG_TRY(cudaStreamWaitEvent(p->panel_stream, dv.ev_begin, 0));
         std::vector<cudaEvent_t> outstanding;
         for (size_t k = 0; k < ns; k++) {
             if (abort_flag.load()) return;
             const DistStep &st = hp.steps[k];
+            if (trace) MG_TRY(cudaEventRecord(dv.ev_trace[k], p->stream));
             if (st.wait_remote && !outstanding.empty()) {
                 for (cudaEvent_t e : outstanding) MG_TRY(cudaStreamWaitEvent(p->stream, e, 0));
                 outstanding.clear();
             }
-            for (int t = st.launch_begin; t < st.launch_mid; t++) if (run_launch(p, hp.launches[t], p->jobs)) { fail(g_last_error); return; }
+            for (int t = st.launch_begin; t < st.launch_mid; t++) if (run_launch(p, hp.launches[t], p->jobs, two)) { fail(g_last_error); return; }
             if (st.bcast_src == r) {
                 MG_TRY(cudaEventRecord(m->ev_ready[k], p->stream));
                 m->ready_epoch[k].store(epoch, std::memory_order_release);
@@ -1249,29 +1270,59 @@ extern "C" int ssb200_mg_factorize(ssb200_mg *m, int stype, const ssb_long *Ap, 
                 mg_spin_until(m->ready_epoch[k], epoch, abort_flag);
                 if (abort_flag.load()) return;
                 MG_TRY(cudaStreamWaitEvent(dv.comm, m->ev_ready[k], 0));
+                // A finished panel goes to everybody: binomial relay instead of N-1 pulls from one source.  The receivers are
+                // ordered starting with the owner of the NEXT panel (the critical path); receiver q (0-based) pulls from holder
+                // (q+1) - 2^floor(log2(q+1)), where holder 0 is the source and holder i the receiver i-1: after round j, 2^j devices
+                // hold the panel and every NVLink port carries one copy at a time.
                 const int nxt = hp.step_next[k];
-                if (nxt >= 0 && nxt != r) {
-                    // the owner of the next panel pulls first: it is the one on the critical path
-                    mg_spin_until(m->arrived_epoch[(size_t) nxt * ns + k], epoch, abort_flag);
-                    if (abort_flag.load()) return;
-                    MG_TRY(cudaStreamWaitEvent(dv.comm, m->d[nxt].ev_arrived[k], 0));
+                int from = st.bcast_src;
+                if (nxt >= 0 && N > 2) {
+                    const int q = ((r - nxt) % N + N) % N - (((st.bcast_src - nxt) % N + N) % N < ((r - nxt) % N + N) % N ? 1 : 0);   // position among the receivers
+                    int pw = 1; while (2 * pw <= q + 1) pw *= 2;
+                    const int holder = (q + 1) - pw;                            // 0 = source, i = receiver at position i-1
+                    if (holder > 0) {
+                        int pos = holder - 1, cand = nxt;                       // walk to the receiver at position `pos`
+                        for (int seen = 0;; cand = (cand + 1) % N) { if (cand == st.bcast_src) continue; if (seen == pos) break; seen++; }
+                        from = cand;
+                        mg_spin_until(m->arrived_epoch[(size_t) from * ns + k], epoch, abort_flag);
+                        if (abort_flag.load()) return;
+                        MG_TRY(cudaStreamWaitEvent(dv.comm, m->d[from].ev_arrived[k], 0));
+                    }
                 }
-                const int grid = std::min(dv.nchunk[k], 148 * 4);
-                mg_pull_kernel<<<grid, MG_THREADS, 0, dv.comm>>>(dv.d_chunks + dv.chunk0[k], dv.nchunk[k], m->d[st.bcast_src].plan->d_Lx, p->d_Lx);
-                p->stats.kernel_launches++;
+                const double *src_Lx = m->d[from].plan->d_Lx;
+                if (hp.step_recv[k].size() <= 4) {
+                    // a few large contiguous pieces (a panel, a whole supernode): the copy engines move them, no SM is taken
+                    const HostPlan &sp = m->d[from].plan->hp;
+                    for (const HostPlan::Piece &pc : hp.step_recv[k]) {
+                        const int t0 = (int) (std::upper_bound(hp.px.begin(), hp.px.end(), pc.home_off) - hp.px.begin()) - 1;
+                        MG_TRY(cudaMemcpyPeerAsync(p->d_Lx + hp.lpx[t0] + (pc.home_off - hp.px[t0]), dv.device,
+                                                   src_Lx + sp.lpx[t0] + (pc.home_off - hp.px[t0]), m->d[from].device, (size_t) pc.cnt * sizeof(double), dv.comm));
+                    }
+                } else {
+                    // thousands of scattered supernodes of a finished subtree: one gather kernel on peer pointers
+                    static int pull_ctas = -1;
+                    if (pull_ctas < 0) { const char *v = getenv("SSB200_MG_PULL_CTAS"); pull_ctas = v ? std::max(1, atoi(v)) : 64; }
+                    const int grid = std::min(dv.nchunk[k], pull_ctas);
+                    mg_pull_kernel<<<grid, MG_THREADS, 0, dv.comm>>>(dv.d_chunks + dv.chunk0[k], dv.nchunk[k], src_Lx, p->d_Lx);
+                    p->stats.kernel_launches++;
+                }
                 MG_TRY(cudaEventRecord(dv.ev_arrived[k], dv.comm));
                 m->arrived_epoch[(size_t) r * ns + k].store(epoch, std::memory_order_release);
                 outstanding.push_back(dv.ev_arrived[k]);
             }
-            for (int t = st.launch_mid; t < st.launch_end; t++) if (run_launch(p, hp.launches[t], p->jobs)) { fail(g_last_error); return; }
+            for (int t = st.launch_mid; t < st.launch_end; t++) if (run_launch(p, hp.launches[t], p->jobs, two)) { fail(g_last_error); return; }
         }
         for (cudaEvent_t e : outstanding) MG_TRY(cudaStreamWaitEvent(p->stream, e, 0));
+        if (trace) MG_TRY(cudaEventRecord(dv.ev_trace[ns], p->stream));
+        MG_TRY(cudaEventRecord(dv.ev_t1, p->stream));
         MG_TRY(cudaMemcpyAsync(p->h_info, p->d_info, hp.nsuper * sizeof(int), cudaMemcpyDeviceToHost, p->stream));
         MG_TRY(cudaStreamSynchronize(p->stream));
         MG_TRY(cudaStreamSynchronize(dv.comm));
         MG_TRY(cudaStreamSynchronize(dv.d2h));
         MG_TRY(cudaGetLastError());
         for (long long sn = 0; sn < hp.nsuper; sn++) if (p->h_info[sn] != INT_MAX) { dv.bad = hp.super[sn] + p->h_info[sn] - 1; break; }
+        { float f = 0; cudaEventElapsedTime(&f, dv.ev_t0, dv.ev_t1); dv.ms = f; }
+        if (trace) { dv.trace_ms.assign(ns + 1, 0.f); for (size_t k = 0; k <= ns; k++) cudaEventElapsedTime(&dv.trace_ms[k], dv.ev_t0, dv.ev_trace[k]); }
         p->stats.kernel_launches_total += p->stats.kernel_launches;
         p->factor_on_device = true; p->winv_valid = true;      // the inverses of the blocks THIS rank factorized (what its solve jobs use)
 #undef MG_TRY
@@ -1417,10 +1468,37 @@ extern "C" int ssb200_mg_upload_L(ssb200_mg *m, const double *Lx_host)
 // out[0] = wall ms of the last factorization (threads started -> all devices idle), out[1] = last solve ms,
 // out[2] = bytes pulled over NVLink per factorization (all ranks), out[3 + r] = HBM bytes held by rank r,
 // out[3 + N + r] = dense flops executed by rank r
+// SSB200_MG_TRACE=1: per step k and rank r, device time (ms since the start) at which the rank's compute stream reached the
+// step; out[r * (nsteps + 1) + k], last entry = end.  Also the step table: steps[k*4] = src, level-ish wait flag, cnt, launches.
+extern "C" ssb_long ssb200_mg_trace(const ssb200_mg *m, float *out, ssb_long cap, ssb_long *steps, ssb_long steps_cap)
+{
+    if (!m) return -1;
+    const ssb_long ns = (ssb_long) m->d[0].plan->hp.steps.size();
+    if (out && cap >= (ns + 1) * m->N)
+        for (int r = 0; r < m->N; r++)
+            for (ssb_long k = 0; k <= ns; k++) out[r * (ns + 1) + k] = k < (ssb_long) m->d[r].trace_ms.size() ? m->d[r].trace_ms[k] : 0.f;
+    if (steps && steps_cap >= ns * 4)
+        for (ssb_long k = 0; k < ns; k++) {
+            const DistStep &st = m->d[0].plan->hp.steps[k];
+            steps[4 * k] = st.bcast_src; steps[4 * k + 1] = st.wait_remote; steps[4 * k + 2] = st.cnt; steps[4 * k + 3] = m->d[0].plan->hp.step_next.empty() ? -1 : m->d[0].plan->hp.step_next[k];
+        }
+    return ns;
+}
+
+// kernels launched by the last call, all devices
+extern "C" ssb_long ssb200_mg_launches(const ssb200_mg *m)
+{
+    if (!m) return 0;
+    ssb_long t = 0;
+    for (const auto &dv : m->d) t += dv.plan->stats.kernel_launches;
+    return t;
+}
+
 extern "C" int ssb200_mg_info(const ssb200_mg *m, double *out, int cap)
 {
     if (!m || !out || cap < 3 + 2 * m->N) return SSB_CHOLMOD_INVALID;
     out[0] = m->last_ms; out[1] = m->last_solve_ms; out[2] = (double) m->pulled_bytes;
+    if (cap >= 4 + 2 * m->N) { double mx = 0; for (const auto &dv : m->d) mx = std::max(mx, dv.ms); out[3 + 2 * m->N] = mx; }
     for (int r = 0; r < m->N; r++) { out[3 + r] = (double) m->d[r].plan->device_bytes; out[3 + m->N + r] = m->d[r].plan->hp.my_flops; }
     return m->N;
 }

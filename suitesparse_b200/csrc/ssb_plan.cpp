@@ -510,7 +510,7 @@ bool build_host_plan(long long n, long long nsuper, const long long *super, cons
             // single GPU: look-ahead inside the level's supernodes; the panel stream first waits for the level's descendant
             // updates (everything launched so far on the main stream)
             int after_ev = -1;
-            const bool la = hp.nranks == 1 && lookahead_enabled;
+            const bool la = (hp.nranks == 1 || hp.compact) && lookahead_enabled;      // also inside a rank of the in-process multi-GPU path
             if (la && !hp.launches.empty()) {
                 int maxcol = 0;
                 for (int sn : nodes) maxcol = std::max(maxcol, hp.super[sn + 1] - hp.super[sn]);

@@ -203,6 +203,17 @@ class MultiGpu:
                                               b, _ptr(Lx_host), C.byref(minor))
         return self._check(st), minor.value
 
+    def factorize_resident(self, beta: float = 0.0):
+        """The matrix uploaded by the previous factorize() call, no host copy of L."""
+        b = (C.c_double * 2)(beta, 0.0)
+        minor = c_long(0)
+        st = self.lib.ssb200_mg_factorize(self.h, -1, None, None, None, None, 0, None, None, None, None, b, None, C.byref(minor))
+        return self._check(st), minor.value
+
+    def launches(self) -> int:
+        self.lib.ssb200_mg_launches.restype = c_long; self.lib.ssb200_mg_launches.argtypes = [C.c_void_p]
+        return int(self.lib.ssb200_mg_launches(self.h))
+
     def solve(self, X: np.ndarray, which: int = 2) -> np.ndarray:
         X = np.array(X, dtype=np.float64, order="F", copy=True)
         X2 = X.reshape(X.shape[0], -1, order="F")
@@ -215,7 +226,19 @@ class MultiGpu:
     def info(self) -> dict:
         out = np.zeros(3 + 2 * 16)
         N = self.lib.ssb200_mg_info(self.h, _ptr(out), out.size)
-        return dict(ndev=N, ms_factorize=out[0], ms_solve=out[1], nvlink_bytes=out[2], device_bytes=out[3:3 + N].tolist(), rank_flops=out[3 + N:3 + 2 * N].tolist())
+        return dict(ndev=N, ms_factorize=out[0], ms_solve=out[1], nvlink_bytes=out[2], device_bytes=out[3:3 + N].tolist(),
+                    rank_flops=out[3 + N:3 + 2 * N].tolist(), ms_device=out[3 + 2 * N])
+
+    def trace(self):
+        """(times[ndev, nsteps+1] in ms, steps[nsteps, 4] = src, wait_remote, cnt, next_owner); needs SSB200_MG_TRACE=1."""
+        L = self.lib
+        L.ssb200_mg_trace.restype = c_long
+        L.ssb200_mg_trace.argtypes = [C.c_void_p, C.c_void_p, c_long, C.c_void_p, c_long]
+        ns = L.ssb200_mg_trace(self.h, None, 0, None, 0)
+        N = self.info()["ndev"]
+        t = np.zeros((N, ns + 1), dtype=np.float32); st = np.zeros((ns, 4), dtype=np.int64)
+        L.ssb200_mg_trace(self.h, _ptr(t), t.size, _ptr(st), st.size)
+        return t, st
 
     def close(self):
         if self.h and self.owned:
