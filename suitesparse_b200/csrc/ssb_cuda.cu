@@ -94,6 +94,9 @@ struct ssb200_plan {
     double *d_probe = nullptr;               // 8-byte scratch of the host-registration probe
     DevJobs jobs;
     SolveJob *d_solve_jobs = nullptr; int *d_solve_tiles = nullptr;
+    // second solve schedule (256-column blocks of the wide supernodes; needs the inverses of the diagonal blocks)
+    SolveJob *d_solve2_jobs = nullptr; int *d_solve2_tiles = nullptr; SolveBlk *d_solve_blks = nullptr; int *d_solve_blk_ctas = nullptr;
+    double *d_sol_scratch = nullptr; int *d_sol_flags = nullptr; long long sol_nrhs_cap = 0;
     int *h_info = nullptr;                 // pinned
     // matrix on the device
     struct CscBuf *bufA = nullptr, *bufF = nullptr;
@@ -104,7 +107,7 @@ struct ssb200_plan {
     double last_beta0 = 0.0;               // beta of the running sharded factorization (not-positive-definite repeat)
     bool winv_valid = false;               // d_winv matches d_Lx (false after ssb200_upload_L or a sharded factorization)
     // the whole solve sequence is replayed as one CUDA graph (thousands of tiny dependent kernels)
-    cudaGraphExec_t solve_graph = nullptr; double *sg_X = nullptr; long long sg_nrhs = 0, sg_ldx = 0; int sg_which = -1; bool sg_winv = false;
+    cudaGraphExec_t solve_graph = nullptr; double *sg_X = nullptr; long long sg_nrhs = 0, sg_ldx = 0, sg_launches = 0; int sg_which = -1; bool sg_winv = false;
     std::vector<cudaEvent_t> events;
     ssb200_stats stats{};
     std::vector<float> launch_ms;          // device time of every launch of the last factorize (debug / tuning)
@@ -137,6 +140,10 @@ static int configure_kernels_once()
     if (e5 != cudaSuccess) e1 = e5;
     cudaError_t e4 = cudaFuncSetAttribute(trsm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) trsm_tc_smem_bytes());
     if (e4 != cudaSuccess) e1 = e4;
+    cudaError_t e6 = cudaFuncSetAttribute(solve_blk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) solve_blk_smem_bytes());
+    cudaError_t e7 = cudaFuncSetAttribute(solve_blk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) solve_blk_smem_bytes());
+    if (e6 != cudaSuccess) e1 = e6;
+    if (e7 != cudaSuccess) e1 = e7;
     if (e1 != cudaSuccess || e2 != cudaSuccess) { set_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : e2)); return SSB_CHOLMOD_GPU_PROBLEM; }
     return 0;
 }
@@ -151,6 +158,7 @@ static void plan_free(ssb200_plan *p)
     cudaSetDevice(p->device);
     void *ptrs[] = {p->d_probe, p->d_owner, p->d_super, p->d_ls, p->d_supermap, p->d_relmap, p->d_info, p->d_pi, p->d_px, p->d_Lx, p->d_winv, p->jobs.gemm_jobs,
                     p->jobs.gemm_tiles, p->jobs.potrf_jobs, p->jobs.trsm_jobs, p->jobs.trsm_tiles, p->d_solve_jobs, p->d_solve_tiles,
+                    p->d_solve2_jobs, p->d_solve2_tiles, p->d_solve_blks, p->d_solve_blk_ctas, p->d_sol_scratch, p->d_sol_flags,
                     p->d_X};
     for (void *q : ptrs) if (q) cudaFree(q);
     free_cscbuf(p->bufA); free_cscbuf(p->bufF);
@@ -199,6 +207,11 @@ static int plan_build_device(ssb200_plan *p)
     if (upload_jobs(p, hp, p->jobs)) return SSB_CHOLMOD_GPU_PROBLEM;
     if (dev_alloc_copy(p, &p->d_solve_jobs, hp.solve_jobs)) return SSB_CHOLMOD_GPU_PROBLEM;
     if (dev_alloc_copy(p, &p->d_solve_tiles, hp.solve_tiles)) return SSB_CHOLMOD_GPU_PROBLEM;
+    if (dev_alloc_copy(p, &p->d_solve2_jobs, hp.solve2_jobs)) return SSB_CHOLMOD_GPU_PROBLEM;
+    if (dev_alloc_copy(p, &p->d_solve2_tiles, hp.solve2_tiles)) return SSB_CHOLMOD_GPU_PROBLEM;
+    if (dev_alloc_copy(p, &p->d_solve_blks, hp.solve_blks)) return SSB_CHOLMOD_GPU_PROBLEM;
+    if (dev_alloc_copy(p, &p->d_solve_blk_ctas, hp.solve_blk_ctas)) return SSB_CHOLMOD_GPU_PROBLEM;
+    { const size_t fb = std::max<size_t>(hp.solve_blks.size(), 1) * sizeof(int); CU_TRY(cudaMalloc((void **) &p->d_sol_flags, fb)); p->device_bytes += fb; }
     p->lx_alloc = hp.compact ? hp.lxsize : hp.xsize;
     const size_t xbytes = std::max<long long>(p->lx_alloc, 1) * sizeof(double);
     CU_TRY(cudaMalloc((void **) &p->d_Lx, xbytes)); p->device_bytes += xbytes;
@@ -848,6 +861,69 @@ extern "C" int ssb200_factorize(ssb200_plan *p, int stype, const ssb_long *Ap, c
 // ---------------------------------------------------------------------------------------------------------------
 // solves
 // ---------------------------------------------------------------------------------------------------------------
+// Which solve schedule.  Default: 64-column steps (diag + update kernel per step).  SSB200_SOLVE_BLK=1 selects the second
+// schedule, where the big supernodes are solved in fused 256-column block steps (solve_blk_kernel; needs the inverses of
+// the diagonal blocks, i.e. a factor computed by this library).  Measured on B200 at lap7 128^3: 32.1-35.3 ms against
+// 31.6 ms for the default - the diagonal CTA's dependent load batches cost more than the launches they save - so it stays
+// an experiment.
+static bool use_blk_schedule(const ssb200_plan *p)
+{
+    static int on = -1;
+    if (on < 0) { const char *v = getenv("SSB200_SOLVE_BLK"); on = (v && atoi(v) != 0) ? 1 : 0; }
+    return on && p->winv_valid;
+}
+static const std::vector<SolveStep> &solve_schedule(const ssb200_plan *p, bool blk) { return blk ? p->hp.solve2_steps : p->hp.solve_steps; }
+
+// scratch of the block schedule (256 doubles per job and right-hand side) and its reset before a pass
+static int solve_blk_prepare(ssb200_plan *p, long long nrhs)
+{
+    const size_t nb = p->hp.solve_blks.size();
+    if (nb == 0) return 0;
+    if (nrhs > p->sol_nrhs_cap) {
+        if (p->d_sol_scratch) { cudaFree(p->d_sol_scratch); p->d_sol_scratch = nullptr; }
+        CU_TRY(cudaMalloc((void **) &p->d_sol_scratch, nb * SB_W * nrhs * sizeof(double)));
+        p->sol_nrhs_cap = nrhs;
+    }
+    return 0;
+}
+static int solve_blk_reset(ssb200_plan *p, long long nrhs)
+{
+    const size_t nb = p->hp.solve_blks.size();
+    if (nb == 0) return 0;
+    CU_TRY(cudaMemsetAsync(p->d_sol_flags, 0, nb * sizeof(int), p->stream));
+    CU_TRY(cudaMemsetAsync(p->d_sol_scratch, 0, nb * SB_W * nrhs * sizeof(double), p->stream));
+    return 0;
+}
+
+// the kernels of one step of a pass (dir > 0: forward, L; dir < 0: backward, L'); returns the number of launches or < 0
+static int enqueue_solve_step(ssb200_plan *p, const SolveStep &st, bool blk, int dir, double *dX, int nrhs, long long ldx)
+{
+    const SolveJob *jobs = (blk ? p->d_solve2_jobs : p->d_solve_jobs) + st.job0;
+    const int *tiles = (blk ? p->d_solve2_tiles : p->d_solve_tiles) + st.tile0;
+    const double *winv = p->winv_valid ? p->d_winv : nullptr;
+    int n = 0;
+    if (dir > 0) {
+        if (st.njobs > 0) {
+            lsolve_diag_kernel<<<st.njobs, SOLVE_THREADS, 0, p->stream>>>(jobs, p->d_Lx, winv, dX, nrhs, ldx); n++;
+            if (st.ntiles > 0) { lsolve_update_kernel<<<st.ntiles, SOLVE_THREADS, 0, p->stream>>>(jobs, tiles, p->d_Lx, p->d_ls, dX, nrhs, ldx); n++; }
+        }
+        if (blk && st.nblk > 0) {
+            solve_blk_kernel<true><<<st.nctas + st.nblk, SB_THREADS, solve_blk_smem_bytes(), p->stream>>>(p->d_solve_blks + st.blk0, p->d_solve_blk_ctas + st.cta0, p->d_Lx, p->d_ls,
+                                                                                                p->d_winv, dX, nrhs, ldx, p->d_sol_scratch, p->d_sol_flags); n++;
+        }
+    } else {
+        if (blk && st.nblk > 0) {
+            solve_blk_kernel<false><<<st.nctas + st.nblk, SB_THREADS, solve_blk_smem_bytes(), p->stream>>>(p->d_solve_blks + st.blk0, p->d_solve_blk_ctas + st.cta0, p->d_Lx, p->d_ls,
+                                                                                                 p->d_winv, dX, nrhs, ldx, p->d_sol_scratch, p->d_sol_flags); n++;
+        }
+        if (st.njobs > 0) {
+            if (st.ntiles > 0) { ltsolve_update_kernel<<<st.ntiles, SOLVE_THREADS, 0, p->stream>>>(jobs, tiles, p->d_Lx, p->d_ls, dX, nrhs, ldx); n++; }
+            ltsolve_diag_kernel<<<st.njobs, SOLVE_THREADS, 0, p->stream>>>(jobs, p->d_Lx, winv, dX, nrhs, ldx); n++;
+        }
+    }
+    return n;
+}
+
 extern "C" int ssb200_solve_resident(ssb200_plan *p, int which, double *dX, ssb_long nrhs, ssb_long ldx)
 {
     if (!p || (!dX && p->hp.n > 0 && nrhs > 0)) { set_error("null argument"); return SSB_CHOLMOD_INVALID; }
@@ -856,48 +932,40 @@ extern "C" int ssb200_solve_resident(ssb200_plan *p, int which, double *dX, ssb_
     CU_TRY(cudaSetDevice(p->device));
     p->stats.kernel_launches = 0;
     if (p->hp.n == 0 || nrhs == 0) return 0;
-    const HostPlan &hp = p->hp;
     cudaEvent_t e0 = get_event(p, 0), e1 = get_event(p, 1);
-    const int nsteps = (int) hp.solve_steps.size();
+    const bool blk = use_blk_schedule(p);
+    const std::vector<SolveStep> &steps = solve_schedule(p, blk);
+    const int nsteps = (int) steps.size();
+    if (blk && solve_blk_prepare(p, nrhs)) return SSB_CHOLMOD_GPU_PROBLEM;
     static int use_graph = -1;
     if (use_graph < 0) { const char *v = getenv("SSB200_SOLVE_GRAPH"); use_graph = (v && atoi(v) == 0) ? 0 : 1; }
     const bool cached = use_graph && p->solve_graph && p->sg_X == dX && p->sg_nrhs == nrhs && p->sg_ldx == ldx && p->sg_which == which && p->sg_winv == p->winv_valid;
+    long long launches = 0;
     if (!cached) {
         if (use_graph) {
             if (p->solve_graph) { cudaGraphExecDestroy(p->solve_graph); p->solve_graph = nullptr; }
             CU_TRY(cudaStreamBeginCapture(p->stream, cudaStreamCaptureModeThreadLocal));
         } else cudaEventRecord(e0, p->stream);
+        int rc = 0;
         if (which == 0 || which == 2) {
-            for (int t = 0; t < nsteps; t++) {
-                const SolveStep &st = hp.solve_steps[t];
-                lsolve_diag_kernel<<<st.njobs, SOLVE_THREADS, 0, p->stream>>>(p->d_solve_jobs + st.job0, p->d_Lx, p->winv_valid ? p->d_winv : nullptr, dX, (int) nrhs, ldx);
-                if (st.ntiles > 0)
-                    lsolve_update_kernel<<<st.ntiles, SOLVE_THREADS, 0, p->stream>>>(p->d_solve_jobs + st.job0, p->d_solve_tiles + st.tile0, p->d_Lx, p->d_ls, dX, (int) nrhs, ldx);
-            }
+            if (blk) rc |= solve_blk_reset(p, nrhs);
+            for (int t = 0; t < nsteps && !rc; t++) { const int n = enqueue_solve_step(p, steps[t], blk, +1, dX, (int) nrhs, ldx); if (n < 0) rc = 1; else launches += n; }
         }
         if (which == 1 || which == 2) {
-            for (int t = nsteps - 1; t >= 0; t--) {
-                const SolveStep &st = hp.solve_steps[t];
-                if (st.ntiles > 0)
-                    ltsolve_update_kernel<<<st.ntiles, SOLVE_THREADS, 0, p->stream>>>(p->d_solve_jobs + st.job0, p->d_solve_tiles + st.tile0, p->d_Lx, p->d_ls, dX, (int) nrhs, ldx);
-                ltsolve_diag_kernel<<<st.njobs, SOLVE_THREADS, 0, p->stream>>>(p->d_solve_jobs + st.job0, p->d_Lx, p->winv_valid ? p->d_winv : nullptr, dX, (int) nrhs, ldx);
-            }
+            if (blk) rc |= solve_blk_reset(p, nrhs);
+            for (int t = nsteps - 1; t >= 0 && !rc; t--) { const int n = enqueue_solve_step(p, steps[t], blk, -1, dX, (int) nrhs, ldx); if (n < 0) rc = 1; else launches += n; }
         }
         if (use_graph) {
             cudaGraph_t g = nullptr;
-            CU_TRY(cudaStreamEndCapture(p->stream, &g));
+            cudaError_t ce = cudaStreamEndCapture(p->stream, &g);
+            if (rc || ce != cudaSuccess) { if (g) cudaGraphDestroy(g); (void) cudaGetLastError(); set_error("solve graph capture failed"); return SSB_CHOLMOD_GPU_PROBLEM; }
             cudaError_t ie = cudaGraphInstantiate(&p->solve_graph, g, 0);
             cudaGraphDestroy(g);
             if (ie != cudaSuccess) { p->solve_graph = nullptr; set_error(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ie)); return SSB_CHOLMOD_GPU_PROBLEM; }
-            p->sg_X = dX; p->sg_nrhs = nrhs; p->sg_ldx = ldx; p->sg_which = which; p->sg_winv = p->winv_valid;
-        }
+            p->sg_X = dX; p->sg_nrhs = nrhs; p->sg_ldx = ldx; p->sg_which = which; p->sg_winv = p->winv_valid; p->sg_launches = launches;
+        } else if (rc) return SSB_CHOLMOD_GPU_PROBLEM;
     }
-    // launches of one solve: a diag kernel per step and an update kernel per step that has rows below, per direction
-    {
-        long long per_dir = 0;
-        for (const SolveStep &st : hp.solve_steps) per_dir += 1 + (st.ntiles > 0 ? 1 : 0);
-        p->stats.kernel_launches = per_dir * (which == 2 ? 2 : 1);
-    }
+    p->stats.kernel_launches = use_graph ? p->sg_launches : launches;
     if (use_graph) {
         cudaEventRecord(e0, p->stream);
         CU_TRY(cudaGraphLaunch(p->solve_graph, p->stream));
@@ -1052,7 +1120,8 @@ struct ssb200_mg {
     std::vector<cudaEvent_t> ev_ready;                    // per step: the step's range is final on its source device
     std::vector<std::atomic<long long>> ready_epoch;      // host hand-shake: ev_ready[k] has been recorded in this epoch
     std::vector<std::atomic<long long>> arrived_epoch;    // [r * nsteps + k]
-    std::vector<std::atomic<long long>> solve_epoch;      // [r * nsolve + t]
+    std::vector<std::atomic<long long>> solve_epoch;      // [r * solve_stride + t]
+    long long solve_stride = 0;
     long long epoch = 0;
     double *d_X = nullptr; size_t capX = 0;               // right-hand sides, on device 0 (peers reach it over NVLink)
     cudaEvent_t ev_x = nullptr;
@@ -1136,7 +1205,8 @@ extern "C" ssb200_mg *ssb200_mg_create(ssb_long n, ssb_long nsuper, const ssb_lo
     m->arrived_epoch = std::vector<std::atomic<long long>>(ns * ndev);
     for (auto &a : m->ready_epoch) a.store(0);
     for (auto &a : m->arrived_epoch) a.store(0);
-    const size_t nsolve = m->d[0].plan->hp.solve_steps.size();
+    const size_t nsolve = std::max(m->d[0].plan->hp.solve_steps.size(), m->d[0].plan->hp.solve2_steps.size());
+    m->solve_stride = (long long) nsolve;
     m->solve_epoch = std::vector<std::atomic<long long>>(nsolve * ndev);
     for (auto &a : m->solve_epoch) a.store(0);
     for (size_t k = 0; k < ns; k++) {
@@ -1156,7 +1226,7 @@ extern "C" ssb200_mg *ssb200_mg_create(ssb_long n, ssb_long nsuper, const ssb_lo
             set_error("stream/event creation failed"); mg_free(m); return nullptr; }
         dv.ev_arrived.assign(ns, nullptr); dv.chunk0.assign(ns, 0); dv.nchunk.assign(ns, 0);
         dv.ev_solve.assign(nsolve, nullptr);
-        for (size_t t = 0; t < nsolve; t++) if (hp.solve_steps[t].njobs > 0) cudaEventCreateWithFlags(&dv.ev_solve[t], cudaEventDisableTiming);
+        for (size_t t = 0; t < nsolve; t++) cudaEventCreateWithFlags(&dv.ev_solve[t], cudaEventDisableTiming);
         std::vector<MgPiece> chunks;
         for (size_t k = 0; k < ns; k++) {
             if (hp.step_recv[k].empty()) continue;
@@ -1375,52 +1445,47 @@ extern "C" int ssb200_mg_solve(ssb200_mg *m, int which, double *X, ssb_long nrhs
     if ((size_t) n * nrhs > m->capX) { if (m->d_X) cudaFree(m->d_X); m->d_X = nullptr; m->capX = (size_t) n * nrhs; CU_TRY(cudaMalloc((void **) &m->d_X, m->capX * sizeof(double))); }
     CU_TRY(cudaMemcpy2DAsync(m->d_X, n * sizeof(double), X, ldx * sizeof(double), n * sizeof(double), nrhs, cudaMemcpyHostToDevice, d0.plan->stream));
     CU_TRY(cudaStreamSynchronize(d0.plan->stream));
-    const long long T = (long long) d0.plan->hp.solve_steps.size();
+    bool blk = true;                                     // the block schedule only if every device has its inverses
+    for (int r = 0; r < N; r++) blk = blk && use_blk_schedule(m->d[r].plan);
+    const long long T = (long long) solve_schedule(d0.plan, blk).size();
     std::atomic<int> abort_flag{0};
     const auto t_begin = std::chrono::steady_clock::now();
     auto run_pass = [&](int r, int dir, long long ep) {
         MgDev &dv = m->d[r];
         ssb200_plan *p = dv.plan;
-        const HostPlan &hp = p->hp;
+        const std::vector<SolveStep> &steps = solve_schedule(p, blk);
         auto fail = [&](const std::string &msg) { dv.rc = SSB_CHOLMOD_GPU_PROBLEM; dv.err = msg; abort_flag.store(1); };
         if (cudaSetDevice(dv.device) != cudaSuccess) { fail("cudaSetDevice failed"); return; }
-        const double *winv = p->winv_valid ? p->d_winv : nullptr;
         std::vector<long long> last_waited(N, -1);
         bool was_sync = false;          // backward pass: the first step below the cut still waits for the top
         long long launches = 0;
+        if (blk && (solve_blk_prepare(p, nrhs) || solve_blk_reset(p, nrhs))) { fail(g_last_error); return; }
         for (long long q = 0; q < T; q++) {
             if (abort_flag.load()) return;
             const long long t = dir > 0 ? q : T - 1 - q;
-            const SolveStep &st = hp.solve_steps[t];
+            const SolveStep &st = steps[t];
             const bool barrier = st.sync || (dir < 0 && was_sync);
             if (st.sync) was_sync = true;
-            if (st.njobs == 0) continue;
+            if (st.njobs == 0 && st.nblk == 0) continue;
             if (barrier) {
                 for (int o = 0; o < N; o++) {
                     if (o == r) continue;
                     long long tw = t - dir;                                     // the other device's latest non-empty step before t
-                    const auto &os = m->d[o].plan->hp.solve_steps;
-                    while (tw >= 0 && tw < T && os[tw].njobs == 0) tw -= dir;
+                    const auto &os = solve_schedule(m->d[o].plan, blk);
+                    while (tw >= 0 && tw < T && os[tw].njobs == 0 && os[tw].nblk == 0) tw -= dir;
                     if (tw < 0 || tw >= T || tw == last_waited[o]) continue;
-                    mg_spin_until(m->solve_epoch[(size_t) o * T + tw], ep, abort_flag);
+                    mg_spin_until(m->solve_epoch[(size_t) o * m->solve_stride + tw], ep, abort_flag);
                     if (abort_flag.load()) return;
                     if (cudaStreamWaitEvent(p->stream, m->d[o].ev_solve[tw], 0) != cudaSuccess) { fail("cudaStreamWaitEvent failed"); return; }
                     last_waited[o] = tw;
                 }
                 if (!st.sync) was_sync = false;                                  // below the cut from here on: no more waits
             }
-            if (dir > 0) {
-                lsolve_diag_kernel<<<st.njobs, SOLVE_THREADS, 0, p->stream>>>(p->d_solve_jobs + st.job0, p->d_Lx, winv, m->d_X, (int) nrhs, n);
-                if (st.ntiles > 0)
-                    lsolve_update_kernel<<<st.ntiles, SOLVE_THREADS, 0, p->stream>>>(p->d_solve_jobs + st.job0, p->d_solve_tiles + st.tile0, p->d_Lx, p->d_ls, m->d_X, (int) nrhs, n);
-            } else {
-                if (st.ntiles > 0)
-                    ltsolve_update_kernel<<<st.ntiles, SOLVE_THREADS, 0, p->stream>>>(p->d_solve_jobs + st.job0, p->d_solve_tiles + st.tile0, p->d_Lx, p->d_ls, m->d_X, (int) nrhs, n);
-                ltsolve_diag_kernel<<<st.njobs, SOLVE_THREADS, 0, p->stream>>>(p->d_solve_jobs + st.job0, p->d_Lx, winv, m->d_X, (int) nrhs, n);
-            }
-            launches += 1 + (st.ntiles > 0 ? 1 : 0);
+            const int nl = enqueue_solve_step(p, st, blk, dir, m->d_X, (int) nrhs, n);
+            if (nl < 0) { fail("solve launch failed"); return; }
+            launches += nl;
             if (cudaEventRecord(dv.ev_solve[t], p->stream) != cudaSuccess) { fail("cudaEventRecord failed"); return; }
-            m->solve_epoch[(size_t) r * T + t].store(ep, std::memory_order_release);
+            m->solve_epoch[(size_t) r * m->solve_stride + t].store(ep, std::memory_order_release);
         }
         if (cudaStreamSynchronize(p->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess) { fail("solve kernels failed"); return; }
         p->stats.kernel_launches = launches;

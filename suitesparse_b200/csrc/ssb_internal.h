@@ -58,7 +58,25 @@ struct SolveJob {
     int winv_slot;       // >= 0: the inverse of the diagonal block is in winv[slot] (diagonal solve = 64x64 mat-vec)
 };
 constexpr int SOLVE_ROWS = 128;     // rows per solve-update tile
-struct SolveStep { long long job0; int njobs; long long tile0; int ntiles; int level = 0; int sync = 0; };   // sync: multi-GPU solve - a step above the subtree cut (all devices pass it in lock step)
+// Wide supernodes (more than 64 columns) are solved in 256-column blocks by ONE launch per step: the block's diagonal CTA
+// solves with the four 64x64 inverses and the off-diagonal blocks inside the 256x256 triangle, the row-tile CTAs of the
+// same launch prefetch their 32-row tiles of the rows below meanwhile and wait for its flag (forward), or run first and
+// are counted by it (backward).  4x fewer dependent steps than the 64-column schedule, and no second launch per step.
+constexpr int SB_W = 256, SB_ROWS = 32;
+struct SolveBlk {
+    long long x_off;     // offset in Lx of the block's diagonal entry (0,0)
+    long long ls_off;    // offset in Ls of the first row below the block
+    int lda, w, rows_below, xcol0;
+    int cta0, ntiles;    // row CTAs of this job inside its launch are [cta0, cta0+ntiles) counted after (forward) / before (backward) the
+                         // launch's diagonal CTAs; the job's diagonal CTA is its index in the step
+    int slot[4];         // inverse slot of each 64-column sub-block
+    int scratch;         // job index over the whole schedule (flag / counter / 256*nrhs doubles of scratch)
+    int nxt_w;           // columns of the following 256-block of the same supernode (0: none) - its triangle is prefetched into L2
+    int prv_w;           // columns of the preceding block (0: none), for the backward pass
+    int njobs_step;      // jobs in this launch: the diagonal CTAs of ALL jobs come first (forward) / last (backward)
+};
+struct SolveStep { long long job0; int njobs; long long tile0; int ntiles; int level = 0; int sync = 0;
+                   long long blk0 = 0; int nblk = 0; long long cta0 = 0; int nctas = 0; };   // + the wide (256-column) jobs of the step   // sync: multi-GPU solve - a step above the subtree cut (all devices pass it in lock step)
 
 enum LaunchKind : int { L_GEMM_BIG = 0, L_GEMM_SMALL = 1, L_POTRF = 2, L_TRSM = 3, L_TRSM_TC = 4, L_NKINDS = 5,
                         L_SYNC = 5 };   // L_SYNC: no kernel, only the launch's wait (joins the panel stream into the main stream)
@@ -136,6 +154,11 @@ struct HostPlan {
     std::vector<SolveJob> solve_jobs;
     std::vector<int> solve_tiles;
     std::vector<SolveStep> solve_steps;   // forward order; the backward solve walks them in reverse
+    // second schedule, used when the inverses of the diagonal blocks are valid: supernodes up to 64 columns as above,
+    // wider ones in 256-column blocks (SolveBlk)
+    std::vector<SolveJob> solve2_jobs; std::vector<int> solve2_tiles;
+    std::vector<SolveBlk> solve_blks; std::vector<int> solve_blk_ctas;   // CTA -> job index relative to the step's blk0
+    std::vector<SolveStep> solve2_steps;
     double flops_update = 0, flops_potrf = 0, flops_trsm = 0;
     double bytes_update_panel = 0, bytes_update_scatter = 0;
     std::string error;

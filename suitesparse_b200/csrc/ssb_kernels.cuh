@@ -1034,4 +1034,247 @@ __global__ void __launch_bounds__(SOLVE_THREADS) ltsolve_diag_kernel(const Solve
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Wide supernodes: one launch per 256-column block step (SolveBlk).  FWD: CTA cta0 of a job is its diagonal CTA, the next
+// ntiles CTAs own 32-row tiles of the rows below the block; they stage their tile with cp.async while the diagonal CTA
+// solves, wait for its flag, then subtract L2 * x1 from X.  BWD: the row CTAs come first, add their part of L2' * X[rows]
+// to the job's scratch and bump its counter; the diagonal CTA (last) waits for the counter, then solves with the
+// transposed blocks.  Waiting is safe: CTAs are dispatched in blockIdx order and a job's producers always precede its
+// consumers.  flags/counters/scratch are zeroed by the caller before every pass.
+// Inside the 256x256 triangle: the four 64x64 inverses W (mat-vec), the off-diagonal panels staged through shared memory.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int SB_THREADS = 256;
+constexpr int SB_TLD = SB_ROWS + 1;                       // row-tile leading dimension (odd: conflict-free transposed reads)
+constexpr int SB_PLD = 3 * NB_INNER + 1;                  // off-diagonal panel: up to 192 rows below a 64-column sub-block
+constexpr size_t solve_blk_smem_bytes()
+{
+    const size_t tile = (size_t) SB_W * SB_TLD, panel = (size_t) NB_INNER * SB_PLD;
+    return ((tile > panel ? tile : panel) + 2 * SB_W + SB_THREADS + 64) * sizeof(double);
+}
+
+__device__ __forceinline__ int ld_acquire_int(const int *p)
+{
+    int v; asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
+}
+
+template <bool FWD>
+__global__ void __launch_bounds__(SB_THREADS) solve_blk_kernel(const SolveBlk *__restrict__ blks, const int *__restrict__ cta_blk,
+                                                              const double *__restrict__ Lx, const int *__restrict__ ls,
+                                                              const double *__restrict__ winv, double *__restrict__ X, int nrhs, long long ldx,
+                                                              double *__restrict__ scratch, int *__restrict__ flags)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *buf = reinterpret_cast<double *>(smem_raw);                          // row tile [c][SB_TLD] or panel [k][SB_PLD]
+    constexpr size_t BUF = ((size_t) SB_W * SB_TLD > (size_t) NB_INNER * SB_PLD) ? (size_t) SB_W * SB_TLD : (size_t) NB_INNER * SB_PLD;
+    double *xs = buf + BUF;                                                      // [SB_W]
+    double *xn = xs + SB_W;                                                      // [SB_W] second vector
+    double *part = xn + SB_W;                                                    // [SB_THREADS]
+    int *rowidx = reinterpret_cast<int *>(part + SB_THREADS);                    // [SB_ROWS]
+    // CTA layout of the launch: forward [diagonal CTAs of all jobs][row CTAs], backward [row CTAs][diagonal CTAs]: every
+    // diagonal solve of a step runs side by side, and a waiting CTA always has its producers in front of it
+    const int nj = blks[0].njobs_step, nrow_ctas = (int) gridDim.x - nj;
+    const bool is_diag = FWD ? ((int) blockIdx.x < nj) : ((int) blockIdx.x >= nrow_ctas);
+    const int rowcta = FWD ? (int) blockIdx.x - nj : (int) blockIdx.x;
+    const SolveBlk job = blks[is_diag ? (FWD ? (int) blockIdx.x : (int) blockIdx.x - nrow_ctas) : cta_blk[rowcta]];
+    const int local = rowcta - job.cta0;                                         // row tile of the job (row CTAs only)
+    const int tid = threadIdx.x, w = job.w;
+    const long long lda = job.lda;
+    const double *__restrict__ A = Lx + job.x_off;                              // A(i,k) = A[i + k*lda], block-local indices
+    double *__restrict__ scr = scratch + (long long) job.scratch * SB_W * nrhs; // [nrhs][SB_W]
+    int *flag = flags + job.scratch;
+    const int nsb = (w + NB_INNER - 1) / NB_INNER;
+
+    if (!is_diag) {
+        // ---------------------------------------------------------------- row tile: rows [r0, r0+nr) below the block
+        // thread = (row r, group g of 32 columns): its 32 entries are loaded into registers right away - 32 independent,
+        // coalesced loads in flight per thread while (forward) the diagonal CTA is still solving
+        const int tile = local;
+        const int r0 = tile * SB_ROWS;
+        const int nr = min(SB_ROWS, job.rows_below - r0);
+        const int r = tid % SB_ROWS, g = tid / SB_ROWS;
+        const double *__restrict__ L2 = A + w + r0 + (r < nr ? r : 0) + (long long) (g * 32) * lda;   // column 32g+j at L2[j*lda]
+        double v[32];
+#pragma unroll
+        for (int j = 0; j < 32; j++) v[j] = (r < nr && g * 32 + j < w) ? __ldcs(L2 + (long long) j * lda) : 0.0;
+        if (tid < SB_ROWS) rowidx[tid] = tid < nr ? ls[job.ls_off + r0 + tid] : 0;
+        if (FWD) {
+            if (tid == 0) { while (ld_acquire_int(flag) == 0) { } }              // the diagonal CTA has published x1
+        } else {
+            // transposed use: through shared memory, [c][SB_TLD]
+#pragma unroll
+            for (int j = 0; j < 32; j++) buf[(g * 32 + j) * SB_TLD + r] = v[j];
+        }
+        __syncthreads();
+        for (int rh = 0; rh < nrhs; rh++) {
+            double *__restrict__ x = X + rh * ldx;
+            if (FWD) {
+                for (int c = tid; c < w; c += SB_THREADS) xs[c] = __ldcg(scr + rh * SB_W + c);
+                for (int c = w + tid; c < SB_W; c += SB_THREADS) xs[c] = 0.0;
+                __syncthreads();
+                double acc = 0.0;
+#pragma unroll
+                for (int j = 0; j < 32; j++) acc += v[j] * xs[g * 32 + j];
+                part[tid] = acc;
+                __syncthreads();
+                if (tid < nr) {
+                    double sum = 0.0;
+#pragma unroll
+                    for (int q = 0; q < SB_THREADS / SB_ROWS; q++) sum += part[q * SB_ROWS + tid];
+                    red_add_f64(x + rowidx[tid], -sum);
+                }
+                __syncthreads();
+            } else {
+                if (tid < SB_ROWS) xs[tid] = tid < nr ? x[rowidx[tid]] : 0.0;
+                __syncthreads();
+                // thread = column c: dot product over the tile's rows
+                if (tid < w) {
+                    double acc = 0.0;
+#pragma unroll 8
+                    for (int rr = 0; rr < SB_ROWS; rr++) acc += buf[tid * SB_TLD + rr] * xs[rr];
+                    red_add_f64(scr + rh * SB_W + tid, acc);
+                }
+                __syncthreads();
+            }
+        }
+        if (!FWD) {
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) atomicAdd(flag, 1);                                     // this tile's contribution is in the scratch
+        }
+        return;
+    }
+
+    // -------------------------------------------------------------------- diagonal CTA
+    {
+        // the triangle (and inverses) of the block that follows in this pass go to L2 now: the next step's diagonal CTA then
+        // works out of L2 instead of HBM (its dependent load batches are the critical path of the whole solve)
+        const int nw = FWD ? job.nxt_w : job.prv_w;
+        if (nw > 0) {
+            const double *__restrict__ An = FWD ? A + w + (long long) w * lda : A - SB_W - (long long) SB_W * lda;
+            for (int idx = tid; idx < nw * (nw / 16 + 1); idx += SB_THREADS) {   // one 128-byte line per 16 rows of each column's lower part
+                const int c = idx / (nw / 16 + 1), rb = idx % (nw / 16 + 1);
+                const int i = c + 16 * rb;
+                if (i < nw) asm volatile("prefetch.global.L2 [%0];" ::"l"(An + i + (long long) c * lda));
+            }
+            const double *__restrict__ Wn = winv + (long long) (FWD ? job.slot[0] + 4 : job.slot[0] - 4) * (NB_INNER * NB_INNER);
+            const int nwb = (nw + NB_INNER - 1) / NB_INNER;
+            for (int idx = tid; idx < nwb * (NB_INNER * NB_INNER / 16); idx += SB_THREADS) asm volatile("prefetch.global.L2 [%0];" ::"l"(Wn + 16 * idx));
+        }
+    }
+    if (!FWD) {
+        if (tid == 0) { while (ld_acquire_int(flag) < job.ntiles) { } }          // every row tile has contributed
+        __syncthreads();
+    }
+    // stage the off-diagonal panel below sub-block sb: rows [64(sb+1), w) x 64 columns -> buf[k][i]
+    auto stage_panel = [&](int sb) {
+        const int i0 = NB_INNER * (sb + 1), ni = w - i0, k0 = NB_INNER * sb;
+        const int wk = min(NB_INNER, w - k0);
+        const int tot = wk * ni;
+        // batches of 16 coalesced loads per thread (consecutive threads = consecutive rows), then the stores
+        for (int base = 0; base < tot; base += SB_THREADS * 16) {
+            double q[16];
+#pragma unroll
+            for (int u = 0; u < 16; u++) {
+                const int idx = base + u * SB_THREADS + tid;
+                q[u] = idx < tot ? A[(i0 + idx % ni) + (long long) (k0 + idx / ni) * lda] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 16; u++) {
+                const int idx = base + u * SB_THREADS + tid;
+                if (idx < tot) buf[(idx / ni) * SB_PLD + idx % ni] = q[u];
+            }
+        }
+    };
+    for (int rh = 0; rh < nrhs; rh++) {
+        double *__restrict__ x = X + rh * ldx + job.xcol0;
+        __syncthreads();
+        for (int c = tid; c < SB_W; c += SB_THREADS) xs[c] = c < w ? (FWD ? x[c] : x[c] - __ldcg(scr + rh * SB_W + c)) : 0.0;
+        __syncthreads();
+        if (FWD) {
+            for (int sb = 0; sb < nsb; sb++) {
+                const int k0 = NB_INNER * sb, wk = min(NB_INNER, w - k0);
+                const bool below = sb + 1 < nsb;
+                if (below) stage_panel(sb);                                      // its loads are in flight while the inverse is applied
+                // x_sb <- W_sb x_sb: thread = (row i, quarter h): W(i,k) at W[i + 64k], k <= i
+                const double *__restrict__ W = winv + (long long) job.slot[sb] * (NB_INNER * NB_INNER);
+                {
+                    const int i = tid & 63, h = tid >> 6;
+                    double acc = 0.0, wv[16];
+#pragma unroll
+                    for (int u = 0; u < 16; u++) { const int k = h + 4 * u; wv[u] = (i < wk && k <= i) ? W[i + NB_INNER * k] : 0.0; }   // one batch of loads
+#pragma unroll
+                    for (int u = 0; u < 16; u++) acc += wv[u] * xs[k0 + h + 4 * u];
+                    part[tid] = acc;
+                }
+                __syncthreads();
+                if (tid < wk) xs[k0 + tid] = part[tid] + part[tid + 64] + part[tid + 128] + part[tid + 192];
+                __syncthreads();
+                if (below) {
+                    // x_rest -= P x_sb: thread = row i of the rest
+                    const int i0 = k0 + NB_INNER, ni = w - i0;
+                    if (tid < ni) {
+                        double acc = 0.0;
+#pragma unroll 8
+                        for (int k = 0; k < wk; k++) acc += buf[k * SB_PLD + tid] * xs[k0 + k];
+                        xs[i0 + tid] -= acc;
+                    }
+                    __syncthreads();
+                }
+            }
+            for (int c = tid; c < w; c += SB_THREADS) { x[c] = xs[c]; scr[rh * SB_W + c] = xs[c]; }
+        } else {
+            for (int sb = nsb - 1; sb >= 0; sb--) {
+                const int k0 = NB_INNER * sb, wk = min(NB_INNER, w - k0);
+                if (sb + 1 < nsb) {
+                    stage_panel(sb);
+                    __syncthreads();
+                    // x_sb -= P' x_rest: thread = (column k, quarter h) over the rows of the rest
+                    const int i0 = k0 + NB_INNER, ni = w - i0;
+                    const int k = tid & 63, h = tid >> 6;
+                    double acc = 0.0;
+                    if (k < wk) {
+#pragma unroll 4
+                        for (int i = h; i < ni; i += 4) acc += buf[k * SB_PLD + i] * xs[i0 + i];
+                    }
+                    part[tid] = acc;
+                    __syncthreads();
+                    if (tid < wk) xs[k0 + tid] -= part[tid] + part[tid + 64] + part[tid + 128] + part[tid + 192];
+                    __syncthreads();
+                }
+                // x_sb <- W_sb' x_sb: sum over k >= i of W(k,i) x(k).  W(k,i) sits at W[k + 64 i]: staged through shared memory
+                // (coalesced reads, then conflict-free transposed use: buf[i*65 + k])
+                const double *__restrict__ W = winv + (long long) job.slot[sb] * (NB_INNER * NB_INNER);
+                {
+                    double q[16];
+#pragma unroll
+                    for (int u = 0; u < 16; u++) q[u] = W[u * SB_THREADS + tid];
+#pragma unroll
+                    for (int u = 0; u < 16; u++) { const int idx = u * SB_THREADS + tid; buf[(idx >> 6) * (NB_INNER + 1) + (idx & 63)] = q[u]; }
+                }
+                __syncthreads();
+                {
+                    const int i = tid & 63, h = tid >> 6;
+                    double acc = 0.0;
+                    if (i < wk) {
+#pragma unroll 4
+                        for (int k = i + h; k < wk; k += 4) acc += buf[i * (NB_INNER + 1) + k] * xs[k0 + k];
+                    }
+                    part[tid] = acc;
+                }
+                __syncthreads();
+                if (tid < wk) xn[tid] = part[tid] + part[tid + 64] + part[tid + 128] + part[tid + 192];
+                __syncthreads();
+                if (tid < wk) xs[k0 + tid] = xn[tid];
+                __syncthreads();
+            }
+            for (int c = tid; c < w; c += SB_THREADS) x[c] = xs[c];
+        }
+    }
+    if (FWD) {
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) atomicExch(flag, 1);                                        // x1 of every right-hand side is in the scratch
+    }
+}
+
 }  // namespace ssb

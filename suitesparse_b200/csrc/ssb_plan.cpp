@@ -25,6 +25,7 @@ int winv_slot_of(const HostPlan &hp, int s, int j0)
     const int nscol = hp.super[s + 1] - hp.super[s];
     const int nsrow = (int) (hp.pi[s + 1] - hp.pi[s]);
     const int w = std::min(NB_INNER, nscol - j0);
+    if (nscol > NB_INNER) return hp.winv_base[s] + j0 / NB_INNER;       // wide supernode: every block (the 256-column solve needs them all)
     if (w < TRSM_TC_MIN_W || nsrow - j0 - w <= 0) return -1;
     return hp.winv_base[s] + j0 / NB_INNER;
 }
@@ -297,7 +298,7 @@ bool build_host_plan(long long n, long long nsuper, const long long *super, cons
         for (int t = 0; t < (int) nsuper; t++) {
             const int nscol = hp.super[t + 1] - hp.super[t];
             const int nsrow = (int) (hp.pi[t + 1] - hp.pi[t]);
-            if (nscol >= TRSM_TC_MIN_W && nsrow > NB_INNER / 2) { hp.winv_base[t] = slots; slots += (nscol + NB_INNER - 1) / NB_INNER; }
+            if ((nscol >= TRSM_TC_MIN_W && nsrow > NB_INNER / 2) || nscol > NB_INNER) { hp.winv_base[t] = slots; slots += (nscol + NB_INNER - 1) / NB_INNER; }
         }
         hp.max_winv_slots = slots;
     }
@@ -653,6 +654,73 @@ bool build_host_plan(long long n, long long nsuper, const long long *super, cons
             if (st.njobs || hp.compact) hp.solve_steps.push_back(st);
         }
     }
+    // ---- second solve schedule: the big supernodes (>= blk_min columns) in fused 256-column block steps, everything else
+    // in 64-column steps as in the first schedule.  Supernodes of one level are independent, so a level is: the 64-column
+    // steps of its small supernodes, then the block steps of its big ones.  (Measured: the fused kernel wins where a step
+    // has few jobs with many rows - the top of the tree; with thousands of jobs per step its diagonal CTA's latency does not.)
+    int blk_min = 1024;
+    if (const char *e = getenv("SSB200_SOLVE_BLK_MIN")) blk_min = std::max(NB_INNER + 1, atoi(e));
+    for (int l = 0; l < hp.nlevels; l++) {
+        int maxsmall = 0, maxbig = 0;
+        for (int t = hp.level_ptr[l]; t < hp.level_ptr[l + 1]; t++) {
+            const int sn = hp.level_nodes[t];
+            const int nscol = hp.super[sn + 1] - hp.super[sn];
+            if (nscol >= blk_min) maxbig = std::max(maxbig, nscol); else maxsmall = std::max(maxsmall, nscol);
+        }
+        auto mine = [&](int sn, int j0) {
+            if (!hp.compact) return true;
+            const int o = hp.owner[sn];
+            return o >= 0 ? (o == hp.rank) : ((j0 / NB_MID) % hp.nranks == hp.rank);
+        };
+        for (int j0 = 0; j0 < maxsmall; j0 += NB_INNER) {
+            SolveStep st{(long long) hp.solve2_jobs.size(), 0, (long long) hp.solve2_tiles.size(), 0};
+            st.level = l; st.sync = (hp.compact && l >= top_min_level) ? 1 : 0;
+            st.blk0 = (long long) hp.solve_blks.size(); st.cta0 = (long long) hp.solve_blk_ctas.size();
+            for (int t = hp.level_ptr[l]; t < hp.level_ptr[l + 1]; t++) {
+                const int sn = hp.level_nodes[t];
+                const int nscol = hp.super[sn + 1] - hp.super[sn];
+                if (nscol >= blk_min || nscol <= j0 || !mine(sn, j0)) continue;
+                const int nsrow = (int) (hp.pi[sn + 1] - hp.pi[sn]);
+                SolveJob sj{};
+                sj.w = std::min(NB_INNER, nscol - j0);
+                sj.x_off = hp.px[sn] + j0 + (long long) j0 * nsrow;
+                sj.ls_off = hp.pi[sn] + j0 + sj.w;
+                sj.lda = nsrow; sj.rows_below = nsrow - j0 - sj.w; sj.xcol0 = hp.super[sn] + j0;
+                sj.tile_start = st.ntiles; sj.winv_slot = winv_slot_of(hp, sn, j0);
+                const int nt = (sj.rows_below + SOLVE_ROWS - 1) / SOLVE_ROWS;
+                for (int z = 0; z < nt; z++) hp.solve2_tiles.push_back(st.njobs);
+                st.ntiles += nt; hp.solve2_jobs.push_back(sj); st.njobs++;
+            }
+            if (st.njobs || hp.compact) hp.solve2_steps.push_back(st);
+        }
+        for (int j0 = 0; j0 < maxbig; j0 += SB_W) {
+            SolveStep st{(long long) hp.solve2_jobs.size(), 0, (long long) hp.solve2_tiles.size(), 0};
+            st.level = l; st.sync = (hp.compact && l >= top_min_level) ? 1 : 0;
+            st.blk0 = (long long) hp.solve_blks.size(); st.cta0 = (long long) hp.solve_blk_ctas.size();
+            for (int t = hp.level_ptr[l]; t < hp.level_ptr[l + 1]; t++) {
+                const int sn = hp.level_nodes[t];
+                const int nscol = hp.super[sn + 1] - hp.super[sn];
+                if (nscol < blk_min || nscol <= j0 || !mine(sn, j0)) continue;
+                const int nsrow = (int) (hp.pi[sn + 1] - hp.pi[sn]);
+                SolveBlk b{};
+                b.w = std::min(SB_W, nscol - j0);
+                b.x_off = hp.px[sn] + j0 + (long long) j0 * nsrow;
+                b.ls_off = hp.pi[sn] + j0 + b.w;
+                b.lda = nsrow; b.rows_below = nsrow - j0 - b.w; b.xcol0 = hp.super[sn] + j0;
+                b.cta0 = st.nctas; b.ntiles = (b.rows_below + SB_ROWS - 1) / SB_ROWS;
+                for (int z = 0; z < 4; z++) b.slot[z] = (64 * z < b.w) ? winv_slot_of(hp, sn, j0 + 64 * z) : -1;
+                b.scratch = (int) hp.solve_blks.size();
+                b.nxt_w = (j0 + SB_W < nscol) ? std::min(SB_W, nscol - j0 - SB_W) : 0;
+                b.prv_w = j0 > 0 ? SB_W : 0;
+                if (hp.compact && hp.owner[sn] < 0) b.nxt_w = b.prv_w = 0;         // the neighbouring block lives on another rank
+                for (int z = 0; z < b.ntiles; z++) hp.solve_blk_ctas.push_back(st.nblk);
+                st.nctas += b.ntiles; hp.solve_blks.push_back(b); st.nblk++;
+            }
+            // the launch = [nblk diagonal CTAs][row CTAs] forward, [row CTAs][nblk diagonal CTAs] backward
+            for (int z = 0; z < st.nblk; z++) hp.solve_blks[st.blk0 + z].njobs_step = st.nblk;
+            if (st.nblk || hp.compact) hp.solve2_steps.push_back(st);
+        }
+    }
     // ---- distributed storage: local layout, relocation of every offset, receive lists ---------------------------------
     if (hp.compact) {
         hp.lpx.assign(nsuper + 1, -1);
@@ -673,6 +741,8 @@ bool build_host_plan(long long n, long long nsuper, const long long *super, cons
         for (auto &j : hp.potrf_jobs) j.x_off = loc(j.x_off);
         for (auto &j : hp.trsm_jobs) j.x_off = loc(j.x_off);
         for (auto &j : hp.solve_jobs) j.x_off = loc(j.x_off);
+        for (auto &j : hp.solve2_jobs) j.x_off = loc(j.x_off);
+        for (auto &j : hp.solve_blks) j.x_off = loc(j.x_off);
         if (!hp.error.empty()) return false;
         // what this rank pulls out of every finished range: maximal runs of consecutive needed supernodes
         hp.step_recv.assign(hp.steps.size(), {});
