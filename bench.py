@@ -285,6 +285,11 @@ def main_mg(args, torch, dist, dev, rank, world, local, workload):
     import scipy.sparse as sp
     out = None
     t_dev = t_host = 0.0
+    # The waiting ranks must wait on the CPU: an NCCL barrier is a kernel that spins on THEIR GPU until rank 0 arrives, and a
+    # busy context of another process time-slices the device with rank 0's kernels (measured: 936 ms instead of 312 ms per
+    # step).  So: NCCL for the one all-reduce of the times at the end, a gloo group for the barriers around the timed regions.
+    cpu_group = dist.new_group(backend="gloo")
+    barrier = lambda: dist.barrier(group=cpu_group)
     if rank == 0:
         from suitesparse_b200.cholmod_host import Cholmod, _np_view
         from suitesparse_b200 import plain
@@ -302,7 +307,7 @@ def main_mg(args, torch, dist, dev, rank, world, local, workload):
         st, minor = mg.factorize(Sl)                      # uploads S to every device
         assert st == 0
         sampler = ClockSampler(local); sampler.start()
-    dist.barrier(); torch.cuda.synchronize(dev)
+    barrier(); torch.cuda.synchronize(dev)
     if rank == 0:
         for _ in range(args.warmup):
             mg.factorize_resident()
@@ -311,7 +316,7 @@ def main_mg(args, torch, dist, dev, rank, world, local, workload):
             st, minor = mg.factorize_resident()
             tdev.append(mg.info()["ms_device"] * 1e-3); launches += mg.launches()
         t_dev = float(np.mean(tdev))
-    dist.barrier(); torch.cuda.synchronize(dev)
+    barrier(); torch.cuda.synchronize(dev)
     if rank == 0:
         # e2e: host S in, host L->x out (page-locked once; every device copies its share out over its own PCIe link)
         host_t = torch.empty(xsize, dtype=torch.float64)
@@ -333,8 +338,10 @@ def main_mg(args, torch, dist, dev, rank, world, local, workload):
         resid = float(np.linalg.norm(Af @ x - b) / np.linalg.norm(b))
         # the host copy is the factor: solve with it through a fresh upload of a sample? cheap check: finite and equal to a re-download
         assert np.isfinite(host[:: 100003]).all()
+    barrier()
     tt = torch.tensor([t_dev, t_host], dtype=torch.float64, device=dev)
-    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)            # NCCL sees all N ranks; nobody is computing at this point
+    torch.cuda.synchronize(dev)
     t_dev, t_host = tt.tolist()
     if rank == 0:
         a_bytes = int(s2.nzmax) * 16 + (n + 1) * 8
@@ -363,7 +370,7 @@ def main_mg(args, torch, dist, dev, rank, world, local, workload):
             # BASELINE configs[3], second half: elasticity 100^3 x 3 DOF on 2 B200 (factor resident, distributed)
             out["extra_configs"] = [run_extra("elas", 100, ndev=2)]
         print(json.dumps(out), flush=True)
-    dist.barrier(); dist.destroy_process_group()
+    barrier(); dist.destroy_process_group()
 
 
 def main():

@@ -107,7 +107,8 @@ struct ssb200_plan {
     double last_beta0 = 0.0;               // beta of the running sharded factorization (not-positive-definite repeat)
     bool winv_valid = false;               // d_winv matches d_Lx (false after ssb200_upload_L or a sharded factorization)
     // the whole solve sequence is replayed as one CUDA graph (thousands of tiny dependent kernels)
-    cudaGraphExec_t solve_graph = nullptr; double *sg_X = nullptr; long long sg_nrhs = 0, sg_ldx = 0, sg_launches = 0; int sg_which = -1; bool sg_winv = false;
+    // one cached graph per direction (L, L', both): cholmod_solve2 calls lsolve and ltsolve alternately, each with its own graph
+    struct SolveGraph { cudaGraphExec_t exec = nullptr; double *X = nullptr; long long nrhs = 0, ldx = 0, launches = 0; bool winv = false, blk = false; } sg[3];
     std::vector<cudaEvent_t> events;
     ssb200_stats stats{};
     std::vector<float> launch_ms;          // device time of every launch of the last factorize (debug / tuning)
@@ -162,7 +163,7 @@ static void plan_free(ssb200_plan *p)
                     p->d_X};
     for (void *q : ptrs) if (q) cudaFree(q);
     free_cscbuf(p->bufA); free_cscbuf(p->bufF);
-    if (p->solve_graph) cudaGraphExecDestroy(p->solve_graph);
+    for (auto &g : p->sg) if (g.exec) cudaGraphExecDestroy(g.exec);
     if (p->fgraph) cudaGraphExecDestroy(p->fgraph);
     if (p->h_info) cudaFreeHost(p->h_info);
     for (auto e : p->events) cudaEventDestroy(e);
@@ -499,11 +500,12 @@ static int run_launch(ssb200_plan *p, const Launch &L, const DevJobs &dj, bool t
         break;
     case L_POTRF:
     {
-        // version 3 (four columns per barrier) is the default; SSB200_POTRF=1 selects version 1 (one barrier per column),
-        // =2 version 2 (16-column sub-panels with a warp-shuffle diagonal block; measured slower than version 1 on B200)
+        // version 4 (four columns per step, rank-4 updates on the fp64 tensor cores) is the default; SSB200_POTRF=3: the same
+        // scheme with fp64 FMAs, =1: one barrier per column, =2: 16-column sub-panels with a warp-shuffle diagonal block
         static int ver = -1;
-        if (ver < 0) { const char *v = getenv("SSB200_POTRF"); ver = v ? atoi(v) : 3; if (ver < 1 || ver > 3) ver = 3; }
-        if (ver == 3) ce = launch_ex(potrf_block_kernel3, L.njobs, POTRF_THREADS, 0, st, high, pr, (const PanelJob *) (dj.potrf_jobs + L.job0), p->d_Lx, p->d_info, p->d_winv);
+        if (ver < 0) { const char *v = getenv("SSB200_POTRF"); ver = v ? atoi(v) : 4; if (ver < 1 || ver > 4) ver = 4; }
+        if (ver == 4) ce = launch_ex(potrf_block_kernel4, L.njobs, POTRF_THREADS, 0, st, high, pr, (const PanelJob *) (dj.potrf_jobs + L.job0), p->d_Lx, p->d_info, p->d_winv);
+        else if (ver == 3) ce = launch_ex(potrf_block_kernel3, L.njobs, POTRF_THREADS, 0, st, high, pr, (const PanelJob *) (dj.potrf_jobs + L.job0), p->d_Lx, p->d_info, p->d_winv);
         else if (ver == 1) ce = launch_ex(potrf_block_kernel, L.njobs, POTRF_THREADS, 0, st, high, pr, (const PanelJob *) (dj.potrf_jobs + L.job0), p->d_Lx, p->d_info, p->d_winv);
         else ce = launch_ex(potrf_block_kernel2, L.njobs, POTRF_THREADS, potrf2_smem_bytes(), st, high, pr, (const PanelJob *) (dj.potrf_jobs + L.job0), p->d_Lx, p->d_info, p->d_winv);
     }
@@ -868,9 +870,8 @@ extern "C" int ssb200_factorize(ssb200_plan *p, int stype, const ssb_long *Ap, c
 // an experiment.
 static bool use_blk_schedule(const ssb200_plan *p)
 {
-    static int on = -1;
-    if (on < 0) { const char *v = getenv("SSB200_SOLVE_BLK"); on = (v && atoi(v) != 0) ? 1 : 0; }
-    return on && p->winv_valid;
+    const char *v = getenv("SSB200_SOLVE_BLK");
+    return v && atoi(v) != 0 && p->winv_valid;
 }
 static const std::vector<SolveStep> &solve_schedule(const ssb200_plan *p, bool blk) { return blk ? p->hp.solve2_steps : p->hp.solve_steps; }
 
@@ -939,11 +940,12 @@ extern "C" int ssb200_solve_resident(ssb200_plan *p, int which, double *dX, ssb_
     if (blk && solve_blk_prepare(p, nrhs)) return SSB_CHOLMOD_GPU_PROBLEM;
     static int use_graph = -1;
     if (use_graph < 0) { const char *v = getenv("SSB200_SOLVE_GRAPH"); use_graph = (v && atoi(v) == 0) ? 0 : 1; }
-    const bool cached = use_graph && p->solve_graph && p->sg_X == dX && p->sg_nrhs == nrhs && p->sg_ldx == ldx && p->sg_which == which && p->sg_winv == p->winv_valid;
+    ssb200_plan::SolveGraph &sg = p->sg[which];
+    const bool cached = use_graph && sg.exec && sg.X == dX && sg.nrhs == nrhs && sg.ldx == ldx && sg.winv == p->winv_valid && sg.blk == blk;
     long long launches = 0;
     if (!cached) {
         if (use_graph) {
-            if (p->solve_graph) { cudaGraphExecDestroy(p->solve_graph); p->solve_graph = nullptr; }
+            if (sg.exec) { cudaGraphExecDestroy(sg.exec); sg.exec = nullptr; }
             CU_TRY(cudaStreamBeginCapture(p->stream, cudaStreamCaptureModeThreadLocal));
         } else cudaEventRecord(e0, p->stream);
         int rc = 0;
@@ -959,16 +961,16 @@ extern "C" int ssb200_solve_resident(ssb200_plan *p, int which, double *dX, ssb_
             cudaGraph_t g = nullptr;
             cudaError_t ce = cudaStreamEndCapture(p->stream, &g);
             if (rc || ce != cudaSuccess) { if (g) cudaGraphDestroy(g); (void) cudaGetLastError(); set_error("solve graph capture failed"); return SSB_CHOLMOD_GPU_PROBLEM; }
-            cudaError_t ie = cudaGraphInstantiate(&p->solve_graph, g, 0);
+            cudaError_t ie = cudaGraphInstantiate(&sg.exec, g, 0);
             cudaGraphDestroy(g);
-            if (ie != cudaSuccess) { p->solve_graph = nullptr; set_error(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ie)); return SSB_CHOLMOD_GPU_PROBLEM; }
-            p->sg_X = dX; p->sg_nrhs = nrhs; p->sg_ldx = ldx; p->sg_which = which; p->sg_winv = p->winv_valid; p->sg_launches = launches;
+            if (ie != cudaSuccess) { sg.exec = nullptr; set_error(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ie)); return SSB_CHOLMOD_GPU_PROBLEM; }
+            sg.X = dX; sg.nrhs = nrhs; sg.ldx = ldx; sg.winv = p->winv_valid; sg.blk = blk; sg.launches = launches;
         } else if (rc) return SSB_CHOLMOD_GPU_PROBLEM;
     }
-    p->stats.kernel_launches = use_graph ? p->sg_launches : launches;
+    p->stats.kernel_launches = use_graph ? sg.launches : launches;
     if (use_graph) {
         cudaEventRecord(e0, p->stream);
-        CU_TRY(cudaGraphLaunch(p->solve_graph, p->stream));
+        CU_TRY(cudaGraphLaunch(sg.exec, p->stream));
     }
     cudaEventRecord(e1, p->stream);
     CU_TRY(cudaGetLastError());
@@ -1318,13 +1320,22 @@ extern "C" int ssb200_mg_factorize(ssb200_mg *m, int stype, const ssb_long *Ap, 
         MG_TRY(cudaStreamWaitEvent(dv.comm, dv.ev_begin, 0));
         if (two) MG_TRY(cudaStreamWaitEvent(p->panel_stream, dv.ev_begin, 0));
         std::vector<cudaEvent_t> outstanding;
+        std::vector<char> waited(ns, 0);
+        static int wait_all = -1;
+        if (wait_all < 0) { const char *v = getenv("SSB200_MG_WAIT_ALL"); wait_all = (v && atoi(v)) ? 1 : 0; }
         for (size_t k = 0; k < ns; k++) {
             if (abort_flag.load()) return;
             const DistStep &st = hp.steps[k];
             if (trace) MG_TRY(cudaEventRecord(dv.ev_trace[k], p->stream));
-            if (st.wait_remote && !outstanding.empty()) {
-                for (cudaEvent_t e : outstanding) MG_TRY(cudaStreamWaitEvent(p->stream, e, 0));
-                outstanding.clear();
+            if (wait_all) {
+                if (st.wait_remote && !outstanding.empty()) {
+                    for (cudaEvent_t e : outstanding) MG_TRY(cudaStreamWaitEvent(p->stream, e, 0));
+                    outstanding.clear();
+                }
+            } else {
+                // only the pulls whose data this step's launches read (the others keep streaming in behind the compute)
+                for (int dep : hp.step_deps[k])
+                    if (!waited[dep] && dv.ev_arrived[dep]) { MG_TRY(cudaStreamWaitEvent(p->stream, dv.ev_arrived[dep], 0)); waited[dep] = 1; }
             }
             for (int t = st.launch_begin; t < st.launch_mid; t++) if (run_launch(p, hp.launches[t], p->jobs, two)) { fail(g_last_error); return; }
             if (st.bcast_src == r) {

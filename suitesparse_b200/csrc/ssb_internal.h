@@ -146,6 +146,7 @@ struct HostPlan {
     long long lxsize = 0;                // doubles of local factor storage
     struct Piece { long long home_off, cnt; };
     std::vector<std::vector<Piece>> step_recv;   // per step: the parts of the step's finished range this rank reads (home offsets)
+    std::vector<std::vector<int>> step_deps;     // per step: the earlier steps whose (remote) finished ranges its launches read
     std::vector<int> step_next;          // per step: for a finished panel of a cyclic supernode, the owner of the next panel (-1 none)
     int top_min_level = 0;               // lowest etree level that holds a supernode above the subtree cut
     // solve schedule: supernodes ordered by level

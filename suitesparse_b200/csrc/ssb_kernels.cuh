@@ -479,6 +479,130 @@ __global__ void __launch_bounds__(POTRF_THREADS) potrf_block_kernel3(const Panel
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// diagonal block Cholesky, version 4 (default): version 3's four-columns-per-step scheme with the rank-4 updates on the
+// fp64 tensor cores.  ncu on version 3 (profiles/r2_ncu_full_potrf3.txt): 35 us, one SM, stall reason "wait" - the ~290
+// dependent fp64 instructions per thread and step, not the barriers.  Here the 64x64 tile T and its inverse Y (both lower
+// triangular, 36 8x8 tiles each) live in DMMA accumulator fragments: warp I owns tile row I of T and tile row 7-I of Y
+// (9 tiles per warp).  Per step: the owners publish the four panel columns of T and the four panel rows of Y; barrier;
+// every thread factorizes the 4x4 diagonal block (four dependent rsqrt); thread t then computes ONE final panel entry
+// L(t%64, j+t/64) and ONE final Y(j+t/64, t%64), stores them to shared memory (and L to global); barrier; each warp
+// applies T -= Lp Lp' and Y -= Lp Yp with one m8n8k4 DMMA per tile (K = 4 is exactly the panel width).
+// Entries at or above the panel are masked to zero in the fragments, so no garbage ever enters the accumulators.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(POTRF_THREADS) potrf_block_kernel4(const PanelJob *__restrict__ jobs, double *__restrict__ Lx,
+                                                                    int *__restrict__ info, double *__restrict__ winv)
+{
+    __shared__ double cb[4][NB_INNER];      // panel columns of T before the panel is factorized
+    __shared__ double rb[4][NB_INNER];      // panel rows of Y before
+    __shared__ double Lp[4][NB_INNER];      // final L(row, j+c), 0 for rows at or above the panel
+    __shared__ double Yp[4][NB_INNER];      // final Y(j+c, col)
+    const PanelJob job = jobs[blockIdx.x];
+    const int w = job.w, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int gr = lane >> 2, gc = lane & 3;            // fragment coordinates: C(gr, 2gc+e), A(gr, gc), B(gc, gr)
+    const int I = warp, IY = 7 - warp;
+    const long long lda = job.lda;
+    const bool want_inv = job.winv_slot >= 0;
+    double *__restrict__ A = Lx + job.x_off;
+    double tT[8][2], tY[8][2];
+#pragma unroll
+    for (int K = 0; K < 8; K++)
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+            const int i = 8 * I + gr, k = 8 * K + 2 * gc + e;
+            tT[K][e] = (K <= I && i < w && k < w && i >= k) ? A[i + k * lda] : 0.0;
+            tY[K][e] = (8 * IY + gr == k) ? 1.0 : 0.0;
+        }
+    for (int e = tid; e < 4 * NB_INNER; e += POTRF_THREADS) (&rb[0][0])[e] = 0.0;
+    __syncthreads();
+    for (int j = 0; j < w; j += 4) {
+        const int Jt = j >> 3, jj = j & 7;
+        // publish columns j..j+3 of T (rows of this warp's tile row) and rows j..j+3 of Y
+        if (I >= Jt && (gc >> 1) == (jj >> 2)) {
+            double v0 = 0.0, v1 = 0.0;
+#pragma unroll
+            for (int K = 0; K < 8; K++) if (K == Jt) { v0 = tT[K][0]; v1 = tT[K][1]; }
+            const int c = 2 * (gc & 1);
+            cb[c][8 * I + gr] = v0; cb[c + 1][8 * I + gr] = v1;
+        }
+        if (want_inv && IY == Jt && gr >= jj && gr < jj + 4) {
+            const int c = gr - jj;
+#pragma unroll
+            for (int K = 0; K < 8; K++) if (K <= Jt) { rb[c][8 * K + 2 * gc] = tY[K][0]; rb[c][8 * K + 2 * gc + 1] = tY[K][1]; }
+        }
+        __syncthreads();
+        // 4x4 diagonal block, factorized by every thread
+        double l[4][4], rinv[4];
+        int failc = -1;
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            double dcc = cb[c][j + c];
+#pragma unroll
+            for (int q = 0; q < c; q++) dcc -= l[c][q] * l[c][q];
+            if (j + c >= w) dcc = 1.0;
+            if (!(dcc > 0.0)) { if (failc < 0) failc = c; dcc = 1.0; }
+            const double ri = rsqrt(dcc);
+            rinv[c] = ri; l[c][c] = dcc * ri;
+#pragma unroll
+            for (int r = c + 1; r < 4; r++) {
+                double v = cb[c][j + r];
+#pragma unroll
+                for (int q = 0; q < c; q++) v -= l[r][q] * l[c][q];
+                l[r][c] = v * ri;
+            }
+        }
+        if (failc >= 0) {
+            if (tid == 0) atomicMin(&info[job.snode], job.col0 + j + failc + 1);
+            break;
+        }
+        // one final panel entry of L and one of Y per thread
+        {
+            const int row = tid & 63, c = tid >> 6;
+            const double x0 = cb[0][row] * rinv[0];
+            const double x1 = (cb[1][row] - x0 * l[1][0]) * rinv[1];
+            const double x2 = (cb[2][row] - x0 * l[2][0] - x1 * l[2][1]) * rinv[2];
+            const double x3 = (cb[3][row] - x0 * l[3][0] - x1 * l[3][1] - x2 * l[3][2]) * rinv[3];
+            const double xc = c == 0 ? x0 : c == 1 ? x1 : c == 2 ? x2 : x3;
+            Lp[c][row] = row > j + 3 ? xc : 0.0;
+            if (row >= j + c && row < w && j + c < w) A[row + (long long) (j + c) * lda] = xc;
+            if (want_inv) {
+                const double y0 = rb[0][row] * rinv[0];
+                const double y1 = (rb[1][row] - l[1][0] * y0) * rinv[1];
+                const double y2 = (rb[2][row] - l[2][0] * y0 - l[2][1] * y1) * rinv[2];
+                const double y3 = (rb[3][row] - l[3][0] * y0 - l[3][1] * y1 - l[3][2] * y2) * rinv[3];
+                Yp[c][row] = c == 0 ? y0 : c == 1 ? y1 : c == 2 ? y2 : y3;
+            }
+        }
+        __syncthreads();
+        // T(i,k) -= sum_c Lp[c][i] Lp[c][k] for the tiles right of the panel; rows/columns at or above the panel are zero in Lp
+        {
+            const double a = -Lp[gc][8 * I + gr];
+#pragma unroll
+            for (int K = 0; K < 8; K++)
+                if (K >= Jt && K <= I) dmma884(tT[K][0], tT[K][1], a, Lp[gc][8 * K + gr]);
+        }
+        if (want_inv) {
+            // Y(i,:) -= sum_c Lp[c][i] Yp[c][:] for the rows below the panel; the panel rows themselves become Yp
+            const double a = -Lp[gc][8 * IY + gr];
+#pragma unroll
+            for (int K = 0; K < 8; K++)
+                if (K <= IY && K <= Jt) dmma884(tY[K][0], tY[K][1], a, Yp[gc][8 * K + gr]);
+            if (IY == Jt && gr >= jj && gr < jj + 4) {
+                const int c = gr - jj;
+#pragma unroll
+                for (int K = 0; K < 8; K++) if (K <= Jt) { tY[K][0] = Yp[c][8 * K + 2 * gc]; tY[K][1] = Yp[c][8 * K + 2 * gc + 1]; }
+            }
+        }
+    }
+    if (want_inv) {
+        double *__restrict__ W = winv + (long long) job.winv_slot * (NB_INNER * NB_INNER);
+#pragma unroll
+        for (int K = 0; K < 8; K++)
+#pragma unroll
+            for (int e = 0; e < 2; e++) W[(8 * IY + gr) + NB_INNER * (8 * K + 2 * gc + e)] = K <= IY ? tY[K][e] : 0.0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // diagonal block Cholesky, version 2: blocked by 16-column sub-panels so that the column-by-column part has NO block
 // barriers.  Per sub-panel: (1) ONE warp factorizes the 16x16 diagonal sub-block in registers with shuffles - lanes 0..15
 // hold its rows, lanes 16..31 hold the rows of its inverse, built by the same elimination; (2) all threads bring the rows

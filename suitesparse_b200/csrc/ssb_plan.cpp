@@ -723,6 +723,46 @@ bool build_host_plan(long long n, long long nsuper, const long long *super, cons
     }
     // ---- distributed storage: local layout, relocation of every offset, receive lists ---------------------------------
     if (hp.compact) {
+        // ---- which finished ranges does every step read?  (before the offsets are relocated: home offsets identify supernodes)
+        {
+            std::vector<int> final_step(nsuper, -1);                       // whole supernodes: the step that finished them
+            std::map<std::pair<int, int>, int> panel_step;                  // (cyclic supernode, panel) -> step
+            for (size_t k = 0; k < hp.steps.size(); k++) {
+                const DistStep &st = hp.steps[k];
+                if (st.bcast_src < 0 || st.cnt <= 0) continue;
+                const int t0 = (int) (std::upper_bound(hp.px.begin(), hp.px.end(), st.off) - hp.px.begin()) - 1;
+                if (hp.owner[t0] < 0) {
+                    const long long nsrow = hp.pi[t0 + 1] - hp.pi[t0];
+                    panel_step[{t0, (int) ((st.off - hp.px[t0]) / ((long long) NB_MID * nsrow))}] = (int) k;
+                } else
+                    for (int t = t0; t < (int) nsuper && hp.px[t] < st.off + st.cnt; t++) final_step[t] = (int) k;
+            }
+            hp.step_deps.assign(hp.steps.size(), {});
+            for (size_t k = 0; k < hp.steps.size(); k++) {
+                const DistStep &st = hp.steps[k];
+                std::vector<int> &deps = hp.step_deps[k];
+                for (int t = st.launch_begin; t < st.launch_end; t++) {
+                    const Launch &L = hp.launches[t];
+                    if (L.kind != L_GEMM_BIG && L.kind != L_GEMM_SMALL) continue;
+                    for (long long q = L.job0; q < L.job0 + L.njobs; q++) {
+                        const GemmJob &g = hp.gemm_jobs[q];
+                        const int d = (int) (std::upper_bound(hp.px.begin(), hp.px.end(), g.a_off) - hp.px.begin()) - 1;
+                        if (hp.owner[d] == hp.rank) continue;
+                        if (hp.owner[d] >= 0) { if (final_step[d] >= 0) deps.push_back(final_step[d]); continue; }
+                        const long long nsrow = hp.pi[d + 1] - hp.pi[d];
+                        const int c0 = (int) ((g.a_off - hp.px[d]) / nsrow);
+                        for (int J = c0 / NB_MID; J <= (c0 + g.K - 1) / NB_MID; J++) {
+                            if (J % hp.nranks == hp.rank) continue;
+                            auto it = panel_step.find({d, J});
+                            if (it != panel_step.end()) deps.push_back(it->second);
+                        }
+                    }
+                }
+                std::sort(deps.begin(), deps.end());
+                deps.erase(std::unique(deps.begin(), deps.end()), deps.end());
+                for (int dep : deps) if (dep >= (int) k) { hp.error = "internal: a step reads a range that is finished later"; return false; }
+            }
+        }
         hp.lpx.assign(nsuper + 1, -1);
         long long pos = 0;
         for (int t = 0; t < (int) nsuper; t++) {
@@ -840,9 +880,20 @@ extern "C" long long ssb200_export_compact_fetch(long long *lpx, long long *piec
         for (const auto &pc : hp.step_recv[k]) { pieces[3 * q] = (long long) k; pieces[3 * q + 1] = pc.home_off; pieces[3 * q + 2] = pc.cnt; q++; }
     for (size_t k = 0; k < hp.step_next.size(); k++) step_next[k] = hp.step_next[k];
     const long long nsj = (long long) hp.solve_jobs.size();
+    if (!lpx && !pieces) return nsj;
     if (solve && solve_cap >= nsj)
         for (long long t = 0; t < nsj; t++) { solve[4 * t] = hp.solve_jobs[t].x_off; solve[4 * t + 1] = hp.solve_jobs[t].w; solve[4 * t + 2] = hp.solve_jobs[t].xcol0; solve[4 * t + 3] = hp.solve_jobs[t].rows_below; }
     return nsj;
+}
+
+// (step, dependency) pairs of the compact plan: returns their number; fills out[2*i], out[2*i+1] when cap suffices
+extern "C" long long ssb200_export_compact_deps(long long *out, long long cap)
+{
+    if (!g_export || !g_export->compact) return -4;
+    long long q = 0;
+    for (size_t k = 0; k < g_export->step_deps.size(); k++)
+        for (int d : g_export->step_deps[k]) { if (out && q < cap) { out[2 * q] = (long long) k; out[2 * q + 1] = d; } q++; }
+    return q;
 }
 
 // launches[nl*7] = kind, job0, njobs, phase, stream, wait_ev, rec_ev; gemm[ng*8] = a_off,c_off,map_off,lda,ldc,K,nd1,nd2; panel arrays [..*6] = x_off,lda,w,

@@ -40,13 +40,17 @@ def export_plan_compact(n, super_, pi, px, s, nranks, rank):
     nsj = lib.ssb200_export_compact_fetch(P(lpx), P(pieces), P(nxt), None, C.c_int64(0))
     solve = np.zeros((max(int(nsj), 1), 4), np.int64)
     lib.ssb200_export_compact_fetch(P(lpx), P(pieces), P(nxt), P(solve), C.c_int64(nsj))
+    lib.ssb200_export_compact_deps.restype = C.c_int64
+    nd = lib.ssb200_export_compact_deps(None, C.c_int64(0))
+    deps = np.zeros((max(int(nd), 1), 2), np.int64)
+    lib.ssb200_export_compact_deps(P(deps), C.c_int64(nd))
     out = dict(launches=np.zeros((nl, 7), np.int64), gemm=np.zeros((ng, 8), np.int64), potrf=np.zeros((npo, 6), np.int64),
                trsm=np.zeros((nt, 6), np.int64), steps=np.zeros((ns, 7), np.int64), updates=np.zeros((nu, 6), np.int64),
                owner=np.zeros(len(super_) - 1, np.int32))
     rc = lib.ssb200_export_fetch(*[P(out[k]) for k in ("launches", "gemm", "potrf", "trsm", "steps", "updates", "owner")])
     assert rc == 0
     out.update(relmap_size=int(sizes[6]), nlevels=int(sizes[7]), nranks=nranks, rank=rank, lpx=lpx, lxsize=int(cs[0]),
-               pieces=pieces[:int(cs[1])], step_next=nxt[:ns], solve=solve[:int(nsj)])
+               pieces=pieces[:int(cs[1])], step_next=nxt[:ns], solve=solve[:int(nsj)], deps=deps[:int(nd)])
     return out
 
 
@@ -71,10 +75,14 @@ def assemble_compact(plan, super_, pi, px, s, S_lower, Lx):
                         Lx[lpx[sn] + pos + (k - k1) * nsrow] = Sx[p]
 
 
-def run_lockstep_compact(plans, rel, Lx, px):
+def run_lockstep_compact(plans, rel, Lx, px, selective=False):
     """Distributed storage, all ranks in one process, asynchronous pulls: a pull snapshots the source's range when the step's
-    range becomes final and is delivered at the next wait_remote step (or the end).  Returns doubles pulled per rank."""
+    range becomes final and is delivered as LATE as the schedule allows: at the next wait_remote step, or - selective - only
+    when the receiving rank reaches a step that names the pull's step as a dependency (what ssb200_mg_factorize waits for).
+    A missing dependency shows up as a wrong factor.  Returns doubles pulled per rank."""
     nr = len(plans)
+    if selective:
+        return _run_lockstep_compact_selective(plans, rel, Lx, px)
     pending = []
     pulled = [0] * nr
     loc = lambda pl, home: int(pl["lpx"][np.searchsorted(px, home, side="right") - 1] + home - px[np.searchsorted(px, home, side="right") - 1])
@@ -104,6 +112,40 @@ def run_lockstep_compact(plans, rel, Lx, px):
             run_launches(plans[r], rel, Lx[r], mid, hi)
     for r, dst, data in pending:
         Lx[r][dst: dst + len(data)] = data
+    return pulled
+
+
+def _run_lockstep_compact_selective(plans, rel, Lx, px):
+    nr = len(plans)
+    pulled = [0] * nr
+    loc = lambda pl, home: int(pl["lpx"][np.searchsorted(px, home, side="right") - 1] + home - px[np.searchsorted(px, home, side="right") - 1])
+    by_step = [dict() for _ in range(nr)]; deps = [dict() for _ in range(nr)]
+    for r in range(nr):
+        for k, ho, cnt in plans[r]["pieces"]:
+            by_step[r].setdefault(int(k), []).append((int(ho), int(cnt)))
+        for k, d in plans[r]["deps"]:
+            deps[r].setdefault(int(k), []).append(int(d))
+    pending = [dict() for _ in range(nr)]                 # per rank: step -> [(dst, data)]
+    for k in range(len(plans[0]["steps"])):
+        src = int(plans[0]["steps"][k][3])
+        for r in range(nr):
+            for d in deps[r].get(k, []):
+                assert d < k
+                for dst, data in pending[r].pop(d, []):
+                    Lx[r][dst: dst + len(data)] = data
+            lo, mid, hi = plans[r]["steps"][k][:3]
+            run_launches(plans[r], rel, Lx[r], lo, mid)
+        for r in range(nr):
+            for ho, cnt in by_step[r].get(k, []):
+                so = loc(plans[src], ho); dn = loc(plans[r], ho)
+                pending[r].setdefault(k, []).append((dn, Lx[src][so: so + cnt].copy())); pulled[r] += cnt
+        for r in range(nr):
+            lo, mid, hi = plans[r]["steps"][k][:3]
+            run_launches(plans[r], rel, Lx[r], mid, hi)
+    for r in range(nr):
+        for lst in pending[r].values():
+            for dst, data in lst:
+                Lx[r][dst: dst + len(data)] = data
     return pulled
 
 

@@ -90,8 +90,9 @@ def test_sharded_schedule_with_cyclic_supernode_single_process(kind, N, nr, jit)
     ch.free_sparse(S2); ch.free_factor(L)
 
 
+@pytest.mark.parametrize("selective", [False, True])
 @pytest.mark.parametrize("kind,N,nr", [("lap7", 22, 4), ("lap7", 24, 2), ("lap27", 18, 3), ("elas", 8, 3), ("lap7", 26, 8)])
-def test_distributed_storage_schedule_single_process(kind, N, nr):
+def test_distributed_storage_schedule_single_process(kind, N, nr, selective):
     """The in-process multi-GPU path (ssb200_mg_*): every rank stores only its supernodes, the cyclic ones and the remote
     supernodes its updates read; finished ranges are pulled piecewise by the ranks that read them.  Emulated ranks with
     asynchronous pulls must reproduce the oracle's factor in the gathered host copy; local storage is smaller than L;
@@ -121,7 +122,7 @@ def test_distributed_storage_schedule_single_process(kind, N, nr):
     Lx = [np.zeros(max(pl["lxsize"], 1)) for pl in plans]
     for r in range(nr):
         E.assemble_compact(plans[r], f["super"], f["pi"], f["px"], f["s"], Sl, Lx[r])
-    pulled = E.run_lockstep_compact(plans, rel, Lx, f["px"])
+    pulled = E.run_lockstep_compact(plans, rel, Lx, f["px"], selective=selective)   # selective: a pull is delivered only when a step depends on it
     host = E.gather_compact(plans, Lx, f["px"], xsize)
     assert persuper_relerr(f["px"], host, Lo) < 1e-11
     # distributed: the ranks together pull less than a full replication would move, nobody stores everything (nr > 2)

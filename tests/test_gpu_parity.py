@@ -304,6 +304,37 @@ def test_solve_leading_dimension_and_many_rhs():
     ch.free_factor(L)
 
 
+def test_block_solve_schedule(monkeypatch):
+    """SSB200_SOLVE_BLK=1: the big supernodes are solved in fused 256-column block steps (solve_blk_kernel: diagonal CTA and
+    row-tile CTAs in one launch).  Off by default (measured slower than the 64-column steps); must give the same solution,
+    for several right-hand sides, forward and backward separately."""
+    from suitesparse_b200 import gen, cholmod_host as H, plain
+    from oracle import oracle
+    monkeypatch.setenv("SSB200_SOLVE_BLK_MIN", "100")        # read when the plan is built: most supernodes of this mesh become block jobs
+    ch = H.Cholmod(gpu=True)
+    A, p = gen.make_problem("lap7", 30)
+    S = ch.sparse(A, +1); L = ch.analyze(S, p)
+    f = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in ch.factor_arrays(L).items()}
+    S2 = ch.lower_permuted(S, L); s2 = S2.contents; n = s2.nrow
+    Ap = H._np_view(s2.p, n + 1, np.int64).copy(); Ai = H._np_view(s2.i, int(Ap[n]), np.int64).copy(); Ax = H._np_view(s2.x, int(Ap[n]), np.float64).copy()
+    Sl = sp.csc_matrix((Ax, Ai, Ap), shape=(n, n))
+    pl = plain.Plan(n, f["super"], f["pi"], f["px"], f["s"])
+    st, minor, Lx = pl.factorize(Sl)
+    assert st == 0
+    rng = np.random.default_rng(42)
+    B = rng.standard_normal((n, 3))
+    ref_f = pl.solve(B, which=0); ref_b = pl.solve(B, which=1); ref = pl.solve(B, which=2)
+    n_default = pl.stats()["kernel_launches"]
+    monkeypatch.setenv("SSB200_SOLVE_BLK", "1")
+    got_f = pl.solve(B, which=0); got_b = pl.solve(B, which=1); got = pl.solve(B, which=2)
+    assert pl.stats()["kernel_launches"] < n_default                    # the other schedule really ran
+    for a, b in ((got_f, ref_f), (got_b, ref_b), (got, ref)):
+        assert np.abs(a - b).max() < 1e-11 * np.abs(b).max()
+    Yo = oracle.lsolve(f["super"], f["pi"], f["px"], f["s"], Lx, B)
+    assert np.abs(got_f - Yo).max() < 1e-10 * np.abs(Yo).max()
+    pl.close(); ch.free_sparse(S2); ch.free_factor(L)
+
+
 def test_gpu_resource_functions_and_env_switch(monkeypatch):
     """cholmod_l_gpu_* (GPU/cholmod_gpu.c:71,170,208,255,364) and CHOLMOD_USE_GPU=0 (no CPU path inside this library)."""
     from suitesparse_b200 import gen, cholmod_host as H
