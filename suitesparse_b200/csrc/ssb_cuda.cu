@@ -1120,6 +1120,7 @@ struct ssb200_mg {
     long long n = 0, xsize = 0;
     std::vector<MgDev> d;
     std::vector<cudaEvent_t> ev_ready;                    // per step: the step's range is final on its source device
+    std::atomic<long long> A_epoch{0};                    // host hand-shake: device 0 holds the matrix of this factorization
     std::vector<std::atomic<long long>> ready_epoch;      // host hand-shake: ev_ready[k] has been recorded in this epoch
     std::vector<std::atomic<long long>> arrived_epoch;    // [r * nsteps + k]
     std::vector<std::atomic<long long>> solve_epoch;      // [r * solve_stride + t]
@@ -1299,7 +1300,33 @@ extern "C" int ssb200_mg_factorize(ssb200_mg *m, int stype, const ssb_long *Ap, 
         auto fail = [&](const std::string &msg) { dv.rc = SSB_CHOLMOD_GPU_PROBLEM; dv.err = msg; abort_flag.store(1); };
 #define MG_TRY(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { fail(std::string(#expr) + ": " + cudaGetErrorString(_e)); return; } } while (0)
         MG_TRY(cudaSetDevice(dv.device));
-        if (Ap) { if (ssb200_upload_A(p, stype, Ap, Ai, Anz, Ax, ncolA, Fp, Fi, Fnz, Fx)) { fail(g_last_error); return; } }
+        if (Ap && r == 0) {
+            // the matrix crosses PCIe once (device 0); the other devices take it from there over NVLink
+            if (ssb200_upload_A(p, stype, Ap, Ai, Anz, Ax, ncolA, Fp, Fi, Fnz, Fx)) { fail(g_last_error); return; }
+            m->A_epoch.store(epoch, std::memory_order_release);
+        } else if (Ap) {
+            if (stype > 0 || (stype < 0 && ncolA != hp.n)) { fail("invalid matrix"); return; }
+            auto take = [&](CscBuf &dst, const CscBuf &src, const ssb_long *Hp, const ssb_long *Hnz, ssb_long ncol) -> bool {
+                const long long nz = Hp[ncol];
+                if (ensure_cap(p, &dst.p, &dst.capP, (size_t) ncol + 1) || ensure_cap(p, &dst.i, &dst.capI, (size_t) std::max<long long>(nz, 1)) ||
+                    ensure_cap(p, &dst.x, &dst.capX, (size_t) std::max<long long>(nz, 1))) return false;
+                if (Hnz && ensure_cap(p, &dst.nz, &dst.capNz, (size_t) std::max<long long>(ncol, 1))) return false;
+                dst.haveNz = Hnz != nullptr;
+                mg_spin_until(m->A_epoch, epoch, abort_flag);
+                if (abort_flag.load()) return false;
+                const int d0 = m->d[0].device;
+                bool ok = cudaMemcpyPeerAsync(dst.p, dv.device, src.p, d0, (ncol + 1) * sizeof(long long), p->stream) == cudaSuccess;
+                if (nz > 0) {
+                    ok = ok && cudaMemcpyPeerAsync(dst.i, dv.device, src.i, d0, nz * sizeof(long long), p->stream) == cudaSuccess;
+                    ok = ok && cudaMemcpyPeerAsync(dst.x, dv.device, src.x, d0, nz * sizeof(double), p->stream) == cudaSuccess;
+                }
+                if (Hnz) ok = ok && cudaMemcpyPeerAsync(dst.nz, dv.device, src.nz, d0, ncol * sizeof(long long), p->stream) == cudaSuccess;
+                return ok;
+            };
+            if (!take(*p->bufA, *m->d[0].plan->bufA, Ap, Anz, ncolA)) { if (!abort_flag.load()) fail("matrix transfer from device 0 failed"); return; }
+            if (stype == 0 && !take(*p->bufF, *m->d[0].plan->bufF, Fp, Fnz, hp.n)) { if (!abort_flag.load()) fail("matrix transfer from device 0 failed"); return; }
+            p->stype = stype; p->haveA = true;
+        }
         else if (!p->haveA) { fail("no matrix on the devices yet"); return; }      // Ap == NULL: the matrix of the previous call
         p->stats.kernel_launches = 0; p->factor_on_device = false;
         if (hp.nsuper == 0) return;

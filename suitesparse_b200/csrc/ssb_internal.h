@@ -135,7 +135,8 @@ struct HostPlan {
     int n_events = 0;                    // cross-stream events of the look-ahead schedule
     // ---- elimination-tree shard over several GPUs (one process per GPU) -------------------------------------
     int nranks = 1, rank = 0;
-    std::vector<int> owner;              // per supernode: rank that computes it, or -1 = its 256-column panels are cyclic over ranks
+    std::vector<int> owner;              // per supernode: rank that computes it, or < 0: its 256-column panels are cyclic over the
+                                         // ranks, panel J belongs to rank (J + offset) mod nranks with offset = -1 - owner
     std::vector<DistStep> steps;         // launches [begin,end) of this rank, then an optional broadcast of a finished Lx range
     double my_flops = 0;                 // dense flops this rank executes
     // ---- distributed storage (multi-GPU inside one process): a rank stores only the supernodes it owns, the panel-cyclic
@@ -179,6 +180,8 @@ int winv_slot_of(const HostPlan &hp, int s, int j0);
 void append_factor_jobs(const HostPlan &hp, const std::vector<int> &snodes, int ncol_limit, HostPlan &out, bool panel_copies = false,
                         int only_panel_J0 = -1, bool lookahead = false, int after_ev = -1);
 
+int cyc_offset(const HostPlan &hp, int sn);
+int panel_owner(const HostPlan &hp, int sn, int J);
 int gemm_tile_size(int kind);       // 128 for L_GEMM_BIG, 64 for L_GEMM_SMALL
 
 }  // namespace ssb

@@ -901,7 +901,7 @@ __global__ void scatter_A_kernel(DevSym sym, int stype, DevCsc A, DevCsc F, doub
     const int k1 = sym.super[s];
     if (owner) {        // sharded factorization: only the rank that computes this column assembles it
         const int o = owner[s];
-        if (o >= 0 ? (o != rank) : ((int) ((k - k1) / NB_MID) % nranks != rank)) return;
+        if (o >= 0 ? (o != rank) : (((int) ((k - k1) / NB_MID) + (-1 - o)) % nranks != rank)) return;      // cyclic: owner = -1 - offset
     }
     const long long psi = sym.pi[s];
     const int nsrow = (int) (sym.pi[s + 1] - psi);

@@ -30,6 +30,10 @@ int winv_slot_of(const HostPlan &hp, int s, int j0)
     return hp.winv_base[s] + j0 / NB_INNER;
 }
 
+// Panel-cyclic supernodes: owner[sn] = -1 - offset, panel J belongs to rank (J + offset) mod nranks
+int cyc_offset(const HostPlan &hp, int sn) { return -1 - hp.owner[sn]; }
+int panel_owner(const HostPlan &hp, int sn, int J) { return (J + cyc_offset(hp, sn)) % hp.nranks; }
+
 namespace {
 
 // Append one launch of gemm jobs (already final except tile_start) of a given kind; builds the tile->job array.
@@ -373,6 +377,10 @@ bool build_host_plan(long long n, long long nsuper, const long long *super, cons
         // keeps going down.
         const double rate = dist_rate;
         const double tau = dist_tau;
+        bool balance_global = false;
+        if (const char *e = getenv("SSB200_DIST_BALANCE")) balance_global = atoi(e) != 0;
+        int cyc_min_cols = 2 * NB_MID;                  // narrower supernodes are never shared (tests lower it)
+        if (const char *e = getenv("SSB200_DIST_CYC_MIN")) cyc_min_cols = std::max(2, atoi(e));
         std::vector<std::vector<int>> top_by_level(hp.nlevels);
         for (int t = 0; t < (int) nsuper; t++) if (in_top[t]) top_by_level[hp.level[t]].push_back(t);
         for (int l = 0; l < hp.nlevels; l++) {
@@ -389,6 +397,11 @@ bool build_host_plan(long long n, long long nsuper, const long long *super, cons
                 if (assign) assign->assign(v.size(), -1);
                 for (int i = ncyc; i < (int) v.size(); i++) {
                     int q = 0;
+                    if (balance_global) {
+                        // the ranks are not in lock step (a step only waits for the data it reads): balance the work a rank has
+                        // been given so far, subtrees included, not just this level's
+                        for (int r = 1; r < hp.nranks; r++) if (load[r] + lvl[r] < load[q] + lvl[q]) q = r;
+                    } else
                     for (int r = 1; r < hp.nranks; r++) if (lvl[r] < lvl[q] || (lvl[r] == lvl[q] && load[r] < load[q])) q = r;
                     lvl[q] += sn_flops[v[i]];
                     if (assign) (*assign)[i] = q;
@@ -401,14 +414,18 @@ bool build_host_plan(long long n, long long nsuper, const long long *super, cons
             double best = model(0, nullptr);
             for (int c = 1; c <= (int) v.size(); c++) {
                 const int nscol = hp.super[v[c - 1] + 1] - hp.super[v[c - 1]];
-                if (nscol < 2 * NB_MID) break;
+                if (nscol < cyc_min_cols) break;
                 const double t1 = model(c, nullptr);
                 if (t1 < best) { best = t1; ncyc = c; }
             }
             std::vector<int> assign;
             model(ncyc, &assign);
-            for (int i = 0; i < (int) v.size(); i++) {
-                hp.owner[v[i]] = assign[i];
+            int ncyc_level = 0;
+            for (int i = 0; i < (int) v.size(); i++) if (assign[i] < 0) ncyc_level++;
+            const int stride = std::max(1, hp.nranks / std::max(1, ncyc_level));
+            for (int i = 0, c = 0; i < (int) v.size(); i++) {
+                // cyclic: owner = -1 - offset; the level's cyclic supernodes start their panel chains on different ranks
+                hp.owner[v[i]] = assign[i] >= 0 ? assign[i] : -1 - ((c++ * stride) % hp.nranks);
                 if (assign[i] >= 0) load[assign[i]] += sn_flops[v[i]];
             }
         }
@@ -483,7 +500,7 @@ bool build_host_plan(long long n, long long nsuper, const long long *super, cons
                     const int blk = (rows[jlo] - k1) / NB_MID;
                     int jhi = jlo + 1;
                     while (jhi < u.nd1 && (rows[jhi] - k1) / NB_MID == blk) jhi++;
-                    if (blk % hp.nranks == hp.rank) {
+                    if (panel_owner(hp, u.s, blk) == hp.rank) {
                         GemmJob h = g;
                         h.a_off += jlo; h.map_off += jlo; h.nd1 = jhi - jlo; h.nd2 = u.nd2 - jlo;
                         hp.my_flops += 2.0 * ndcol * ((double) h.nd1 * h.nd2 - 0.5 * (double) h.nd1 * (h.nd1 - 1));
@@ -542,69 +559,84 @@ bool build_host_plan(long long n, long long nsuper, const long long *super, cons
         if (hp.nranks > 1) {
             // panel-cyclic supernodes of this level, with a look-ahead of one panel: the owner of panel J+1 first brings that
             // panel up to date with panel J and factorizes it, the broadcast of panel J+1 starts, and only then everybody
-            // runs the rest of the trailing update with panel J (which overlaps the broadcast).
+            // runs the rest of the trailing update with panel J (which overlaps the broadcast).  The level's cyclic supernodes
+            // are independent: their panel chains are INTERLEAVED (panel J of every supernode, then panel J+1 ...), and their
+            // panel owners are staggered (owner = (J + offset) mod nranks), so that different ranks work on different chains
+            // at the same time and one chain's latency (factor + transfer) is hidden behind the others.
+            struct Cyc { int sn, nscol, npan, off; long long nsrow; bool jit; };
+            std::vector<Cyc> cyc;
             for (int t = hp.level_ptr[l]; t < hp.level_ptr[l + 1]; t++) {
                 const int sn = hp.level_nodes[t];
                 if (hp.owner[sn] >= 0) continue;
-                const int nscol = hp.super[sn + 1] - hp.super[sn];
-                const long long nsrow = hp.pi[sn + 1] - hp.pi[sn];
-                const int npan = (nscol + NB_MID - 1) / NB_MID;
-                std::vector<int> one{sn};
-                auto panel_w = [&](int J) { return std::min(NB_MID, nscol - J * NB_MID); };
-                auto factor_panel = [&](int J) {
-                    const int J0 = J * NB_MID, W = panel_w(J);
-                    append_factor_jobs(hp, one, -1, hp, false, J0);
-                    hp.my_flops += (double) W * W * W / 3.0 + (double) W * W * (nsrow - J0 - W);
-                };
-                auto update_block = [&](int J, int J1) {       // block J1 -= panel J contribution
-                    const int J0 = J * NB_MID, C0 = J1 * NB_MID, W = panel_w(J), W1 = panel_w(J1);
-                    GemmJob g{};
-                    g.a_off = hp.px[sn] + C0 + (long long) J0 * nsrow;
-                    g.c_off = hp.px[sn] + C0 + (long long) C0 * nsrow;
-                    g.map_off = -1; g.lda = (int) nsrow; g.ldc = (int) nsrow; g.K = W; g.nd1 = W1; g.nd2 = (int) (nsrow - C0); g.atomic = 1;
-                    hp.my_flops += 2.0 * W * ((double) g.nd1 * g.nd2 - 0.5 * (double) g.nd1 * (g.nd1 - 1));
-                    route_gemm(g, gs, gb);
-                };
-                auto descendant_updates = [&](int J) {         // this rank's descendant updates into panel J (it owns J)
-                    auto it = cyc_jobs.find({sn, J});
-                    if (it == cyc_jobs.end()) return;
-                    for (const GemmJob &h : it->second) route_gemm(h, gs, gb);
-                    cyc_jobs.erase(it);
-                    emit_update_launches(hp, gs, gb, 0);
-                };
+                Cyc c; c.sn = sn; c.nscol = hp.super[sn + 1] - hp.super[sn]; c.nsrow = hp.pi[sn + 1] - hp.pi[sn];
+                c.npan = (c.nscol + NB_MID - 1) / NB_MID; c.off = cyc_offset(hp, sn);
                 // Just-in-time descendant updates only pay when the panel chain is the bottleneck, i.e. when a rank's share of
                 // the trailing update per panel is shorter than a panel step; otherwise one big up-front launch is more
                 // efficient (measured: 8 GPUs 324 -> 296 ms with, 2 GPUs 670 -> 697 ms with).
-                const double own_flops = (double) nscol * nscol * nscol / 3.0 + (double) nscol * nscol * (double) (nsrow - nscol);
-                bool jit = own_flops / (hp.nranks * dist_rate * npan) < dist_tau;
-                if (const char *e = getenv("SSB200_DIST_JIT")) jit = atoi(e) != 0;      // tests force either schedule
-                // prologue: every rank brings its FIRST panel (or, without jit, all its panels) up to date with the
-                // descendants, rank 0 factorizes panel 0
-                if (jit) { if (hp.rank < npan) descendant_updates(hp.rank); }
-                else {
-                    for (int J = hp.rank; J < npan; J += hp.nranks) {
-                        auto it = cyc_jobs.find({sn, J});
+                const double own_flops = (double) c.nscol * c.nscol * c.nscol / 3.0 + (double) c.nscol * c.nscol * (double) (c.nsrow - c.nscol);
+                c.jit = own_flops / (hp.nranks * dist_rate * c.npan) < dist_tau;
+                if (const char *e = getenv("SSB200_DIST_JIT")) c.jit = atoi(e) != 0;      // tests force either schedule
+                cyc.push_back(c);
+            }
+            auto panel_w = [&](const Cyc &c, int J) { return std::min(NB_MID, c.nscol - J * NB_MID); };
+            auto factor_panel = [&](const Cyc &c, int J) {
+                const int J0 = J * NB_MID, W = panel_w(c, J);
+                std::vector<int> one{c.sn};
+                append_factor_jobs(hp, one, -1, hp, false, J0);
+                hp.my_flops += (double) W * W * W / 3.0 + (double) W * W * (c.nsrow - J0 - W);
+            };
+            auto update_block = [&](const Cyc &c, int J, int J1) {       // block J1 -= panel J contribution
+                const int J0 = J * NB_MID, C0 = J1 * NB_MID, W = panel_w(c, J), W1 = panel_w(c, J1);
+                GemmJob g{};
+                g.a_off = hp.px[c.sn] + C0 + (long long) J0 * c.nsrow;
+                g.c_off = hp.px[c.sn] + C0 + (long long) C0 * c.nsrow;
+                g.map_off = -1; g.lda = (int) c.nsrow; g.ldc = (int) c.nsrow; g.K = W; g.nd1 = W1; g.nd2 = (int) (c.nsrow - C0); g.atomic = 1;
+                hp.my_flops += 2.0 * W * ((double) g.nd1 * g.nd2 - 0.5 * (double) g.nd1 * (g.nd1 - 1));
+                route_gemm(g, gs, gb);
+            };
+            auto descendant_updates = [&](const Cyc &c, int J) {         // this rank's descendant updates into panel J (it owns J)
+                auto it = cyc_jobs.find({c.sn, J});
+                if (it == cyc_jobs.end()) return;
+                for (const GemmJob &h : it->second) route_gemm(h, gs, gb);
+                cyc_jobs.erase(it);
+                emit_update_launches(hp, gs, gb, 0);
+            };
+            auto owner_of = [&](const Cyc &c, int J) { return (J + c.off) % hp.nranks; };
+            // prologues: every rank brings its FIRST panel (or, without jit, all its panels) up to date with the descendants,
+            // the owner of panel 0 factorizes it
+            for (const Cyc &c : cyc) {
+                if (c.jit) {
+                    const int Jfirst = ((hp.rank - c.off) % hp.nranks + hp.nranks) % hp.nranks;
+                    if (Jfirst < c.npan) descendant_updates(c, Jfirst);
+                } else {
+                    for (int J = 0; J < c.npan; J++) {
+                        if (owner_of(c, J) != hp.rank) continue;
+                        auto it = cyc_jobs.find({c.sn, J});
                         if (it == cyc_jobs.end()) continue;
                         for (const GemmJob &h : it->second) route_gemm(h, gs, gb);
                         cyc_jobs.erase(it);
                     }
                     emit_update_launches(hp, gs, gb, 0);
                 }
-                if (0 % hp.nranks == hp.rank) factor_panel(0);
-                close_step(step_begin, 0, hp.px[sn], (long long) panel_w(0) * nsrow, l);
-                for (int J = 0; J < npan; J++) {
-                    const bool own_next = (J + 1 < npan) && ((J + 1) % hp.nranks == hp.rank);
-                    if (own_next) { update_block(J, J + 1); emit_update_launches(hp, gs, gb, 1); factor_panel(J + 1); }
+                if (owner_of(c, 0) == hp.rank) factor_panel(c, 0);
+                close_step(step_begin, owner_of(c, 0), hp.px[c.sn], (long long) panel_w(c, 0) * c.nsrow, l);
+            }
+            int maxpan = 0;
+            for (const Cyc &c : cyc) maxpan = std::max(maxpan, c.npan);
+            for (int J = 0; J < maxpan; J++)
+                for (const Cyc &c : cyc) {
+                    if (J >= c.npan) continue;
+                    const bool own_next = (J + 1 < c.npan) && (owner_of(c, J + 1) == hp.rank);
+                    if (own_next) { update_block(c, J, J + 1); emit_update_launches(hp, gs, gb, 1); factor_panel(c, J + 1); }
                     step_mid = (int) hp.launches.size();
-                    for (int J1 = J + 2; J1 < npan; J1++) if (J1 % hp.nranks == hp.rank) update_block(J, J1);
+                    for (int J1 = J + 2; J1 < c.npan; J1++) if (owner_of(c, J1) == hp.rank) update_block(c, J, J1);
                     emit_update_launches(hp, gs, gb, 1);
                     // the owner of panel J has just finished its turn in the chain: its NEXT panel (J + nranks) gets its
                     // descendant updates now, nranks-1 steps before it is needed
-                    if (jit && J % hp.nranks == hp.rank && J + hp.nranks < npan) descendant_updates(J + hp.nranks);
-                    if (J + 1 < npan) close_step(step_begin, (J + 1) % hp.nranks, hp.px[sn] + (long long) (J + 1) * NB_MID * nsrow, (long long) panel_w(J + 1) * nsrow, l);
+                    if (c.jit && owner_of(c, J) == hp.rank && J + hp.nranks < c.npan) descendant_updates(c, J + hp.nranks);
+                    if (J + 1 < c.npan) close_step(step_begin, owner_of(c, J + 1), hp.px[c.sn] + (long long) (J + 1) * NB_MID * c.nsrow, (long long) panel_w(c, J + 1) * c.nsrow, l);
                     else close_step(step_begin, -1, 0, 0, l);
                 }
-            }
             // finished subtrees / narrow top supernodes of this level: replicate them
             for (int t = hp.level_ptr[l]; t < hp.level_ptr[l + 1]; t++) {
                 const int sn = hp.level_nodes[t];
@@ -635,7 +667,7 @@ bool build_host_plan(long long n, long long nsuper, const long long *super, cons
                 if (nscol <= j0) continue;
                 if (hp.compact) {
                     const int o = hp.owner[sn];
-                    if (o >= 0 ? (o != hp.rank) : ((j0 / NB_MID) % hp.nranks != hp.rank)) continue;
+                    if (o >= 0 ? (o != hp.rank) : (panel_owner(hp, sn, j0 / NB_MID) != hp.rank)) continue;
                 }
                 const int nsrow = (int) (hp.pi[sn + 1] - hp.pi[sn]);
                 SolveJob sj{};
@@ -670,7 +702,7 @@ bool build_host_plan(long long n, long long nsuper, const long long *super, cons
         auto mine = [&](int sn, int j0) {
             if (!hp.compact) return true;
             const int o = hp.owner[sn];
-            return o >= 0 ? (o == hp.rank) : ((j0 / NB_MID) % hp.nranks == hp.rank);
+            return o >= 0 ? (o == hp.rank) : (panel_owner(hp, sn, j0 / NB_MID) == hp.rank);
         };
         for (int j0 = 0; j0 < maxsmall; j0 += NB_INNER) {
             SolveStep st{(long long) hp.solve2_jobs.size(), 0, (long long) hp.solve2_tiles.size(), 0};
@@ -752,7 +784,7 @@ bool build_host_plan(long long n, long long nsuper, const long long *super, cons
                         const long long nsrow = hp.pi[d + 1] - hp.pi[d];
                         const int c0 = (int) ((g.a_off - hp.px[d]) / nsrow);
                         for (int J = c0 / NB_MID; J <= (c0 + g.K - 1) / NB_MID; J++) {
-                            if (J % hp.nranks == hp.rank) continue;
+                            if (panel_owner(hp, d, J) == hp.rank) continue;
                             auto it = panel_step.find({d, J});
                             if (it != panel_step.end()) deps.push_back(it->second);
                         }
@@ -797,7 +829,7 @@ bool build_host_plan(long long n, long long nsuper, const long long *super, cons
                 const long long nsrow = hp.pi[t0 + 1] - hp.pi[t0];
                 const int nscol = hp.super[t0 + 1] - hp.super[t0];
                 const int J = (int) ((st.off - hp.px[t0]) / ((long long) NB_MID * nsrow));
-                if ((J + 1) * NB_MID < nscol) hp.step_next[k] = (J + 1) % hp.nranks;
+                if ((J + 1) * NB_MID < nscol) hp.step_next[k] = panel_owner(hp, t0, J + 1);
                 continue;
             }
             long long run_off = -1, run_end = -1;

@@ -64,7 +64,7 @@ def assemble_compact(plan, super_, pi, px, s, S_lower, Lx):
         rows = s[pi[sn]: pi[sn + 1]]; nsrow = len(rows)
         o = plan["owner"][sn]
         for k in range(k1, k2):
-            if (o != plan["rank"]) if o >= 0 else (((k - k1) // NB_MID) % plan["nranks"] != plan["rank"]):
+            if (o != plan["rank"]) if o >= 0 else (((k - k1) // NB_MID + (-1 - o)) % plan["nranks"] != plan["rank"]):
                 continue
             assert lpx[sn] >= 0
             for p in range(Sp[k], Sp[k + 1]):
@@ -184,7 +184,7 @@ def assemble(plan, super_, pi, px, s, S_lower, Lx, beta=0.0):
         rows = s[pi[sn]: pi[sn + 1]]; nsrow = len(rows)
         for k in range(k1, k2):
             o = plan["owner"][sn]
-            if plan["nranks"] > 1 and (o != plan["rank"] if o >= 0 else ((k - k1) // NB_MID) % plan["nranks"] != plan["rank"]):
+            if plan["nranks"] > 1 and (o != plan["rank"] if o >= 0 else ((k - k1) // NB_MID + (-1 - o)) % plan["nranks"] != plan["rank"]):
                 continue
             for p in range(Sp[k], Sp[k + 1]):
                 i = Si[p]

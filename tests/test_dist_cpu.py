@@ -91,7 +91,7 @@ def test_sharded_schedule_with_cyclic_supernode_single_process(kind, N, nr, jit)
 
 
 @pytest.mark.parametrize("selective", [False, True])
-@pytest.mark.parametrize("kind,N,nr", [("lap7", 22, 4), ("lap7", 24, 2), ("lap27", 18, 3), ("elas", 8, 3), ("lap7", 26, 8)])
+@pytest.mark.parametrize("kind,N,nr", [("lap7", 22, 4), ("lap7", 24, 2), ("lap27", 18, 3), ("elas", 8, 3), ("lap7", 26, 8), ("lap7", 34, 3)])
 def test_distributed_storage_schedule_single_process(kind, N, nr, selective):
     """The in-process multi-GPU path (ssb200_mg_*): every rank stores only its supernodes, the cyclic ones and the remote
     supernodes its updates read; finished ranges are pulled piecewise by the ranks that read them.  Emulated ranks with
@@ -113,11 +113,21 @@ def test_distributed_storage_schedule_single_process(kind, N, nr, selective):
     Sl = sp.csc_matrix((Ax, Ai, Ap), shape=(n, n))
     st, minor, Lo = oracle.factorize(n, f["super"], f["pi"], f["px"], f["s"], Sl)
     os.environ["SSB200_DIST_TAU"] = "0"
+    if N == 34:
+        # three supernodes of 255-289 columns on one level become panel-cyclic too: their chains are interleaved and start on
+        # different ranks
+        os.environ["SSB200_DIST_CYC_MIN"] = "200"
     try:
         plans = [E.export_plan_compact(n, f["super"], f["pi"], f["px"], f["s"], nr, r) for r in range(nr)]
     finally:
         del os.environ["SSB200_DIST_TAU"]
+        os.environ.pop("SSB200_DIST_CYC_MIN", None)
     xsize = int(f["px"][-1])
+    if N == 34:
+        # two panel-cyclic supernodes on one level (the children of the root separator): their chains are interleaved and
+        # start on different ranks
+        cyc = np.nonzero(plans[0]["owner"] < 0)[0]
+        assert len(cyc) >= 4 and len(set(plans[0]["owner"][cyc].tolist())) >= 2, plans[0]["owner"][cyc]
     rel = E.relmap_of(plans[0], f["pi"], f["s"])
     Lx = [np.zeros(max(pl["lxsize"], 1)) for pl in plans]
     for r in range(nr):

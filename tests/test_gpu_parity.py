@@ -505,6 +505,30 @@ def test_multi_gpu_plain_layer_vs_oracle(kind, N, tau, monkeypatch):
     mg.close(); ch.free_factor(L)
 
 
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_multi_gpu_golden(path, monkeypatch):
+    """The reference-generated fixtures (tiny matrices, unsymmetric A*A' cases, not-positive-definite cases) through
+    ssb200_mg_factorize on two devices: ranks with little or no work, every assembly branch, status and minor."""
+    if _ndev() < 2:
+        pytest.skip("needs two or more GPUs")
+    from suitesparse_b200 import plain
+    monkeypatch.setenv("SSB200_DIST_TAU", "0")
+    g = load_golden(path)
+    S, F = golden_matrix(g)
+    mg = plain.MultiGpu(int(g["n"]), g["super"], g["pi"], g["px"], g["s"], ndev=2)
+    host = np.zeros(max(mg.xsize, 1))
+    st, minor = mg.factorize(S, beta=float(g["beta"]), Lx_host=host, F=F)
+    assert st == int(g["status"]) and minor == int(g["minor"])
+    if st == 0:
+        assert persuper_relerr(g["px"], host[:mg.xsize], g["Lx"]) < TOL_L
+        if g["x"].size:
+            perm = g["Perm"]
+            y = mg.solve(g["b"][perm], which=2)
+            x = np.empty_like(y); x[perm] = y
+            assert np.abs(x - g["x"]).max() <= TOL_X * max(1.0, np.abs(g["x"]).max())
+    mg.close()
+
+
 def test_multi_gpu_dropin_symbols(monkeypatch):
     """cholmod_l_factorize / cholmod_l_solve through the host library with SSB200_DEVICES=all: the interposed symbols fan
     out over every device; a matrix that is not positive definite falls back to the single-GPU protocol."""
