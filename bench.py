@@ -369,6 +369,10 @@ def main_mg(args, torch, dist, dev, rank, world, local, workload):
         if not args.no_extra and world >= 2:
             # BASELINE configs[3], second half: elasticity 100^3 x 3 DOF on 2 B200 (factor resident, distributed)
             out["extra_configs"] = [run_extra("elas", 100, ndev=2)]
+            if world >= 8:
+                # a factor LARGER than one GPU's HBM: 7-point 208^3, L = 213 GB, distributed over the 8 devices (own supernodes,
+                # trailing rows of the remote ones a rank reads, own panels of the root + a ring for the others)
+                out["extra_configs"].append(run_extra("lap7", 208, ndev=8))
         print(json.dumps(out), flush=True)
     barrier(); dist.destroy_process_group()
 

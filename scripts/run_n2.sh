@@ -1,3 +1,2 @@
 (timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "multi_gpu" 2>&1 | tail -6)
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 5 --warmup 3 --no-extra > gpurun_out/r2_bench_n2.json 2> gpurun_out/r2_bench_n2.err
-tail -c 1500 gpurun_out/r2_bench_n2.json | head -c 700; echo; tail -2 gpurun_out/r2_bench_n2.err
+timeout 300 python scripts/mg_bench.py lap7 128 2 2 0 2>&1 | tail -1

@@ -200,7 +200,13 @@ static int plan_build_device(ssb200_plan *p)
     if (configure_kernels_once()) return SSB_CHOLMOD_GPU_PROBLEM;
     if (dev_alloc_copy(p, &p->d_super, hp.super)) return SSB_CHOLMOD_GPU_PROBLEM;
     if (dev_alloc_copy(p, &p->d_pi, hp.pi)) return SSB_CHOLMOD_GPU_PROBLEM;
-    if (dev_alloc_copy(p, &p->d_px, hp.compact ? hp.lpx : hp.px)) return SSB_CHOLMOD_GPU_PROBLEM;   // distributed storage: local offsets
+    {
+        // distributed storage: local offsets; a transient root is marked -2 - (base of its packed own panels) for scatter_A_kernel
+        std::vector<long long> dpx = hp.compact ? hp.lpx : hp.px;
+        if (hp.compact) for (long long t = 0; t < hp.nsuper; t++) if (hp.transient[t]) dpx[t] = -2 - hp.tr_own_base[t];
+        if (dev_alloc_copy(p, &p->d_px, dpx)) return SSB_CHOLMOD_GPU_PROBLEM;
+        CU_TRY(cudaStreamSynchronize(p->stream));           // dpx is a temporary
+    }
     if (dev_alloc_copy(p, &p->d_ls, hp.ls)) return SSB_CHOLMOD_GPU_PROBLEM;
     if (dev_alloc_copy(p, &p->d_supermap, hp.supermap)) return SSB_CHOLMOD_GPU_PROBLEM;
     if (hp.nranks > 1) if (dev_alloc_copy(p, &p->d_owner, hp.owner)) return SSB_CHOLMOD_GPU_PROBLEM;
@@ -1067,12 +1073,16 @@ extern "C" ssb_long ssb200_debug_relmap(ssb200_plan *p, int32_t *out, ssb_long c
 // ===============================================================================================================
 struct MgPiece { long long src_off, dst_off, cnt; };
 
-// chunks of <= MG_CHUNK doubles; one CTA per chunk (grid-stride); 16-byte accesses when both sides are aligned
-constexpr int MG_CHUNK = 16384, MG_THREADS = 256;
+// chunks of <= MG_CHUNK doubles, one WARP per chunk (grid-stride over warps): the pieces range from whole panels to the
+// trailing rows of one 16-column supernode column (a few hundred doubles), so the unit of work is small; 8 loads in flight
+// per lane (16-byte when both sides are aligned) keep ~2 MB in flight per device with 64 CTAs
+constexpr int MG_CHUNK = 4096, MG_THREADS = 256;
 __global__ void __launch_bounds__(MG_THREADS) mg_pull_kernel(const MgPiece *__restrict__ chunks, int nchunks,
                                                             const double *__restrict__ src, double *__restrict__ dst)
 {
-    for (int c = blockIdx.x; c < nchunks; c += gridDim.x) {
+    const int lane = threadIdx.x & 31;
+    const int wid = (int) blockIdx.x * (MG_THREADS / 32) + (threadIdx.x >> 5), nw = (int) gridDim.x * (MG_THREADS / 32);
+    for (int c = wid; c < nchunks; c += nw) {
         const MgPiece pc = chunks[c];
         const double *__restrict__ sp = src + pc.src_off;
         double *__restrict__ dp = dst + pc.dst_off;
@@ -1080,20 +1090,20 @@ __global__ void __launch_bounds__(MG_THREADS) mg_pull_kernel(const MgPiece *__re
             const double2 *__restrict__ s2 = reinterpret_cast<const double2 *>(sp);
             double2 *__restrict__ d2 = reinterpret_cast<double2 *>(dp);
             const long long n2 = pc.cnt >> 1;
-            for (long long i = threadIdx.x; i < n2; i += MG_THREADS * 8) {
+            for (long long i = lane; i < n2; i += 32 * 8) {
                 double2 v[8];
 #pragma unroll
-                for (int q = 0; q < 8; q++) { const long long t = i + (long long) q * MG_THREADS; v[q] = t < n2 ? s2[t] : make_double2(0.0, 0.0); }
+                for (int q = 0; q < 8; q++) { const long long t = i + 32 * q; v[q] = t < n2 ? s2[t] : make_double2(0.0, 0.0); }
 #pragma unroll
-                for (int q = 0; q < 8; q++) { const long long t = i + (long long) q * MG_THREADS; if (t < n2) d2[t] = v[q]; }
+                for (int q = 0; q < 8; q++) { const long long t = i + 32 * q; if (t < n2) d2[t] = v[q]; }
             }
         } else {
-            for (long long i = threadIdx.x; i < pc.cnt; i += MG_THREADS * 8) {
+            for (long long i = lane; i < pc.cnt; i += 32 * 8) {
                 double v[8];
 #pragma unroll
-                for (int q = 0; q < 8; q++) { const long long t = i + (long long) q * MG_THREADS; v[q] = t < pc.cnt ? sp[t] : 0.0; }
+                for (int q = 0; q < 8; q++) { const long long t = i + 32 * q; v[q] = t < pc.cnt ? sp[t] : 0.0; }
 #pragma unroll
-                for (int q = 0; q < 8; q++) { const long long t = i + (long long) q * MG_THREADS; if (t < pc.cnt) dp[t] = v[q]; }
+                for (int q = 0; q < 8; q++) { const long long t = i + 32 * q; if (t < pc.cnt) dp[t] = v[q]; }
             }
         }
     }
@@ -1111,6 +1121,7 @@ struct MgDev {
     int rc = 0; std::string err; ssb_long bad = 0;
     double ms = 0;                                        // device time of the last factorization (assembly .. last kernel / pull)
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;         // timing
+    std::vector<cudaEvent_t> ring_ev;                     // per ring slot of a transient root: its panel has been applied
     std::vector<cudaEvent_t> ev_trace;                    // SSB200_MG_TRACE=1: one timing event per step on the compute stream
     std::vector<float> trace_ms;                          // per step: device time from the start of the factorization
 };
@@ -1147,6 +1158,7 @@ static void mg_free(ssb200_mg *m)
         if (dv.ev_t0) cudaEventDestroy(dv.ev_t0);
         if (dv.ev_t1) cudaEventDestroy(dv.ev_t1);
         for (auto e : dv.ev_trace) if (e) cudaEventDestroy(e);
+        for (auto e : dv.ring_ev) if (e) cudaEventDestroy(e);
         if (dv.d_chunks) cudaFree(dv.d_chunks);
         if (dv.comm) cudaStreamDestroy(dv.comm);
         if (dv.d2h) cudaStreamDestroy(dv.d2h);
@@ -1238,12 +1250,15 @@ extern "C" ssb200_mg *ssb200_mg_create(ssb_long n, ssb_long nsuper, const ssb_lo
             cudaEventCreateWithFlags(&dv.ev_arrived[k], cudaEventDisableTiming);
             dv.chunk0[k] = (long long) chunks.size();
             for (const HostPlan::Piece &pc : hp.step_recv[k]) {
-                // the piece starts inside supernode t; both ranks store the run [t ..] contiguously with the same inner offsets
-                const int t = (int) (std::upper_bound(hp.px.begin(), hp.px.end(), pc.home_off) - hp.px.begin()) - 1;
-                if (sp.lpx[t] < 0 || hp.lpx[t] < 0) { set_error("internal: transfer of a supernode that one side does not store"); mg_free(m); return nullptr; }
-                const long long so = sp.lpx[t] + (pc.home_off - hp.px[t]), dn = hp.lpx[t] + (pc.home_off - hp.px[t]);
-                for (long long o = 0; o < pc.cnt; o += MG_CHUNK) chunks.push_back(MgPiece{so + o, dn + o, std::min<long long>(MG_CHUNK, pc.cnt - o)});
-                m->pulled_bytes += pc.cnt * 8;
+                // 1-D piece: a run of supernodes (or a panel) that both ranks store contiguously with the same inner offsets;
+                // 2-D piece: the trailing rows of every column of one supernode (strided at the source, packed here)
+                for (int c = 0; c < pc.ncols; c++) {
+                    const long long home = pc.home_off + (long long) c * pc.src_ld;
+                    const long long so = sp.local_of(home), dn = hp.local_of(home);
+                    if (so < 0 || dn < 0) { set_error("internal: transfer of a supernode that one side does not store"); mg_free(m); return nullptr; }
+                    for (long long o = 0; o < pc.cnt; o += MG_CHUNK) chunks.push_back(MgPiece{so + o, dn + o, std::min<long long>(MG_CHUNK, pc.cnt - o)});
+                }
+                m->pulled_bytes += pc.cnt * 8 * pc.ncols;
             }
             dv.nchunk[k] = (int) (chunks.size() - dv.chunk0[k]);
         }
@@ -1348,8 +1363,15 @@ extern "C" int ssb200_mg_factorize(ssb200_mg *m, int stype, const ssb_long *Ap, 
         if (two) MG_TRY(cudaStreamWaitEvent(p->panel_stream, dv.ev_begin, 0));
         std::vector<cudaEvent_t> outstanding;
         std::vector<char> waited(ns, 0);
-        static int wait_all = -1;
-        if (wait_all < 0) { const char *v = getenv("SSB200_MG_WAIT_ALL"); wait_all = (v && atoi(v)) ? 1 : 0; }
+        static int wait_all_env = -1;
+        if (wait_all_env < 0) { const char *v = getenv("SSB200_MG_WAIT_ALL"); wait_all_env = (v && atoi(v)) ? 1 : 0; }
+        bool any_transient = false;
+        for (char c : hp.transient) any_transient = any_transient || c;
+        const bool wait_all = wait_all_env && !any_transient;      // the ring of a transient root needs the per-step dependencies
+        std::vector<int> slot_of_step(ns, -1), consumed;
+        std::vector<char> ring_busy(hp.ring_depth, 0);
+        while ((int) dv.ring_ev.size() < hp.ring_depth) { cudaEvent_t e; MG_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); dv.ring_ev.push_back(e); }
+        std::vector<cudaEvent_t> &ring_ev = dv.ring_ev;
         for (size_t k = 0; k < ns; k++) {
             if (abort_flag.load()) return;
             const DistStep &st = hp.steps[k];
@@ -1362,7 +1384,10 @@ extern "C" int ssb200_mg_factorize(ssb200_mg *m, int stype, const ssb_long *Ap, 
             } else {
                 // only the pulls whose data this step's launches read (the others keep streaming in behind the compute)
                 for (int dep : hp.step_deps[k])
-                    if (!waited[dep] && dv.ev_arrived[dep]) { MG_TRY(cudaStreamWaitEvent(p->stream, dv.ev_arrived[dep], 0)); waited[dep] = 1; }
+                    if (!waited[dep] && dv.ev_arrived[dep]) {
+                        MG_TRY(cudaStreamWaitEvent(p->stream, dv.ev_arrived[dep], 0)); waited[dep] = 1;
+                        if (slot_of_step[dep] >= 0) consumed.push_back(slot_of_step[dep]);    // this step applies a panel that sits in a ring slot
+                    }
             }
             for (int t = st.launch_begin; t < st.launch_mid; t++) if (run_launch(p, hp.launches[t], p->jobs, two)) { fail(g_last_error); return; }
             if (st.bcast_src == r) {
@@ -1370,9 +1395,8 @@ extern "C" int ssb200_mg_factorize(ssb200_mg *m, int stype, const ssb_long *Ap, 
                 m->ready_epoch[k].store(epoch, std::memory_order_release);
                 if (Lx_host && host_pinned && st.cnt > 0) {
                     // final here: this device's share of the factor goes to the host while the factorization continues
-                    const int t0 = (int) (std::upper_bound(hp.px.begin(), hp.px.end(), st.off) - hp.px.begin()) - 1;
                     MG_TRY(cudaStreamWaitEvent(dv.d2h, m->ev_ready[k], 0));
-                    MG_TRY(cudaMemcpyAsync(Lx_host + st.off, p->d_Lx + hp.lpx[t0] + (st.off - hp.px[t0]), (size_t) st.cnt * sizeof(double), cudaMemcpyDeviceToHost, dv.d2h));
+                    MG_TRY(cudaMemcpyAsync(Lx_host + st.off, p->d_Lx + hp.local_of(st.off), (size_t) st.cnt * sizeof(double), cudaMemcpyDeviceToHost, dv.d2h));
                 }
             } else if (st.bcast_src >= 0 && dv.nchunk[k] > 0) {
                 mg_spin_until(m->ready_epoch[k], epoch, abort_flag);
@@ -1384,7 +1408,18 @@ extern "C" int ssb200_mg_factorize(ssb200_mg *m, int stype, const ssb_long *Ap, 
                 // hold the panel and every NVLink port carries one copy at a time.
                 const int nxt = hp.step_next[k];
                 int from = st.bcast_src;
-                if (nxt >= 0 && N > 2) {
+                const int t_step = (int) (std::upper_bound(hp.px.begin(), hp.px.end(), st.off) - hp.px.begin()) - 1;
+                const bool tr_step = !hp.transient.empty() && hp.transient[t_step];
+                int ring_slot = -1;
+                if (tr_step) {
+                    // a panel of the transient root lands in a ring slot: its previous occupant must have been applied (the ring
+                    // slots of other ranks are not stable sources either, so everybody pulls from the owner)
+                    const long long nsrow_t = hp.pi[t_step + 1] - hp.pi[t_step];
+                    ring_slot = (int) (((st.off - hp.px[t_step]) / ((long long) NB_MID * nsrow_t)) % hp.ring_depth);
+                    if (ring_busy[ring_slot]) { MG_TRY(cudaStreamWaitEvent(dv.comm, ring_ev[ring_slot], 0)); ring_busy[ring_slot] = 0; }
+                    slot_of_step[k] = ring_slot;
+                }
+                if (nxt >= 0 && N > 2 && !tr_step) {
                     const int q = ((r - nxt) % N + N) % N - (((st.bcast_src - nxt) % N + N) % N < ((r - nxt) % N + N) % N ? 1 : 0);   // position among the receivers
                     int pw = 1; while (2 * pw <= q + 1) pw *= 2;
                     const int holder = (q + 1) - pw;                            // 0 = source, i = receiver at position i-1
@@ -1398,19 +1433,19 @@ extern "C" int ssb200_mg_factorize(ssb200_mg *m, int stype, const ssb_long *Ap, 
                     }
                 }
                 const double *src_Lx = m->d[from].plan->d_Lx;
-                if (hp.step_recv[k].size() <= 4) {
+                bool few_1d = hp.step_recv[k].size() <= 4;
+                for (const HostPlan::Piece &pc : hp.step_recv[k]) few_1d = few_1d && pc.ncols == 1;
+                if (few_1d) {
                     // a few large contiguous pieces (a panel, a whole supernode): the copy engines move them, no SM is taken
                     const HostPlan &sp = m->d[from].plan->hp;
-                    for (const HostPlan::Piece &pc : hp.step_recv[k]) {
-                        const int t0 = (int) (std::upper_bound(hp.px.begin(), hp.px.end(), pc.home_off) - hp.px.begin()) - 1;
-                        MG_TRY(cudaMemcpyPeerAsync(p->d_Lx + hp.lpx[t0] + (pc.home_off - hp.px[t0]), dv.device,
-                                                   src_Lx + sp.lpx[t0] + (pc.home_off - hp.px[t0]), m->d[from].device, (size_t) pc.cnt * sizeof(double), dv.comm));
-                    }
+                    for (const HostPlan::Piece &pc : hp.step_recv[k])
+                        MG_TRY(cudaMemcpyPeerAsync(p->d_Lx + hp.local_of(pc.home_off), dv.device, src_Lx + sp.local_of(pc.home_off), m->d[from].device,
+                                                   (size_t) pc.cnt * sizeof(double), dv.comm));
                 } else {
                     // thousands of scattered supernodes of a finished subtree: one gather kernel on peer pointers
                     static int pull_ctas = -1;
                     if (pull_ctas < 0) { const char *v = getenv("SSB200_MG_PULL_CTAS"); pull_ctas = v ? std::max(1, atoi(v)) : 64; }
-                    const int grid = std::min(dv.nchunk[k], pull_ctas);
+                    const int grid = std::min((dv.nchunk[k] + MG_THREADS / 32 - 1) / (MG_THREADS / 32), pull_ctas);
                     mg_pull_kernel<<<grid, MG_THREADS, 0, dv.comm>>>(dv.d_chunks + dv.chunk0[k], dv.nchunk[k], src_Lx, p->d_Lx);
                     p->stats.kernel_launches++;
                 }
@@ -1419,6 +1454,8 @@ extern "C" int ssb200_mg_factorize(ssb200_mg *m, int stype, const ssb_long *Ap, 
                 outstanding.push_back(dv.ev_arrived[k]);
             }
             for (int t = st.launch_mid; t < st.launch_end; t++) if (run_launch(p, hp.launches[t], p->jobs, two)) { fail(g_last_error); return; }
+            for (int sl : consumed) { MG_TRY(cudaEventRecord(ring_ev[sl], p->stream)); ring_busy[sl] = 1; }     // the slot may be overwritten after this point
+            consumed.clear();
         }
         for (cudaEvent_t e : outstanding) MG_TRY(cudaStreamWaitEvent(p->stream, e, 0));
         if (trace) MG_TRY(cudaEventRecord(dv.ev_trace[ns], p->stream));
@@ -1455,8 +1492,7 @@ extern "C" int ssb200_mg_factorize(ssb200_mg *m, int stype, const ssb_long *Ap, 
             for (size_t k = 0; k < ns; k++) {
                 const DistStep &st = hp.steps[k];
                 if (st.bcast_src != r || st.cnt <= 0) continue;
-                const int t0 = (int) (std::upper_bound(hp.px.begin(), hp.px.end(), st.off) - hp.px.begin()) - 1;
-                CU_TRY(cudaMemcpy(Lx_host + st.off, dv.plan->d_Lx + hp.lpx[t0] + (st.off - hp.px[t0]), (size_t) st.cnt * sizeof(double), cudaMemcpyDeviceToHost));
+                CU_TRY(cudaMemcpy(Lx_host + st.off, dv.plan->d_Lx + hp.local_of(st.off), (size_t) st.cnt * sizeof(double), cudaMemcpyDeviceToHost));
             }
         }
     }
@@ -1555,11 +1591,29 @@ extern "C" int ssb200_mg_upload_L(ssb200_mg *m, const double *Lx_host)
         CU_TRY(cudaSetDevice(dv.device));
         long long run_home = -1, run_loc = -1, run_cnt = 0;
         for (long long t = 0; t <= hp.nsuper; t++) {
-            const bool present = t < hp.nsuper && hp.lpx[t] >= 0;
+            const bool tr = t < hp.nsuper && !hp.transient.empty() && hp.transient[t];
+            const bool red = t < hp.nsuper && hp.lpx[t] >= 0 && !hp.rmin.empty() && hp.rmin[t] > 0;
+            const bool present = t < hp.nsuper && hp.lpx[t] >= 0 && !tr && !red;
             if (present && run_home >= 0 && hp.px[t] == run_home + run_cnt && hp.lpx[t] == run_loc + run_cnt) { run_cnt += hp.px[t + 1] - hp.px[t]; continue; }
             if (run_home >= 0) CU_TRY(cudaMemcpyAsync(dv.plan->d_Lx + run_loc, Lx_host + run_home, (size_t) run_cnt * sizeof(double), cudaMemcpyHostToDevice, dv.plan->stream));
             run_home = -1;
             if (present) { run_home = hp.px[t]; run_loc = hp.lpx[t]; run_cnt = hp.px[t + 1] - hp.px[t]; }
+            if (red) {
+                // a remote supernode stored from row rmin on: trailing rows of every column
+                const long long nsrow = hp.pi[t + 1] - hp.pi[t], ld = nsrow - hp.rmin[t];
+                CU_TRY(cudaMemcpy2DAsync(dv.plan->d_Lx + hp.lpx[t], ld * sizeof(double), Lx_host + hp.px[t] + hp.rmin[t], nsrow * sizeof(double),
+                                         ld * sizeof(double), (size_t) (hp.super[t + 1] - hp.super[t]), cudaMemcpyHostToDevice, dv.plan->stream));
+            }
+            if (tr) {
+                // transient root: only the panels this rank owns are stored
+                const long long nsrow = hp.pi[t + 1] - hp.pi[t];
+                const int nscol = hp.super[t + 1] - hp.super[t];
+                for (int J = 0; J * NB_MID < nscol; J++) {
+                    if (panel_owner(hp, (int) t, J) != hp.rank) continue;
+                    const long long home = hp.px[t] + (long long) J * NB_MID * nsrow, cnt = (long long) std::min(NB_MID, nscol - J * NB_MID) * nsrow;
+                    CU_TRY(cudaMemcpyAsync(dv.plan->d_Lx + hp.local_of(home), Lx_host + home, (size_t) cnt * sizeof(double), cudaMemcpyHostToDevice, dv.plan->stream));
+                }
+            }
         }
         CU_TRY(cudaStreamSynchronize(dv.plan->stream));
         dv.plan->factor_on_device = true; dv.plan->winv_valid = false;

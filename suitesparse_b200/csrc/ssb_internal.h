@@ -31,7 +31,9 @@ struct GemmJob {
     int tile_start;      // first tile of this job inside its launch
     int nti, ntj;        // tile rows / tile columns (tile column tj holds tiles ti = tj .. nti-1)
     int atomic;          // 1: several jobs of the launch may hit the same target entries -> red.add
-    int pad;
+    int c_col0;          // mapped jobs: column index (inside the target supernode) that c_off stands for; the relative map's
+                         // column positions are taken relative to it (a job cut to one 256-column panel of a cyclic supernode
+                         // addresses that panel only, wherever the panel is stored)
 };
 
 // One panel job of the in-supernode factorization.
@@ -145,11 +147,22 @@ struct HostPlan {
     bool compact = false;
     std::vector<long long> lpx;          // local offset of supernode t in this rank's storage, -1 = not stored here
     long long lxsize = 0;                // doubles of local factor storage
-    struct Piece { long long home_off, cnt; };
+    struct Piece { long long home_off, cnt; int ncols = 1; long long src_ld = 0; };   // ncols > 1: ncols segments of cnt doubles, src_ld apart at the
+                                                                                  // source (home offsets), back to back at the destination
     std::vector<std::vector<Piece>> step_recv;   // per step: the parts of the step's finished range this rank reads (home offsets)
     std::vector<std::vector<int>> step_deps;     // per step: the earlier steps whose (remote) finished ranges its launches read
     std::vector<int> step_next;          // per step: for a finished panel of a cyclic supernode, the owner of the next panel (-1 none)
     int top_min_level = 0;               // lowest etree level that holds a supernode above the subtree cut
+    // A panel-cyclic ROOT supernode is read by nobody but its own trailing updates: a rank keeps only the panels it owns
+    // (packed) and receives the others into a ring of `ring_depth` panel slots - a received panel is dead after the one step
+    // that applies it.  This is what lets a factor larger than one GPU's HBM be factorized (the root is the largest block).
+    // A remote supernode that this rank's updates read is stored from its first needed row on (rmin): its trailing rows only,
+    // with leading dimension nsrow - rmin (the updates of an ancestor read rows p0.. of ALL columns of a descendant).
+    std::vector<int> rmin;               // per supernode: first stored row (0: the whole block)
+    std::vector<char> transient;         // per supernode
+    std::vector<long long> tr_own_base, tr_ring_base;   // local offsets of the packed own panels / of the ring (transient supernodes)
+    int ring_depth = 4;
+    long long local_of(long long home) const;    // home offset in Lx -> offset in this rank's storage (-1: not stored here)
     // solve schedule: supernodes ordered by level
     std::vector<int> level_ptr;      // nlevels+1
     std::vector<int> level_nodes;    // supernodes sorted by level

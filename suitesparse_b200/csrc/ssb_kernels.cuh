@@ -207,7 +207,7 @@ gemm_nt_sub_kernel(const GemmJob *__restrict__ jobs, const int *__restrict__ til
             const int jl = wn0 + nn * 8 + 2 * (lane & 3) + e;
             const int j = rowB0 + jl;
             if (j >= nd1) continue;
-            double *__restrict__ colp = Cb + (mapped ? (long long) colmap[jl] * ldc : (long long) j * ldc);
+            double *__restrict__ colp = Cb + (mapped ? (long long) (colmap[jl] - job.c_col0) * ldc : (long long) j * ldc);
             if (atomic) {
 #pragma unroll
                 for (int m = 0; m < MT; m++) {
@@ -906,7 +906,16 @@ __global__ void scatter_A_kernel(DevSym sym, int stype, DevCsc A, DevCsc F, doub
     const long long psi = sym.pi[s];
     const int nsrow = (int) (sym.pi[s + 1] - psi);
     const int *__restrict__ rows = sym.ls + psi;
-    double *__restrict__ col = Lx + sym.px[s] + (k - k1) * (long long) nsrow;
+    long long base = sym.px[s] + (k - k1) * (long long) nsrow;
+    if (sym.px[s] < -1) {
+        // transient root of the multi-GPU path (px = -2 - base of the packed own panels): this rank stores only its own
+        // 256-column panels, back to back
+        const int off = -1 - owner[s];
+        const long long J = (k - k1) / NB_MID;
+        const long long Jf = ((rank - off) % nranks + nranks) % nranks;
+        base = (-2 - sym.px[s]) + ((J - Jf) / nranks) * (long long) NB_MID * nsrow + ((k - k1) - J * NB_MID) * (long long) nsrow;
+    }
+    double *__restrict__ col = Lx + base;
     if (stype != 0) {
         long long p = A.p[k];
         const long long pend = A.nz ? p + A.nz[k] : A.p[k + 1];

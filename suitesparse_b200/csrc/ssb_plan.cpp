@@ -12,6 +12,7 @@
 #include <cstring>
 #include <cstdlib>
 #include <map>
+#include <climits>
 
 namespace ssb {
 
@@ -28,6 +29,30 @@ int winv_slot_of(const HostPlan &hp, int s, int j0)
     if (nscol > NB_INNER) return hp.winv_base[s] + j0 / NB_INNER;       // wide supernode: every block (the 256-column solve needs them all)
     if (w < TRSM_TC_MIN_W || nsrow - j0 - w <= 0) return -1;
     return hp.winv_base[s] + j0 / NB_INNER;
+}
+
+long long HostPlan::local_of(long long home) const
+{
+    const int t = (int) (std::upper_bound(px.begin(), px.end(), home) - px.begin()) - 1;
+    if (t < 0 || t >= (int) nsuper || lpx[t] < 0) return -1;
+    if (!rmin.empty() && rmin[t] > 0) {
+        const long long nsrow = pi[t + 1] - pi[t];
+        const long long col = (home - px[t]) / nsrow, row = (home - px[t]) % nsrow;
+        if (row < rmin[t]) return -1;
+        return lpx[t] + col * (nsrow - rmin[t]) + (row - rmin[t]);
+    }
+    if (transient.empty() || !transient[t]) return lpx[t] + (home - px[t]);
+    const long long nsrow = pi[t + 1] - pi[t];
+    const long long col = (home - px[t]) / nsrow, row = (home - px[t]) % nsrow;
+    const int J = (int) (col / NB_MID);
+    const long long within = (col - (long long) J * NB_MID) * nsrow + row;
+    const long long P = (long long) NB_MID * nsrow;
+    const int off = -1 - owner[t];
+    if ((J + off) % nranks == rank) {
+        const int Jf = ((rank - off) % nranks + nranks) % nranks;       // this rank's first panel; its panels are Jf, Jf+nranks, ...
+        return tr_own_base[t] + (long long) ((J - Jf) / nranks) * P + within;
+    }
+    return tr_ring_base[t] + (long long) (J % ring_depth) * P + within;
 }
 
 // Panel-cyclic supernodes: owner[sn] = -1 - offset, panel J belongs to rank (J + offset) mod nranks
@@ -454,6 +479,7 @@ bool build_host_plan(long long n, long long nsuper, const long long *super, cons
     std::map<std::pair<int, int>, std::vector<GemmJob>> cyc_jobs;   // (panel-cyclic supernode, panel) -> descendant updates of this rank
     std::vector<int> nodes;
     std::vector<char> need(nsuper, 0);      // supernodes whose values this rank's updates read
+    std::vector<int> need_row(nsuper, INT_MAX);   // ... and the first row of them that is read
     int step_begin = 0;
     // Host streaming: every copy is a host-side call between kernel launches, so only the few supernodes near the root are
     // streamed panel by panel; everything up to the `flush` level goes out in merged contiguous ranges right after that
@@ -488,7 +514,7 @@ bool build_host_plan(long long n, long long nsuper, const long long *super, cons
             if (hp.owner[u.s] >= 0) {
                 if (!mine_whole(u.s)) continue;
                 hp.my_flops += 2.0 * ndcol * tri;
-                need[u.d] = 1;
+                need[u.d] = 1; need_row[u.d] = std::min(need_row[u.d], u.p0);
                 route_gemm(g, gs, gb);
             } else {
                 // panel-cyclic target: cut the update where its target column crosses a 256-column panel boundary; a cut
@@ -503,8 +529,9 @@ bool build_host_plan(long long n, long long nsuper, const long long *super, cons
                     if (panel_owner(hp, u.s, blk) == hp.rank) {
                         GemmJob h = g;
                         h.a_off += jlo; h.map_off += jlo; h.nd1 = jhi - jlo; h.nd2 = u.nd2 - jlo;
+                        h.c_off = g.c_off + (long long) blk * NB_MID * nsrow; h.c_col0 = blk * NB_MID;   // the target is panel `blk`
                         hp.my_flops += 2.0 * ndcol * ((double) h.nd1 * h.nd2 - 0.5 * (double) h.nd1 * (h.nd1 - 1));
-                        need[u.d] = 1;
+                        need[u.d] = 1; need_row[u.d] = std::min(need_row[u.d], u.p0 + jlo);
                         // not launched with the level's other updates: the descendant updates of a panel are scheduled just
                         // in time inside the panel loop, where they fill the ranks' idle time behind the serial panel chain
                         cyc_jobs[{u.s, blk}].push_back(h);
@@ -796,20 +823,50 @@ bool build_host_plan(long long n, long long nsuper, const long long *super, cons
             }
         }
         hp.lpx.assign(nsuper + 1, -1);
+        hp.transient.assign(nsuper, 0); hp.tr_own_base.assign(nsuper, -1); hp.tr_ring_base.assign(nsuper, -1);
+        {
+            int tr_on = 1, tr_min = 2 * hp.nranks;
+            if (const char *e = getenv("SSB200_MG_TRANSIENT")) tr_on = atoi(e);
+            if (const char *e = getenv("SSB200_MG_TRANSIENT_MIN")) tr_min = std::max(1, atoi(e));     // panels; tests lower it
+            if (const char *e = getenv("SSB200_MG_RING")) hp.ring_depth = std::max(2, atoi(e));
+            for (int t = 0; t < (int) nsuper && tr_on; t++) {
+                const int nscol = hp.super[t + 1] - hp.super[t];
+                if (hp.owner[t] < 0 && hp.parent[t] < 0 && (nscol + NB_MID - 1) / NB_MID >= std::max(tr_min, hp.ring_depth + 1)) hp.transient[t] = 1;
+            }
+        }
+        hp.rmin.assign(nsuper, 0);
+        {
+            int on = 1;
+            if (const char *e = getenv("SSB200_MG_TRAILING_ROWS")) on = atoi(e);
+            for (int t = 0; t < (int) nsuper && on; t++)
+                if (need[t] && hp.owner[t] >= 0 && hp.owner[t] != hp.rank && need_row[t] != INT_MAX) hp.rmin[t] = need_row[t];
+        }
         long long pos = 0;
         for (int t = 0; t < (int) nsuper; t++) {
             const bool present = hp.owner[t] == hp.rank || hp.owner[t] < 0 || need[t];
             if (!present) continue;
             hp.lpx[t] = pos;
-            pos += hp.px[t + 1] - hp.px[t];            // no padding: a run of consecutive supernodes keeps its internal offsets on every rank
+            if (hp.rmin[t] > 0) { pos += (hp.pi[t + 1] - hp.pi[t] - hp.rmin[t]) * (long long) (hp.super[t + 1] - hp.super[t]); continue; }
+            if (!hp.transient[t]) { pos += hp.px[t + 1] - hp.px[t]; continue; }   // no padding: a run of consecutive supernodes keeps its internal offsets on every rank
+            const long long nsrow = hp.pi[t + 1] - hp.pi[t];
+            const int nscol = hp.super[t + 1] - hp.super[t];
+            const int npan = (nscol + NB_MID - 1) / NB_MID;
+            hp.tr_own_base[t] = pos;
+            for (int J = 0; J < npan; J++) if (panel_owner(hp, t, J) == hp.rank) pos += (long long) std::min(NB_MID, nscol - J * NB_MID) * nsrow;
+            hp.tr_ring_base[t] = pos;
+            pos += (long long) hp.ring_depth * NB_MID * nsrow;
         }
         hp.lxsize = pos; hp.lpx[nsuper] = pos;
         auto loc = [&](long long home) -> long long {
-            const int t = (int) (std::upper_bound(hp.px.begin(), hp.px.end(), home) - hp.px.begin()) - 1;
-            if (t < 0 || t >= (int) nsuper || hp.lpx[t] < 0) { hp.error = "internal: job reads a supernode that is not stored on this rank"; return -1; }
-            return hp.lpx[t] + (home - hp.px[t]);
+            const long long v = hp.local_of(home);
+            if (v < 0) hp.error = "internal: job reads a supernode that is not stored on this rank";
+            return v;
         };
-        for (auto &g : hp.gemm_jobs) { g.a_off = loc(g.a_off); g.c_off = loc(g.c_off); }
+        for (auto &g : hp.gemm_jobs) {
+            const int d = (int) (std::upper_bound(hp.px.begin(), hp.px.end(), g.a_off) - hp.px.begin()) - 1;
+            if (hp.rmin[d] > 0) g.lda = (int) (hp.pi[d + 1] - hp.pi[d] - hp.rmin[d]);       // trailing rows only: shorter columns
+            g.a_off = loc(g.a_off); g.c_off = loc(g.c_off);
+        }
         for (auto &j : hp.potrf_jobs) j.x_off = loc(j.x_off);
         for (auto &j : hp.trsm_jobs) j.x_off = loc(j.x_off);
         for (auto &j : hp.solve_jobs) j.x_off = loc(j.x_off);
@@ -834,7 +891,14 @@ bool build_host_plan(long long n, long long nsuper, const long long *super, cons
             }
             long long run_off = -1, run_end = -1;
             for (int t = t0; t < (int) nsuper && hp.px[t] < st.off + st.cnt; t++) {
-                if (need[t]) {
+                if (need[t] && hp.rmin[t] > 0) {
+                    // trailing rows of every column: a strided (2-D) piece
+                    if (run_off >= 0) { hp.step_recv[k].push_back(HostPlan::Piece{run_off, run_end - run_off}); run_off = -1; }
+                    const long long nsrow = hp.pi[t + 1] - hp.pi[t];
+                    HostPlan::Piece pc{hp.px[t] + hp.rmin[t], nsrow - hp.rmin[t]};
+                    pc.ncols = hp.super[t + 1] - hp.super[t]; pc.src_ld = nsrow;
+                    hp.step_recv[k].push_back(pc);
+                } else if (need[t]) {
                     if (run_off < 0) run_off = hp.px[t];
                     run_end = hp.px[t + 1];
                 } else if (run_off >= 0) { hp.step_recv[k].push_back(HostPlan::Piece{run_off, run_end - run_off}); run_off = -1; }
@@ -900,7 +964,7 @@ extern "C" int ssb200_export_begin_compact(long long n, long long nsuper, const 
     return 0;
 }
 
-// lpx[nsuper+1]; pieces[np*3] = step, home_off, cnt; step_next[nsteps]; solve[nsolvejobs*4] = x_off (local), w, xcol0, rows_below.
+// lpx[nsuper+1]; pieces[np*5] = step, home_off, cnt, ncols, src_ld; step_next[nsteps]; solve[nsolvejobs*4] = x_off (local), w, xcol0, rows_below.
 // Call before ssb200_export_fetch (which releases the plan).
 extern "C" long long ssb200_export_compact_fetch(long long *lpx, long long *pieces, int *step_next, long long *solve, long long solve_cap)
 {
@@ -909,13 +973,22 @@ extern "C" long long ssb200_export_compact_fetch(long long *lpx, long long *piec
     for (size_t t = 0; t < hp.lpx.size(); t++) lpx[t] = hp.lpx[t];
     long long q = 0;
     for (size_t k = 0; k < hp.step_recv.size(); k++)
-        for (const auto &pc : hp.step_recv[k]) { pieces[3 * q] = (long long) k; pieces[3 * q + 1] = pc.home_off; pieces[3 * q + 2] = pc.cnt; q++; }
+        for (const auto &pc : hp.step_recv[k]) { pieces[5 * q] = (long long) k; pieces[5 * q + 1] = pc.home_off; pieces[5 * q + 2] = pc.cnt; pieces[5 * q + 3] = pc.ncols; pieces[5 * q + 4] = pc.src_ld; q++; }
     for (size_t k = 0; k < hp.step_next.size(); k++) step_next[k] = hp.step_next[k];
     const long long nsj = (long long) hp.solve_jobs.size();
     if (!lpx && !pieces) return nsj;
     if (solve && solve_cap >= nsj)
         for (long long t = 0; t < nsj; t++) { solve[4 * t] = hp.solve_jobs[t].x_off; solve[4 * t + 1] = hp.solve_jobs[t].w; solve[4 * t + 2] = hp.solve_jobs[t].xcol0; solve[4 * t + 3] = hp.solve_jobs[t].rows_below; }
     return nsj;
+}
+
+// transient (ring-stored) and trailing-rows-only supernodes of the compact plan: tr[4*t] = transient flag, own base, ring
+// base, first stored row; returns the ring depth
+extern "C" int ssb200_export_compact_tr(long long *tr)
+{
+    if (!g_export || !g_export->compact) return -4;
+    for (long long t = 0; t < g_export->nsuper; t++) { tr[4 * t] = g_export->transient[t]; tr[4 * t + 1] = g_export->tr_own_base[t]; tr[4 * t + 2] = g_export->tr_ring_base[t]; tr[4 * t + 3] = g_export->rmin[t]; }
+    return g_export->ring_depth;
 }
 
 // (step, dependency) pairs of the compact plan: returns their number; fills out[2*i], out[2*i+1] when cap suffices
@@ -928,7 +1001,7 @@ extern "C" long long ssb200_export_compact_deps(long long *out, long long cap)
     return q;
 }
 
-// launches[nl*7] = kind, job0, njobs, phase, stream, wait_ev, rec_ev; gemm[ng*8] = a_off,c_off,map_off,lda,ldc,K,nd1,nd2; panel arrays [..*6] = x_off,lda,w,
+// launches[nl*7] = kind, job0, njobs, phase, stream, wait_ev, rec_ev; gemm[ng*9] = a_off,c_off,map_off,lda,ldc,K,nd1,nd2,c_col0; panel arrays [..*6] = x_off,lda,w,
 // rows_below,col0,snode; steps[ns*7] = launch_begin,launch_mid,launch_end,src,off,cnt,wait_remote; updates[nu*6] = d,s,p0,nd1,nd2,map_off; owner[nsuper]
 extern "C" int ssb200_export_fetch(long long *launches, long long *gemm, long long *potrf, long long *trsm, long long *steps,
                                    long long *updates, int *owner)
@@ -939,7 +1012,7 @@ extern "C" int ssb200_export_fetch(long long *launches, long long *gemm, long lo
         const auto &L = hp.launches[t]; long long *o = launches + 7 * t;
         o[0] = L.kind; o[1] = L.job0; o[2] = L.njobs; o[3] = L.phase; o[4] = L.stream; o[5] = L.wait_ev; o[6] = L.rec_ev;
     }
-    for (size_t t = 0; t < hp.gemm_jobs.size(); t++) { const auto &g = hp.gemm_jobs[t]; long long *o = gemm + 8 * t; o[0] = g.a_off; o[1] = g.c_off; o[2] = g.map_off; o[3] = g.lda; o[4] = g.ldc; o[5] = g.K; o[6] = g.nd1; o[7] = g.nd2; }
+    for (size_t t = 0; t < hp.gemm_jobs.size(); t++) { const auto &g = hp.gemm_jobs[t]; long long *o = gemm + 9 * t; o[0] = g.a_off; o[1] = g.c_off; o[2] = g.map_off; o[3] = g.lda; o[4] = g.ldc; o[5] = g.K; o[6] = g.nd1; o[7] = g.nd2; o[8] = g.c_col0; }
     auto panel = [](const std::vector<ssb::PanelJob> &v, long long *out) { for (size_t t = 0; t < v.size(); t++) { long long *o = out + 6 * t; o[0] = v[t].x_off; o[1] = v[t].lda; o[2] = v[t].w; o[3] = v[t].rows_below; o[4] = v[t].col0; o[5] = v[t].snode; } };
     panel(hp.potrf_jobs, potrf); panel(hp.trsm_jobs, trsm);
     for (size_t t = 0; t < hp.steps.size(); t++) { const auto &st = hp.steps[t]; long long *o = steps + 7 * t; o[0] = st.launch_begin; o[1] = st.launch_mid; o[2] = st.launch_end; o[3] = st.bcast_src; o[4] = st.off; o[5] = st.cnt; o[6] = st.wait_remote; }

@@ -17,7 +17,7 @@ def export_plan(n, super_, pi, px, s, nranks=1, rank=0):
     rc = lib.ssb200_export_begin(C.c_int64(n), C.c_int64(len(super_) - 1), *[P(v) for v in a], C.c_int(nranks), C.c_int(rank), P(sizes))
     assert rc == 0, rc
     nl, ng, npo, nt, ns, nu = [int(v) for v in sizes[:6]]
-    out = dict(launches=np.zeros((nl, 7), np.int64), gemm=np.zeros((ng, 8), np.int64), potrf=np.zeros((npo, 6), np.int64),
+    out = dict(launches=np.zeros((nl, 7), np.int64), gemm=np.zeros((ng, 9), np.int64), potrf=np.zeros((npo, 6), np.int64),
                trsm=np.zeros((nt, 6), np.int64), steps=np.zeros((ns, 7), np.int64), updates=np.zeros((nu, 6), np.int64),
                owner=np.zeros(len(super_) - 1, np.int32))
     rc = lib.ssb200_export_fetch(*[P(out[k]) for k in ("launches", "gemm", "potrf", "trsm", "steps", "updates", "owner")])
@@ -35,23 +35,51 @@ def export_plan_compact(n, super_, pi, px, s, nranks, rank):
     rc = lib.ssb200_export_begin_compact(C.c_int64(n), C.c_int64(len(super_) - 1), *[P(v) for v in a], C.c_int(nranks), C.c_int(rank), P(sizes), P(cs))
     assert rc == 0, rc
     nl, ng, npo, nt, ns, nu = [int(v) for v in sizes[:6]]
-    lpx = np.zeros(len(super_), np.int64); pieces = np.zeros((max(int(cs[1]), 1), 3), np.int64); nxt = np.zeros(max(ns, 1), np.int32)
+    lpx = np.zeros(len(super_), np.int64); pieces = np.zeros((max(int(cs[1]), 1), 5), np.int64); nxt = np.zeros(max(ns, 1), np.int32)
     lib.ssb200_export_compact_fetch.restype = C.c_int64
     nsj = lib.ssb200_export_compact_fetch(P(lpx), P(pieces), P(nxt), None, C.c_int64(0))
     solve = np.zeros((max(int(nsj), 1), 4), np.int64)
     lib.ssb200_export_compact_fetch(P(lpx), P(pieces), P(nxt), P(solve), C.c_int64(nsj))
+    tr = np.zeros((len(super_) - 1, 4), np.int64)
+    ring_depth = int(lib.ssb200_export_compact_tr(P(tr)))
     lib.ssb200_export_compact_deps.restype = C.c_int64
     nd = lib.ssb200_export_compact_deps(None, C.c_int64(0))
     deps = np.zeros((max(int(nd), 1), 2), np.int64)
     lib.ssb200_export_compact_deps(P(deps), C.c_int64(nd))
-    out = dict(launches=np.zeros((nl, 7), np.int64), gemm=np.zeros((ng, 8), np.int64), potrf=np.zeros((npo, 6), np.int64),
+    out = dict(launches=np.zeros((nl, 7), np.int64), gemm=np.zeros((ng, 9), np.int64), potrf=np.zeros((npo, 6), np.int64),
                trsm=np.zeros((nt, 6), np.int64), steps=np.zeros((ns, 7), np.int64), updates=np.zeros((nu, 6), np.int64),
                owner=np.zeros(len(super_) - 1, np.int32))
     rc = lib.ssb200_export_fetch(*[P(out[k]) for k in ("launches", "gemm", "potrf", "trsm", "steps", "updates", "owner")])
     assert rc == 0
     out.update(relmap_size=int(sizes[6]), nlevels=int(sizes[7]), nranks=nranks, rank=rank, lpx=lpx, lxsize=int(cs[0]),
-               pieces=pieces[:int(cs[1])], step_next=nxt[:ns], solve=solve[:int(nsj)], deps=deps[:int(nd)])
+               pieces=pieces[:int(cs[1])], step_next=nxt[:ns], solve=solve[:int(nsj)], deps=deps[:int(nd)],
+               tr=tr, ring_depth=ring_depth, px=np.asarray(px, dtype=np.int64), pi=np.asarray(pi, dtype=np.int64), super=np.asarray(super_, dtype=np.int64))
     return out
+
+
+def local_of(pl, home):
+    """HostPlan::local_of restated: home offset in Lx -> offset in this rank's storage (transient root: own panels packed,
+    the others in ring slots)."""
+    px = pl["px"]
+    t = int(np.searchsorted(px, home, side="right") - 1)
+    assert pl["lpx"][t] >= 0
+    if pl["tr"][t, 3] > 0:                                   # trailing rows only
+        nsrow = int(pl["pi"][t + 1] - pl["pi"][t]); rmin = int(pl["tr"][t, 3])
+        col, row = divmod(int(home - px[t]), nsrow)
+        assert row >= rmin
+        return int(pl["lpx"][t] + col * (nsrow - rmin) + row - rmin)
+    if not pl["tr"][t, 0]:
+        return int(pl["lpx"][t] + home - px[t])
+    nsrow = int(pl["pi"][t + 1] - pl["pi"][t])
+    col, row = divmod(int(home - px[t]), nsrow)
+    J = col // NB_MID
+    within = (col - J * NB_MID) * nsrow + row
+    P = NB_MID * nsrow
+    off = -1 - int(pl["owner"][t]); nr = pl["nranks"]; r = pl["rank"]
+    if (J + off) % nr == r:
+        Jf = (r - off) % nr
+        return int(pl["tr"][t, 1] + ((J - Jf) // nr) * P + within)
+    return int(pl["tr"][t, 2] + (J % pl["ring_depth"]) * P + within)
 
 
 def assemble_compact(plan, super_, pi, px, s, S_lower, Lx):
@@ -67,12 +95,13 @@ def assemble_compact(plan, super_, pi, px, s, S_lower, Lx):
             if (o != plan["rank"]) if o >= 0 else (((k - k1) // NB_MID + (-1 - o)) % plan["nranks"] != plan["rank"]):
                 continue
             assert lpx[sn] >= 0
+            colbase = local_of(plan, int(px[sn]) + (k - k1) * nsrow)          # the column's first entry (transient root: packed panels)
             for p in range(Sp[k], Sp[k + 1]):
                 i = Si[p]
                 if i >= k:
                     pos = np.searchsorted(rows, i)
                     if pos < nsrow and rows[pos] == i:
-                        Lx[lpx[sn] + pos + (k - k1) * nsrow] = Sx[p]
+                        Lx[colbase + pos] = Sx[p]
 
 
 def run_lockstep_compact(plans, rel, Lx, px, selective=False):
@@ -85,11 +114,12 @@ def run_lockstep_compact(plans, rel, Lx, px, selective=False):
         return _run_lockstep_compact_selective(plans, rel, Lx, px)
     pending = []
     pulled = [0] * nr
-    loc = lambda pl, home: int(pl["lpx"][np.searchsorted(px, home, side="right") - 1] + home - px[np.searchsorted(px, home, side="right") - 1])
+    loc = local_of
     by_step = [dict() for _ in range(nr)]
     for r in range(nr):
-        for k, ho, cnt in plans[r]["pieces"]:
-            by_step[r].setdefault(int(k), []).append((int(ho), int(cnt)))
+        for k, ho, cnt, ncols, sld in plans[r]["pieces"]:
+            for c in range(int(ncols)):
+                by_step[r].setdefault(int(k), []).append((int(ho + c * sld), int(cnt)))
     for k in range(len(plans[0]["steps"])):
         if plans[0]["steps"][k][6]:
             for r, dst, data in pending:
@@ -118,11 +148,12 @@ def run_lockstep_compact(plans, rel, Lx, px, selective=False):
 def _run_lockstep_compact_selective(plans, rel, Lx, px):
     nr = len(plans)
     pulled = [0] * nr
-    loc = lambda pl, home: int(pl["lpx"][np.searchsorted(px, home, side="right") - 1] + home - px[np.searchsorted(px, home, side="right") - 1])
+    loc = local_of
     by_step = [dict() for _ in range(nr)]; deps = [dict() for _ in range(nr)]
     for r in range(nr):
-        for k, ho, cnt in plans[r]["pieces"]:
-            by_step[r].setdefault(int(k), []).append((int(ho), int(cnt)))
+        for k, ho, cnt, ncols, sld in plans[r]["pieces"]:
+            for c in range(int(ncols)):
+                by_step[r].setdefault(int(k), []).append((int(ho + c * sld), int(cnt)))
         for k, d in plans[r]["deps"]:
             deps[r].setdefault(int(k), []).append(int(d))
     pending = [dict() for _ in range(nr)]                 # per rank: step -> [(dst, data)]
@@ -156,8 +187,7 @@ def gather_compact(plans, Lx, px, xsize):
         lo, mid, hi, src, off, cnt, wait = plans[0]["steps"][k]
         if src < 0 or cnt <= 0:
             continue
-        t = np.searchsorted(px, off, side="right") - 1
-        so = int(plans[src]["lpx"][t] + off - px[t])
+        so = local_of(plans[src], int(off))
         assert np.isnan(out[off: off + cnt]).all()              # every entry exactly once
         out[off: off + cnt] = Lx[src][so: so + cnt]
     assert not np.isnan(out).any()
@@ -199,13 +229,13 @@ def assemble(plan, super_, pi, px, s, S_lower, Lx, beta=0.0):
 def run_launches(plan, rel, Lx, lo, hi):
     for kind, job0, njobs in plan["launches"][lo:hi, :3]:
         if kind in (L_GEMM_BIG, L_GEMM_SMALL):
-            for a_off, c_off, moff, lda, ldc, K, nd1, nd2 in plan["gemm"][job0: job0 + njobs]:
+            for a_off, c_off, moff, lda, ldc, K, nd1, nd2, c_col0 in plan["gemm"][job0: job0 + njobs]:
                 idx = a_off + np.arange(nd2)[:, None] + np.arange(K)[None, :] * lda
                 Pm = Lx[idx]
                 Cm = Pm @ Pm[:nd1].T
                 ii, jj = np.nonzero(np.arange(nd2)[:, None] >= np.arange(nd1)[None, :])
                 if moff >= 0:
-                    tgt = c_off + rel[moff + ii] + rel[moff + jj] * ldc
+                    tgt = c_off + rel[moff + ii] + (rel[moff + jj] - c_col0) * ldc
                 else:
                     tgt = c_off + ii + jj * ldc
                 np.subtract.at(Lx, tgt, Cm[ii, jj])

@@ -91,7 +91,7 @@ def test_sharded_schedule_with_cyclic_supernode_single_process(kind, N, nr, jit)
 
 
 @pytest.mark.parametrize("selective", [False, True])
-@pytest.mark.parametrize("kind,N,nr", [("lap7", 22, 4), ("lap7", 24, 2), ("lap27", 18, 3), ("elas", 8, 3), ("lap7", 26, 8), ("lap7", 34, 3)])
+@pytest.mark.parametrize("kind,N,nr", [("lap7", 22, 4), ("lap7", 24, 2), ("lap27", 18, 3), ("elas", 8, 3), ("lap7", 26, 8), ("lap7", 34, 3), ("lap7", 30, 2), ("lap7", 31, 3)])
 def test_distributed_storage_schedule_single_process(kind, N, nr, selective):
     """The in-process multi-GPU path (ssb200_mg_*): every rank stores only its supernodes, the cyclic ones and the remote
     supernodes its updates read; finished ranges are pulled piecewise by the ranks that read them.  Emulated ranks with
@@ -113,6 +113,9 @@ def test_distributed_storage_schedule_single_process(kind, N, nr, selective):
     Sl = sp.csc_matrix((Ax, Ai, Ap), shape=(n, n))
     st, minor, Lo = oracle.factorize(n, f["super"], f["pi"], f["px"], f["s"], Sl)
     os.environ["SSB200_DIST_TAU"] = "0"
+    if N in (30, 31):
+        # the root supernode (4+ panels) is stored transiently: own panels packed, received panels in a ring of two slots
+        os.environ["SSB200_MG_TRANSIENT_MIN"] = "1"; os.environ["SSB200_MG_RING"] = "2"
     if N == 34:
         # three supernodes of 255-289 columns on one level become panel-cyclic too: their chains are interleaved and start on
         # different ranks
@@ -121,7 +124,16 @@ def test_distributed_storage_schedule_single_process(kind, N, nr, selective):
         plans = [E.export_plan_compact(n, f["super"], f["pi"], f["px"], f["s"], nr, r) for r in range(nr)]
     finally:
         del os.environ["SSB200_DIST_TAU"]
-        os.environ.pop("SSB200_DIST_CYC_MIN", None)
+        os.environ.pop("SSB200_DIST_CYC_MIN", None); os.environ.pop("SSB200_MG_TRANSIENT_MIN", None); os.environ.pop("SSB200_MG_RING", None)
+    if N in (30, 31):
+        assert all(pl["tr"][:, 0].sum() == 1 for pl in plans)                  # the root is transient on every rank
+        root = int(np.nonzero(plans[0]["tr"][:, 0])[0][0])
+        full = int(f["px"][root + 1] - f["px"][root])
+        nsrow_root = int(f["pi"][root + 1] - f["pi"][root])
+        # nobody stores the whole root: own panels + two ring slots
+        for pl in plans:
+            nxt_base = pl["lxsize"] if root == len(f["px"]) - 2 else None
+            assert pl["tr"][root, 2] + 2 * 256 * nsrow_root - pl["tr"][root, 1] < full
     xsize = int(f["px"][-1])
     if N == 34:
         # two panel-cyclic supernodes on one level (the children of the root separator): their chains are interleaved and
