@@ -705,10 +705,11 @@ static int factorize_impl(ssb200_plan *p, const double beta[2], int quick_return
     if (stream_d2h < 0) { const char *v = getenv("SSB200_STREAM_D2H"); stream_d2h = (v && atoi(v) == 0) ? 0 : 1; }
     if (use_graph == -2) { const char *v = getenv("SSB200_FACTOR_GRAPH"); use_graph = v ? (atoi(v) ? 1 : 0) : -1; }
     const bool streaming = Lx_host && stream_d2h && stop_level == INT_MAX && host_is_pinned(Lx_host);
-    // Graph replay by default when the factor streams to the host: the ~2700 dependent launches then do not cross the PCIe
-    // link that the streaming saturates (+24 us per launch otherwise).  Resident factorizations keep the per-launch events
-    // (per-kernel statistics) unless SSB200_FACTOR_GRAPH=1.
-    const bool graph = stop_level == INT_MAX && (use_graph == 1 || (use_graph == -1 && streaming));
+    // Graph replay (SSB200_FACTOR_GRAPH=1, or by default when the look-ahead is off and the factor streams to the host): with
+    // ONE stream the ~2700 dependent launches otherwise wait behind the PCIe link that the streaming saturates (+24 us per
+    // launch, round 1).  With the two-stream look-ahead schedule stream launches are faster than the replayed graph (1 125 vs
+    // 1 134 ms end to end, 1 069 vs 1 083 ms resident), so that is the default.
+    const bool graph = stop_level == INT_MAX && (use_graph == 1 || (use_graph == -1 && streaming && !(p->lookahead && hp.n_events > 0)));
     const bool two_streams = p->lookahead && hp.n_events > 0 && hp.nranks == 1;
     while ((int) p->la_events.size() < hp.n_events) { cudaEvent_t e; CU_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); p->la_events.push_back(e); }
     // everything the enqueue needs exists before a capture starts
