@@ -537,16 +537,17 @@ def main():
                             "frac": round(ach / peak_tf, 4) if peak_tf else None,
                             # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch, from the committed ncu --set full capture
                             # (the launch is the K = 1024 trailing update of the root's first outer panel: 20 301 tiles, 677.8 GFLOP)
-                            "traffic": 22.09e9,
-                            "traffic_note": "profiles/r2_ncu_full_gemm128_update.txt: 19.49 GB read + 2.60 GB written in 20.6 ms (13 % of DRAM peak) for 5.51 GB "
-                                            "of algorithmic bytes (0.21 GB operand panel + 5.30 GB read-modify-write of the target); the 211 MB panel does not fit L2 "
-                                            "and is re-read once per tile column; the launch runs at 32.9 TFLOP/s with the DMMA pipe 89.5 % active",
+                            "traffic": 7.88e9,
+                            "traffic_note": "profiles/r2_ncu_full_gemm128_update_banded.txt: 5.28 GB read + 2.60 GB written in 20.6 ms (4.7 % of DRAM peak) for 5.51 GB "
+                                            "of algorithmic bytes (0.21 GB operand panel + 5.30 GB read-modify-write of the target); the launch runs at 32.9 TFLOP/s "
+                                            "with the DMMA pipe 89.4 % active.  Before the tiles were enumerated in bands of 8 tile columns the 211 MB panel was "
+                                            "re-read once per tile column: 22.09 GB (profiles/r2_ncu_full_gemm128_update.txt), same duration",
                             "peak_source": "cuBLAS DGEMM 8192^3 (torch.matmul fp64) measured in this run; MEASURED_PEAKS.json has no fp64 entry; "
                                            "profiles/r2_fp64_peak.json: 35.44 burst / 35.45 sustained at 8192^3, 36.15 / 36.15 at 16384^3",
                             "kernel_time_share": share, "launches_per_step": [int(v / n_ser) for v in kind_n[:5]],
                             "kernel_timing": f"separate pass of {n_ser} steps with the look-ahead schedule off (one stream, events around every launch): {ms_serial:.1f} ms/step; the timed steps of `value` run the two-stream look-ahead schedule",
                             "whole_step_frac_of_peak": round(fl / t_dev / 1e12 / peak_tf, 4) if peak_tf else None,
-                            "ncu_capture": "profiles/r2_ncu_full_gemm128_update.txt (one K = 1024 launch), profiles/r2_launches_bench_lap7_128.txt (launch list: this kernel 92.9 % of the device time)"},
+                            "ncu_capture": "profiles/r2_ncu_full_gemm128_update_banded.txt (one K = 1024 launch), profiles/r2_launches_bench_lap7_128.txt (launch list: this kernel 92.9 % of the device time)"},
                "solve": {"value": round(16.0 * xsize / (solve_ms_v * 1e-3) / 1e9, 1), "unit": "GB/s", "ms": round(solve_ms_v, 3), "launches": int(solve_launches),
                          "hbm_peak_GBps": json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(REPO, "MEASURED_PEAKS.json")) else 6650.0,
                          "e2e_cholmod_l_solve_ms": round(t_solve_e2e * 1e3, 2), "resid_2norm_rel": resid},
