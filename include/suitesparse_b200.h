@@ -173,6 +173,10 @@ int  cholmod_l_free_factor   (ssb_cholmod_factor **L, ssb_cholmod_common *Common
 /* The drop-in entry points fan one factorization out over the devices listed in $SSB200_DEVICES ("0,1,2,3" or "all";
  * two or more -> ssb200_mg_*); this returns the multi-GPU plan cached for L, or NULL. */
 struct ssb200_mg *ssb200_mg_of_factor(const ssb_cholmod_factor *L);
+/* Complex and zomplex matrices (cholmod_super_numeric.c:81-86) go through the real kernels: every entry a+ib becomes the block
+ * [a -b; b a]; the Cholesky factor of that real SPD matrix of order 2n is the blockified complex factor, which is written to
+ * L->x in CHOLMOD's complex layout.  Test hook: the blockified copy of A (lower != 0: symmetric-lower input). */
+ssb_long ssb200_debug_blockify(const ssb_cholmod_sparse *A, int lower, ssb_long *p2, ssb_long *i2, double *x2, ssb_long cap);
 /* the caller changed L->x in place: the next solve uploads the host values again.  Returns 1 if L had a cached plan. */
 int  ssb200_invalidate_factor(const ssb_cholmod_factor *L);
 #endif /* SSB200_NO_DROPIN_PROTOTYPES */

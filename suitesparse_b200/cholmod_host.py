@@ -199,27 +199,37 @@ class Cholmod:
         self.lib.cholmod_l_finish(C.byref(self.cm))
 
     # -- objects ---------------------------------------------------------------------------------------------
-    def sparse(self, A, stype: int) -> Sparse:
-        """Wrap a scipy CSC matrix (no copy).  stype=+1: upper triangle stored, -1: lower, 0: unsymmetric."""
+    def sparse(self, A, stype: int, zomplex: bool = False) -> Sparse:
+        """Wrap a scipy CSC matrix (no copy).  stype=+1: upper triangle stored, -1: lower, 0: unsymmetric.
+        A complex matrix becomes CHOLMOD_COMPLEX (interleaved re,im) or, with zomplex=True, CHOLMOD_ZOMPLEX (x and z arrays)."""
         Ap = np.ascontiguousarray(A.indptr, dtype=np.int64)
         Ai = np.ascontiguousarray(A.indices, dtype=np.int64)
-        Ax = np.ascontiguousarray(A.data, dtype=np.float64)
-        self._keep.append((Ap, Ai, Ax))
         S = Sparse()
+        S.nz = None; S.z = None
+        xtype = CHOLMOD_REAL
+        if np.iscomplexobj(A.data):
+            data = np.ascontiguousarray(A.data, dtype=np.complex128)
+            if zomplex:
+                Ax = np.ascontiguousarray(data.real); Az = np.ascontiguousarray(data.imag)
+                self._keep.append(Az); S.z = Az.ctypes.data; xtype = CHOLMOD_ZOMPLEX
+            else:
+                Ax = data.view(np.float64); xtype = CHOLMOD_COMPLEX
+        else:
+            Ax = np.ascontiguousarray(A.data, dtype=np.float64)
+        self._keep.append((Ap, Ai, Ax))
         S.nrow, S.ncol, S.nzmax = A.shape[0], A.shape[1], max(1, Ai.size)
         S.p, S.i, S.x = Ap.ctypes.data, Ai.ctypes.data, Ax.ctypes.data
-        S.nz = None; S.z = None
-        S.stype, S.itype, S.xtype, S.dtype, S.sorted, S.packed = stype, CHOLMOD_LONG, CHOLMOD_REAL, 0, 1, 1
+        S.stype, S.itype, S.xtype, S.dtype, S.sorted, S.packed = stype, CHOLMOD_LONG, xtype, 0, 1, 1
         return S
 
     def dense(self, X: np.ndarray) -> Dense:
-        assert X.dtype == np.float64 and X.flags.f_contiguous or X.ndim == 1
+        assert X.dtype in (np.float64, np.complex128) and (X.flags.f_contiguous or X.ndim == 1)
         X2 = X.reshape(X.shape[0], -1, order="F")
         self._keep.append(X2)
         D = Dense()
         D.nrow, D.ncol, D.d = X2.shape[0], X2.shape[1], X2.shape[0]
         D.nzmax = max(1, X2.size)
-        D.x, D.z, D.xtype, D.dtype = X2.ctypes.data, None, CHOLMOD_REAL, 0
+        D.x, D.z, D.xtype, D.dtype = X2.ctypes.data, None, (CHOLMOD_COMPLEX if X.dtype == np.complex128 else CHOLMOD_REAL), 0
         return D
 
     # -- driver calls ----------------------------------------------------------------------------------------
@@ -255,11 +265,13 @@ class Cholmod:
         return ok
 
     def solve(self, Lp, B: np.ndarray, system: int = CHOLMOD_A) -> np.ndarray:
-        Bd = self.dense(np.asfortranarray(B, dtype=np.float64))
+        cplx = np.iscomplexobj(B)
+        Bd = self.dense(np.asfortranarray(B, dtype=np.complex128 if cplx else np.float64))
         Xp = self.lib.cholmod_l_solve(system, Lp, C.byref(Bd), C.byref(self.cm))
         if not Xp:
             raise RuntimeError(f"cholmod_l_solve failed, status {self.cm.status}")
-        X = _np_view(Xp.contents.x, Xp.contents.nzmax, np.float64)[: Xp.contents.nrow * Xp.contents.ncol].copy()
+        dt = np.complex128 if Xp.contents.xtype == CHOLMOD_COMPLEX else np.float64
+        X = _np_view(Xp.contents.x, Xp.contents.nzmax, dt)[: Xp.contents.nrow * Xp.contents.ncol].copy()
         X = X.reshape((Xp.contents.nrow, Xp.contents.ncol), order="F")
         pp = C.POINTER(Dense)(Xp.contents)
         self.lib.cholmod_l_free_dense(C.byref(pp), C.byref(self.cm))
@@ -296,5 +308,6 @@ class Cholmod:
             out["pi"] = _np_view(L.pi, ns + 1, np.int64)
             out["px"] = _np_view(L.px, ns + 1, np.int64)
             out["s"] = _np_view(L.s, int(out["pi"][ns]) if ns else 0, np.int64)
-            out["x"] = _np_view(L.x, L.xsize, np.float64) if L.xtype != CHOLMOD_PATTERN else None
+            out["x"] = (_np_view(L.x, L.xsize, np.complex128 if L.xtype == CHOLMOD_COMPLEX else np.float64)
+                        if L.xtype != CHOLMOD_PATTERN else None)
         return out

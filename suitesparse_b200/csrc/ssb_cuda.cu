@@ -1690,6 +1690,14 @@ struct CacheEntry {
     const void *xptr = nullptr;
     void *pinned_ptr = nullptr;            // L->x range registered with cudaHostRegister (fast D2H into the caller's buffer)
     size_t pinned_bytes = 0;
+    struct CplxAux *cx = nullptr;          // complex factor: the plan works on the real matrix of twice the order
+};
+// complex / zomplex input (cholmod_super_numeric.c:81-86, t_cholmod_super_numeric.c:41-83): the blockified real problem
+struct CplxAux {
+    std::vector<long long> super2, pi2, px2, s2;     // symbolic structure of the real matrix of order 2n
+    long long *d_pxc = nullptr, *d_px2 = nullptr, *d_pi2 = nullptr;
+    double *d_Lc = nullptr;                           // complex factor on the device (2 * xsize doubles), staging for L->x
+    std::vector<long long> Ap2, Ai2, Fp2, Fi2; std::vector<double> Ax2, Fx2;
 };
 static std::mutex g_cache_mu;
 static std::vector<CacheEntry> g_cache;
@@ -1720,7 +1728,13 @@ static CacheEntry *cache_find(const ssb_cholmod_factor *L)
 
 static void unpin(CacheEntry *e) { if (e->plan && e->plan->fgraph) { cudaGraphExecDestroy(e->plan->fgraph); e->plan->fgraph = nullptr; }   // its copy nodes point into this registration
     if (e->pinned_ptr) { if (cudaHostUnregister(e->pinned_ptr) != cudaSuccess) (void) cudaGetLastError(); e->pinned_ptr = nullptr; e->pinned_bytes = 0; } }
-static void cache_drop(CacheEntry *e) { unpin(e); plan_free(e->plan); mg_free(e->mg); g_cache.erase(g_cache.begin() + (e - g_cache.data())); }
+static void cplx_free(CplxAux *cx)
+{
+    if (!cx) return;
+    for (void *q : {(void *) cx->d_pxc, (void *) cx->d_px2, (void *) cx->d_pi2, (void *) cx->d_Lc}) if (q) cudaFree(q);
+    delete cx;
+}
+static void cache_drop(CacheEntry *e) { unpin(e); cplx_free(e->cx); plan_free(e->plan); mg_free(e->mg); g_cache.erase(g_cache.begin() + (e - g_cache.data())); }
 
 // SSB200_DEVICES = "0,1,2,3" | "all": the devices one factorization fans out over (two or more -> ssb200_mg_*)
 static std::vector<int> devices_from_env()
@@ -1791,11 +1805,12 @@ static void pin_host_x(CacheEntry *e, const ssb_cholmod_factor *L)
 }
 
 // returns the (possibly new) entry for L; nullptr on failure
-static CacheEntry *cache_get_plan(ssb_cholmod_factor *L, bool single_gpu_only = false)
+static CacheEntry *cache_get_plan(ssb_cholmod_factor *L, bool single_gpu_only = false, bool cplx = false)
 {
     const unsigned long long h = hash_symbolic(L);
     CacheEntry *e = cache_find(L);
     if (e && single_gpu_only && e->mg) { cache_drop(e); e = nullptr; }
+    if (e && (e->cx != nullptr) != cplx) { cache_drop(e); e = nullptr; }
     if (e && (e->n != L->n || e->nsuper != L->nsuper || e->ssize != L->ssize || e->xsize != L->xsize || e->sym_hash != h)) { cache_drop(e); e = nullptr; }
     if (e) return e;
     while (g_cache.size() >= cache_capacity()) cache_drop(&g_cache.front());
@@ -1803,6 +1818,30 @@ static CacheEntry *cache_get_plan(ssb_cholmod_factor *L, bool single_gpu_only = 
     if (const char *d = getenv("SSB200_DEVICE")) dev = atoi(d);
     ssb200_plan *plan = nullptr; ssb200_mg *mg = nullptr;
     const std::vector<int> devs = devices_from_env();
+    CplxAux *cx = nullptr;
+    if (cplx) {
+        // the real matrix of order 2n: supernode s has columns 2k, 2k+1 and rows 2r, 2r+1 of the complex one (one GPU)
+        cx = new CplxAux();
+        const long long ns = (long long) L->nsuper;
+        const long long *sup = (const long long *) L->super, *pi = (const long long *) L->pi, *rows = (const long long *) L->s;
+        cx->super2.resize(ns + 1); cx->pi2.resize(ns + 1); cx->px2.resize(ns + 1);
+        cx->px2[0] = 0;
+        for (long long t = 0; t <= ns; t++) { cx->super2[t] = 2 * sup[t]; cx->pi2[t] = 2 * pi[t]; }
+        for (long long t = 0; t < ns; t++) cx->px2[t + 1] = cx->px2[t] + 4 * (pi[t + 1] - pi[t]) * (sup[t + 1] - sup[t]);
+        const long long ss = ns ? pi[ns] : 0;
+        cx->s2.resize(2 * ss);
+        for (long long q = 0; q < ss; q++) { cx->s2[2 * q] = 2 * rows[q]; cx->s2[2 * q + 1] = 2 * rows[q] + 1; }
+        if (devs.size() >= 1 && dev < 0) dev = devs[0];
+        plan = ssb200_plan_create((ssb_long) (2 * L->n), (ssb_long) ns, (const ssb_long *) cx->super2.data(), (const ssb_long *) cx->pi2.data(),
+                                  (const ssb_long *) cx->px2.data(), (const ssb_long *) cx->s2.data(), dev);
+        bool ok = plan != nullptr;
+        const size_t nb = (size_t) (ns + 1) * sizeof(long long);
+        ok = ok && cudaMalloc((void **) &cx->d_pxc, nb) == cudaSuccess && cudaMalloc((void **) &cx->d_px2, nb) == cudaSuccess && cudaMalloc((void **) &cx->d_pi2, nb) == cudaSuccess &&
+             cudaMalloc((void **) &cx->d_Lc, std::max<size_t>(L->xsize, 1) * 2 * sizeof(double)) == cudaSuccess;
+        ok = ok && cudaMemcpy(cx->d_pxc, L->px, nb, cudaMemcpyHostToDevice) == cudaSuccess && cudaMemcpy(cx->d_px2, cx->px2.data(), nb, cudaMemcpyHostToDevice) == cudaSuccess &&
+             cudaMemcpy(cx->d_pi2, cx->pi2.data(), nb, cudaMemcpyHostToDevice) == cudaSuccess;
+        if (!ok) { if (plan) set_error("device allocation for the complex factor failed"); plan_free(plan); cplx_free(cx); return nullptr; }
+    } else
     if (devs.size() >= 2 && !single_gpu_only) {
         mg = ssb200_mg_create((ssb_long) L->n, (ssb_long) L->nsuper, (const ssb_long *) L->super, (const ssb_long *) L->pi,
                               (const ssb_long *) L->px, (const ssb_long *) L->s, (int) devs.size(), devs.data());
@@ -1813,7 +1852,7 @@ static CacheEntry *cache_get_plan(ssb_cholmod_factor *L, bool single_gpu_only = 
                                   (const ssb_long *) L->px, (const ssb_long *) L->s, dev);
         if (!plan) return nullptr;
     }
-    CacheEntry ne; ne.L = L; ne.plan = plan; ne.mg = mg; ne.n = L->n; ne.nsuper = L->nsuper; ne.ssize = L->ssize; ne.xsize = L->xsize; ne.sym_hash = h;
+    CacheEntry ne; ne.L = L; ne.plan = plan; ne.mg = mg; ne.cx = cx; ne.n = L->n; ne.nsuper = L->nsuper; ne.ssize = L->ssize; ne.xsize = L->xsize; ne.sym_hash = h;
     g_cache.push_back(ne);
     return &g_cache.back();
 }
@@ -1822,9 +1861,10 @@ static void take_value_fingerprint(CacheEntry *e, const ssb_cholmod_factor *L)
 {
     const double *x = (const double *) L->x;
     e->sample_idx.clear(); e->sample_val.clear(); e->xptr = L->x;
-    const size_t cnt = std::min<size_t>(L->xsize, 4096);
+    const size_t nd = L->xsize * (e->cx ? 2 : 1);       // doubles behind L->x
+    const size_t cnt = std::min<size_t>(nd, 4096);
     if (!cnt) return;
-    const size_t step = L->xsize / cnt;
+    const size_t step = nd / cnt;
     for (size_t t = 0; t < cnt; t++) { const long long idx = (long long) (t * step); e->sample_idx.push_back(idx); e->sample_val.push_back(x[idx]); }
 }
 static bool value_fingerprint_ok(const CacheEntry *e, const ssb_cholmod_factor *L)
@@ -1840,6 +1880,92 @@ static bool gpu_enabled_by_env()
 {
     const char *e = getenv("CHOLMOD_USE_GPU");      // same switch the reference reads (cholmod_super_symbolic.c:257-296)
     return !(e && atoi(e) == 0);
+}
+
+// Blockified copy of a complex (interleaved x) or zomplex (x, z) CHOLMOD matrix: entry a+ib at (i,j) becomes [a -b; b a] at rows
+// 2i,2i+1 / columns 2j,2j+1.  lower: symmetric-lower input (entries above the diagonal are ignored, as the reference does; the
+// imaginary part of the diagonal is dropped, zpotrf never reads it).
+static void blockify_csc(const ssb_cholmod_sparse *A, bool lower, std::vector<long long> &p2, std::vector<long long> &i2, std::vector<double> &x2)
+{
+    const long long ncol = (long long) A->ncol;
+    const long long *Ap = (const long long *) A->p, *Ai = (const long long *) A->i, *Anz = A->packed ? nullptr : (const long long *) A->nz;
+    const double *Ax = (const double *) A->x, *Az = (const double *) A->z;
+    const bool zomplex = A->xtype == SSB_CHOLMOD_ZOMPLEX;
+    p2.assign(2 * ncol + 1, 0); i2.clear(); x2.clear();
+    for (long long j = 0; j < ncol; j++) {
+        const long long pb = Ap[j], pe = Anz ? pb + Anz[j] : Ap[j + 1];
+        for (int half = 0; half < 2; half++) {             // column 2j, then column 2j+1
+            for (long long q = pb; q < pe; q++) {
+                const long long i = Ai[q];
+                if (lower && i < j) continue;
+                const double re = zomplex ? Ax[q] : Ax[2 * q];
+                const double im = (lower && i == j) ? 0.0 : (zomplex ? Az[q] : Ax[2 * q + 1]);
+                if (half == 0) { i2.push_back(2 * i); x2.push_back(re); i2.push_back(2 * i + 1); x2.push_back(im); }
+                else {
+                    if (!(lower && i == j)) { i2.push_back(2 * i); x2.push_back(-im); }      // (2j, 2j+1) of a diagonal block is above the diagonal
+                    i2.push_back(2 * i + 1); x2.push_back(re);
+                }
+            }
+            p2[2 * j + half + 1] = (long long) i2.size();
+        }
+    }
+}
+
+// test hook (no GPU needed): the blockified copy of a complex / zomplex matrix; returns its number of entries, fills the arrays
+// when cap suffices (p2 has 2*ncol+1 entries)
+extern "C" ssb_long ssb200_debug_blockify(const ssb_cholmod_sparse *A, int lower, ssb_long *p2, ssb_long *i2, double *x2, ssb_long cap)
+{
+    if (!A || A->xtype < SSB_CHOLMOD_COMPLEX) return -1;
+    std::vector<long long> p, i; std::vector<double> x;
+    blockify_csc(A, lower != 0, p, i, x);
+    if (p2 && i2 && x2 && cap >= (ssb_long) i.size()) {
+        memcpy(p2, p.data(), p.size() * sizeof(long long)); memcpy(i2, i.data(), i.size() * sizeof(long long)); memcpy(x2, x.data(), x.size() * sizeof(double));
+    }
+    return (ssb_long) i.size();
+}
+
+// complex / zomplex A (and F): factorize the blockified real matrix with the real kernels, then write CHOLMOD's complex L->x
+static int factorize_complex(CacheEntry *e, const ssb_cholmod_sparse *A, const ssb_cholmod_sparse *F, const double beta[2], int quick,
+                             ssb_cholmod_factor *L, ssb_long *minor)
+{
+    CplxAux *cx = e->cx;
+    ssb200_plan *p = e->plan;
+    const int stype = A->stype;
+    blockify_csc(A, stype < 0, cx->Ap2, cx->Ai2, cx->Ax2);
+    if (stype == 0) blockify_csc(F, false, cx->Fp2, cx->Fi2, cx->Fx2);
+    ssb_long minor2 = 0;
+    const int rc = ssb200_factorize(p, stype, (const ssb_long *) cx->Ap2.data(), (const ssb_long *) cx->Ai2.data(), nullptr, cx->Ax2.data(), (ssb_long) (2 * A->ncol),
+                                    stype == 0 ? (const ssb_long *) cx->Fp2.data() : nullptr, stype == 0 ? (const ssb_long *) cx->Fi2.data() : nullptr, nullptr,
+                                    stype == 0 ? cx->Fx2.data() : nullptr, beta, quick, nullptr, &minor2);
+    if (rc < 0) return rc;
+    *minor = minor2 / 2;                                   // a non-positive pivot shows up at the even column of the pair first
+    if (L->xsize > 0) {
+        const long long xc = (long long) L->xsize;
+        cplx_compress_kernel<<<(unsigned) ((xc + 255) / 256), 256, 0, p->stream>>>(cx->d_pxc, cx->d_px2, cx->d_pi2, (long long) L->nsuper, xc, p->d_Lx, cx->d_Lc);
+        CU_TRY(cudaGetLastError());
+        CU_TRY(cudaMemcpyAsync(L->x, cx->d_Lc, (size_t) xc * 2 * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+        CU_TRY(cudaStreamSynchronize(p->stream));
+        p->stats.kernel_launches++;
+    }
+    return rc;
+}
+
+// host complex factor -> blockified real factor on the device (a factor computed elsewhere, or changed by the caller)
+static int upload_complex_L(CacheEntry *e, const ssb_cholmod_factor *L)
+{
+    CplxAux *cx = e->cx;
+    ssb200_plan *p = e->plan;
+    CU_TRY(cudaSetDevice(p->device));
+    const long long xc = (long long) L->xsize;
+    if (xc > 0) {
+        CU_TRY(cudaMemcpyAsync(cx->d_Lc, L->x, (size_t) xc * 2 * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+        CU_TRY(cudaMemsetAsync(p->d_Lx, 0, (size_t) p->lx_alloc * sizeof(double), p->stream));
+        cplx_expand_kernel<<<(unsigned) ((xc + 255) / 256), 256, 0, p->stream>>>(cx->d_pxc, cx->d_px2, cx->d_pi2, (long long) L->nsuper, xc, cx->d_Lc, p->d_Lx);
+        CU_TRY(cudaGetLastError());
+        CU_TRY(cudaStreamSynchronize(p->stream));
+    }
+    p->factor_on_device = true; p->winv_valid = false;
+    return 0;
 }
 
 extern "C" int cholmod_l_super_numeric(ssb_cholmod_sparse *A, ssb_cholmod_sparse *F, double beta[2], ssb_cholmod_factor *L,
@@ -1871,7 +1997,7 @@ extern "C" int cholmod_l_super_numeric(ssb_cholmod_sparse *A, ssb_cholmod_sparse
     }
     Common->status = SSB_CHOLMOD_OK;
     // ---- scope of the B200 path: real, 64-bit indices.  No CPU fallback. ----
-    if (A->xtype != SSB_CHOLMOD_REAL) { RAISE(Common, SSB_CHOLMOD_NOT_INSTALLED, "suitesparse_b200: complex/zomplex supernodal factorization is not provided on the GPU path"); return 0; }
+    const bool cplx = A->xtype != SSB_CHOLMOD_REAL;     // complex / zomplex: through the blockified real problem (one GPU)
     if (A->itype != SSB_CHOLMOD_LONG || L->itype != SSB_CHOLMOD_LONG) { RAISE(Common, SSB_CHOLMOD_INVALID, "suitesparse_b200: only the cholmod_l_ (64-bit index) interface is accelerated"); return 0; }
     if (!gpu_enabled_by_env()) { RAISE(Common, SSB_CHOLMOD_GPU_PROBLEM, "suitesparse_b200: CHOLMOD_USE_GPU=0 but this library has no CPU path; unload it to use the CPU"); return 0; }
     // ---- numeric part of L (cholmod_super_numeric.c:206-228) ----
@@ -1880,7 +2006,7 @@ extern "C" int cholmod_l_super_numeric(ssb_cholmod_sparse *A, ssb_cholmod_sparse
         static change_factor_fn cf = nullptr;
         if (!cf) cf = (change_factor_fn) host_sym("cholmod_l_change_factor");
         if (!cf) { RAISE(Common, SSB_CHOLMOD_INVALID, "suitesparse_b200: host libcholmod (cholmod_l_change_factor) not found in the process"); return 0; }
-        cf(SSB_CHOLMOD_REAL, 1, 1, 1, 1, L, Common);
+        cf(cplx ? SSB_CHOLMOD_COMPLEX : SSB_CHOLMOD_REAL, 1, 1, 1, 1, L, Common);      // a zomplex A gives a complex L (cholmod_super_numeric.c:211-223)
         if (Common->status < SSB_CHOLMOD_OK) return 0;               // L stays symbolic
     }
     L->is_ll = 1;
@@ -1905,15 +2031,16 @@ extern "C" int cholmod_l_super_numeric(ssb_cholmod_sparse *A, ssb_cholmod_sparse
         raise_error(Common, status, __LINE__, msg.c_str());
         return 0;
     };
-    CacheEntry *e = cache_get_plan(L);
+    CacheEntry *e = cache_get_plan(L, cplx, cplx);
     if (!e) return fail(SSB_CHOLMOD_GPU_PROBLEM, ssb200_last_error());
-    pin_host_x(e, L);
+    if (!cplx) pin_host_x(e, L);
     ssb_long minor = (ssb_long) L->n;
     const ssb_long *Anz_ = A->packed ? nullptr : (const ssb_long *) A->nz;
     const ssb_long *Fp_ = F ? (const ssb_long *) F->p : nullptr, *Fi_ = F ? (const ssb_long *) F->i : nullptr, *Fnz_ = (F && !F->packed) ? (const ssb_long *) F->nz : nullptr;
     const double *Fx_ = F ? (const double *) F->x : nullptr;
     int rc;
-    if (e->mg) {
+    if (cplx) rc = factorize_complex(e, A, F, beta, Common->quick_return_if_not_posdef, L, &minor);
+    else if (e->mg) {
         rc = ssb200_mg_factorize(e->mg, stype, (const ssb_long *) A->p, (const ssb_long *) A->i, Anz_, (const double *) A->x, (ssb_long) A->ncol,
                                  Fp_, Fi_, Fnz_, Fx_, beta, (double *) L->x, &minor);
         if (rc == SSB_CHOLMOD_NOT_POSDEF) {
@@ -1924,7 +2051,7 @@ extern "C" int cholmod_l_super_numeric(ssb_cholmod_sparse *A, ssb_cholmod_sparse
             pin_host_x(e, L);
         }
     }
-    if (!e->mg)
+    if (!cplx && !e->mg)
         rc = ssb200_factorize(e->plan, stype, (const ssb_long *) A->p, (const ssb_long *) A->i, Anz_, (const double *) A->x, (ssb_long) A->ncol,
                               Fp_, Fi_, Fnz_, Fx_, beta, Common->quick_return_if_not_posdef, (double *) L->x, &minor);
     if (rc < 0) return fail(rc == SSB_CHOLMOD_INVALID ? SSB_CHOLMOD_INVALID : SSB_CHOLMOD_GPU_PROBLEM, ssb200_last_error());
@@ -1967,15 +2094,24 @@ static int super_solve_common(ssb_cholmod_factor *L, ssb_cholmod_dense *X, ssb_c
     if (!L->is_ll || !L->is_super) { RAISE(Common, SSB_CHOLMOD_INVALID, "L not supernodal"); return 0; }
     Common->status = SSB_CHOLMOD_OK;
     if (L->n == 0 || X->ncol == 0) return 1;
-    if (L->xtype != SSB_CHOLMOD_REAL) { RAISE(Common, SSB_CHOLMOD_NOT_INSTALLED, "suitesparse_b200: complex supernodal solve is not provided on the GPU path"); return 0; }
+    const bool cplx = L->xtype == SSB_CHOLMOD_COMPLEX;  // X is complex too (checked above): interleaved (re,im) = the real vector of order 2n
     std::lock_guard<std::mutex> lk(g_cache_mu);
     {
         static int verbose = -1;
         if (verbose < 0) { const char *v = getenv("SSB200_VERBOSE"); verbose = (v && atoi(v)) ? 1 : 0; }
         if (verbose) fprintf(stderr, "[suitesparse_b200] cholmod_l_super_%ssolve: n=%zu nrhs=%zu (CUDA path)\n", which ? "lt" : "l", L->n, X->ncol);
     }
-    CacheEntry *e = cache_get_plan(L);
+    CacheEntry *e = cache_get_plan(L, cplx, cplx);
     if (!e) { RAISE(Common, SSB_CHOLMOD_GPU_PROBLEM, ssb200_last_error()); return 0; }
+    if (cplx) {
+        if (!value_fingerprint_ok(e, L)) {
+            if (upload_complex_L(e, L)) { RAISE(Common, SSB_CHOLMOD_GPU_PROBLEM, ssb200_last_error()); return 0; }
+            take_value_fingerprint(e, L);
+        }
+        const int rc = ssb200_solve(e->plan, which, (double *) X->x, (ssb_long) X->ncol, (ssb_long) (2 * X->d));
+        if (rc) { RAISE(Common, rc == SSB_CHOLMOD_INVALID ? SSB_CHOLMOD_INVALID : SSB_CHOLMOD_GPU_PROBLEM, ssb200_last_error()); return 0; }
+        return 1;
+    }
     if (!value_fingerprint_ok(e, L)) {
         // L->x was produced or modified elsewhere: bring it to the device (still the GPU path, just slower)
         if (e->mg ? ssb200_mg_upload_L(e->mg, (const double *) L->x) : ssb200_upload_L(e->plan, (const double *) L->x)) { RAISE(Common, SSB_CHOLMOD_GPU_PROBLEM, ssb200_last_error()); return 0; }

@@ -975,6 +975,44 @@ __global__ void factor_diag_kernel(DevSym sym, const double *__restrict__ Lx, do
     diag[k] = Lx[sym.px[s] + j + j * nsrow];
 }
 
+// Complex Hermitian factors through the real kernels (t_cholmod_super_numeric.c:41-83 are the reference's zherk/zgemm/zpotrf/
+// ztrsm instantiations).  With every complex entry a+ib replaced by the 2x2 block [a -b; b a] (rows/columns 2i, 2i+1), a
+// Hermitian positive definite A becomes a real SPD matrix of twice the order whose Cholesky factor is exactly the
+// blockified complex factor (its diagonal blocks are l*I with l real and positive, so it is lower triangular, and the
+// Cholesky factor is unique).  These two kernels convert between the blockified real factor (the plan's d_Lx, supernode s =
+// 2nsrow x 2nscol at px2[s]) and CHOLMOD's complex layout (nsrow x nscol interleaved (re,im) pairs at pxc[s]).
+__global__ void cplx_compress_kernel(const long long *__restrict__ pxc, const long long *__restrict__ px2, const long long *__restrict__ pi2,
+                                     long long nsuper, long long xsize_c, const double *__restrict__ Lt, double *__restrict__ Lc)
+{
+    const long long e = blockIdx.x * (long long) blockDim.x + threadIdx.x;       // complex entry
+    if (e >= xsize_c) return;
+    long long lo = 0, hi = nsuper;                                                // supernode with pxc[s] <= e < pxc[s+1]
+    while (hi - lo > 1) { const long long mid = (lo + hi) >> 1; if (pxc[mid] <= e) lo = mid; else hi = mid; }
+    const long long s = lo, nsrow2 = pi2[s + 1] - pi2[s], nsrow = nsrow2 >> 1;
+    const long long q = e - pxc[s];
+    if (q >= nsrow * ((px2[s + 1] - px2[s]) / (2 * nsrow2))) { Lc[2 * e] = 0.0; Lc[2 * e + 1] = 0.0; return; }   // padding behind the block
+    const long long i = q % nsrow, j = q / nsrow;
+    const double *__restrict__ col = Lt + px2[s] + (2 * j) * nsrow2;
+    Lc[2 * e] = col[2 * i]; Lc[2 * e + 1] = col[2 * i + 1];
+}
+
+__global__ void cplx_expand_kernel(const long long *__restrict__ pxc, const long long *__restrict__ px2, const long long *__restrict__ pi2,
+                                   long long nsuper, long long xsize_c, const double *__restrict__ Lc, double *__restrict__ Lt)
+{
+    const long long e = blockIdx.x * (long long) blockDim.x + threadIdx.x;
+    if (e >= xsize_c) return;
+    long long lo = 0, hi = nsuper;
+    while (hi - lo > 1) { const long long mid = (lo + hi) >> 1; if (pxc[mid] <= e) lo = mid; else hi = mid; }
+    const long long s = lo, nsrow2 = pi2[s + 1] - pi2[s], nsrow = nsrow2 >> 1;
+    const long long q = e - pxc[s];
+    if (q >= nsrow * ((px2[s + 1] - px2[s]) / (2 * nsrow2))) return;
+    const long long i = q % nsrow, j = q / nsrow;
+    const double re = Lc[2 * e], im = (i == j) ? 0.0 : Lc[2 * e + 1];             // the diagonal of L is real
+    double *__restrict__ c0 = Lt + px2[s] + (2 * j) * nsrow2, *__restrict__ c1 = c0 + nsrow2;
+    c0[2 * i] = re; c0[2 * i + 1] = im;
+    c1[2 * i] = (i == j) ? 0.0 : -im; c1[2 * i + 1] = re;
+}
+
 __global__ void fill_int_kernel(int *p, long long n, int v)
 {
     const long long t = blockIdx.x * (long long) blockDim.x + threadIdx.x;
