@@ -167,6 +167,10 @@ int  cholmod_l_gpu_probe     (ssb_cholmod_common *Common);
 int  cholmod_l_gpu_allocate  (ssb_cholmod_common *Common);
 int  cholmod_l_gpu_deallocate(ssb_cholmod_common *Common);
 void cholmod_l_gpu_end       (ssb_cholmod_common *Common);
+/* Cholesky/cholmod_solve.c:1020 interposed for its main case (sys = CHOLMOD_A, real supernodal LL' factor held on one device,
+ * real dense B): B goes to the device once, P, L, L', P' are applied there, X (allocated by the host library) comes back once.
+ * Every other case is handed to the host library's own cholmod_l_solve. */
+ssb_cholmod_dense *cholmod_l_solve(int sys, ssb_cholmod_factor *L, ssb_cholmod_dense *B, ssb_cholmod_common *Common);
 /* Core/cholmod_factor.c:152 interposed: drops the cached device plan and the page-lock of L->x, then calls the host
  * library's own cholmod_l_free_factor (next definition in the symbol search order). */
 int  cholmod_l_free_factor   (ssb_cholmod_factor **L, ssb_cholmod_common *Common);

@@ -267,7 +267,12 @@ class Cholmod:
     def solve(self, Lp, B: np.ndarray, system: int = CHOLMOD_A) -> np.ndarray:
         cplx = np.iscomplexobj(B)
         Bd = self.dense(np.asfortranarray(B, dtype=np.complex128 if cplx else np.float64))
-        Xp = self.lib.cholmod_l_solve(system, Lp, C.byref(Bd), C.byref(self.cm))
+        # a C program resolves cholmod_l_solve to the interposed definition (device-side P, L, L', P' for the main case, else
+        # the host library's); ctypes resolves per handle, so pick the same one explicitly
+        lib = self.b200 if self.gpu else self.lib
+        if self.gpu:
+            lib.cholmod_l_solve.argtypes = self.lib.cholmod_l_solve.argtypes; lib.cholmod_l_solve.restype = self.lib.cholmod_l_solve.restype
+        Xp = lib.cholmod_l_solve(system, Lp, C.byref(Bd), C.byref(self.cm))
         if not Xp:
             raise RuntimeError(f"cholmod_l_solve failed, status {self.cm.status}")
         dt = np.complex128 if Xp.contents.xtype == CHOLMOD_COMPLEX else np.float64

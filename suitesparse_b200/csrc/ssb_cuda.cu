@@ -4,6 +4,7 @@
 #include "../../include/suitesparse_b200.h"
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <link.h>
 #include <climits>
 #include <cstdio>
 #include <cstdlib>
@@ -1669,6 +1670,30 @@ typedef int (*error_fn)(int, const char *, int, const char *, ssb_cholmod_common
 
 static void *host_sym(const char *name) { return dlsym(RTLD_DEFAULT, name); }
 
+// The host library's own definition of a symbol this library interposes.  RTLD_NEXT finds it when we sit in front of it in the
+// main search order (LD_PRELOAD, link order).  When both libraries were dlopen'ed (ctypes), RTLD_NEXT only looks at our own
+// dependencies, so walk the loaded objects and take the first other definition.
+struct NextLookup { const char *name; void *self; void *found; };
+static int next_lookup_cb(struct dl_phdr_info *info, size_t, void *data)
+{
+    NextLookup *q = (NextLookup *) data;
+    if (q->found || !info->dlpi_name || !info->dlpi_name[0]) return 0;
+    void *h = dlopen(info->dlpi_name, RTLD_NOLOAD | RTLD_LAZY);
+    if (!h) return 0;
+    void *f = dlsym(h, q->name);
+    if (f && f != q->self) q->found = f;
+    dlclose(h);
+    return 0;
+}
+static void *next_definition(const char *name, void *self)
+{
+    void *f = dlsym(RTLD_NEXT, name);
+    if (f && f != self) return f;
+    NextLookup q{name, self, nullptr};
+    dl_iterate_phdr(next_lookup_cb, &q);
+    return q.found;
+}
+
 static int raise_error(ssb_cholmod_common *cm, int status, int line, const char *msg)
 {
     static error_fn f = (error_fn) host_sym("cholmod_l_error");
@@ -1691,6 +1716,8 @@ struct CacheEntry {
     void *pinned_ptr = nullptr;            // L->x range registered with cudaHostRegister (fast D2H into the caller's buffer)
     size_t pinned_bytes = 0;
     struct CplxAux *cx = nullptr;          // complex factor: the plan works on the real matrix of twice the order
+    long long *d_perm = nullptr;           // L->Perm on the device (cholmod_l_solve fast path)
+    double *d_B = nullptr; size_t capB = 0;
 };
 // complex / zomplex input (cholmod_super_numeric.c:81-86, t_cholmod_super_numeric.c:41-83): the blockified real problem
 struct CplxAux {
@@ -1734,7 +1761,7 @@ static void cplx_free(CplxAux *cx)
     for (void *q : {(void *) cx->d_pxc, (void *) cx->d_px2, (void *) cx->d_pi2, (void *) cx->d_Lc}) if (q) cudaFree(q);
     delete cx;
 }
-static void cache_drop(CacheEntry *e) { unpin(e); cplx_free(e->cx); plan_free(e->plan); mg_free(e->mg); g_cache.erase(g_cache.begin() + (e - g_cache.data())); }
+static void cache_drop(CacheEntry *e) { unpin(e); if (e->d_perm) cudaFree(e->d_perm); if (e->d_B) cudaFree(e->d_B); cplx_free(e->cx); plan_free(e->plan); mg_free(e->mg); g_cache.erase(g_cache.begin() + (e - g_cache.data())); }
 
 // SSB200_DEVICES = "0,1,2,3" | "all": the devices one factorization fans out over (two or more -> ssb200_mg_*)
 static std::vector<int> devices_from_env()
@@ -2132,6 +2159,68 @@ extern "C" int cholmod_l_super_ltsolve(ssb_cholmod_factor *L, ssb_cholmod_dense 
     return super_solve_common(L, X, E, Common, 1);
 }
 
+// ---- cholmod_l_solve (Cholesky/cholmod_solve.c:1020-1060 -> cholmod_solve2 :1097-1680) interposed for its main case: Ax = b with
+// a real supernodal LL' factor that lives on the device and a real dense B.  The reference permutes on the host (Y = P B,
+// :1552-1556), calls super_lsolve / super_ltsolve (two host<->device round trips of Y through our symbols) and permutes back
+// (:1578-1580).  Here B goes to the device once, P, L, L', P' are applied there, X comes back once.  Everything else (other
+// systems, simplicial or complex factors, sparse right-hand sides, the multi-GPU plan) goes to the host library's own
+// cholmod_l_solve, which still reaches the GPU through the interposed lsolve / ltsolve.
+typedef ssb_cholmod_dense *(*solve_fn)(int, ssb_cholmod_factor *, ssb_cholmod_dense *, ssb_cholmod_common *);
+typedef ssb_cholmod_dense *(*alloc_dense_fn)(size_t, size_t, size_t, int, ssb_cholmod_common *);
+extern "C" ssb_cholmod_dense *cholmod_l_solve(int sys, ssb_cholmod_factor *L, ssb_cholmod_dense *B, ssb_cholmod_common *Common)
+{
+    static solve_fn next = nullptr;
+    static alloc_dense_fn alloc_dense = (alloc_dense_fn) host_sym("cholmod_l_allocate_dense");
+    static int fast_on = -1;
+    if (fast_on < 0) { const char *v = getenv("SSB200_SOLVE_FAST"); fast_on = (v && atoi(v) == 0) ? 0 : 1; }
+    auto fallback = [&]() -> ssb_cholmod_dense * {
+        if (!next) next = (solve_fn) next_definition("cholmod_l_solve", (void *) &cholmod_l_solve);
+        if (!next) { if (Common) Common->status = SSB_CHOLMOD_INVALID; return nullptr; }
+        return next(sys, L, B, Common);
+    };
+    const bool fast = fast_on && alloc_dense && Common && L && B && sys == 0 /* CHOLMOD_A */ && Common->itype == SSB_CHOLMOD_LONG && Common->dtype == SSB_CHOLMOD_DOUBLE &&
+                      L->is_super && L->is_ll && L->xtype == SSB_CHOLMOD_REAL && L->x && L->itype == SSB_CHOLMOD_LONG && L->minor == L->n &&
+                      B->xtype == SSB_CHOLMOD_REAL && B->x && B->nrow == L->n && B->d >= B->nrow && L->n > 0 && B->ncol > 0 && gpu_enabled_by_env();
+    if (!fast) return fallback();
+    ssb_cholmod_dense *X = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_cache_mu);
+        CacheEntry *e = cache_find(L);
+        if (!e || e->mg || e->cx || !e->plan || !value_fingerprint_ok(e, L)) e = nullptr;       // only a factor this library holds on one device
+        if (e) {
+            ssb200_plan *p = e->plan;
+            const long long n = (long long) L->n; const int nrhs = (int) B->ncol;
+            bool ok = cudaSetDevice(p->device) == cudaSuccess;
+            if (ok && !e->d_perm && L->Perm) {
+                ok = cudaMalloc((void **) &e->d_perm, n * sizeof(long long)) == cudaSuccess &&
+                     cudaMemcpyAsync(e->d_perm, L->Perm, n * sizeof(long long), cudaMemcpyHostToDevice, p->stream) == cudaSuccess;
+            }
+            const size_t need = (size_t) n * nrhs;
+            if (ok && e->capB < need) { if (e->d_B) cudaFree(e->d_B); e->d_B = nullptr; e->capB = 0; ok = cudaMalloc((void **) &e->d_B, need * sizeof(double)) == cudaSuccess; if (ok) e->capB = need; }
+            if (ok) ok = ensure_cap(p, &p->d_X, &p->capX, need) == 0;
+            if (ok) X = alloc_dense((size_t) n, (size_t) nrhs, (size_t) n, SSB_CHOLMOD_REAL, Common);
+            ok = ok && X != nullptr;
+            if (ok) {
+                const unsigned g = (unsigned) ((n + 255) / 256);
+                ok = cudaMemcpy2DAsync(e->d_B, n * sizeof(double), B->x, B->d * sizeof(double), n * sizeof(double), nrhs, cudaMemcpyHostToDevice, p->stream) == cudaSuccess;
+                if (ok) perm_gather_kernel<<<g, 256, 0, p->stream>>>(e->d_perm, e->d_B, n, p->d_X, n, nrhs);
+                ok = ok && ssb200_solve_resident(p, 2, p->d_X, nrhs, n) == 0;
+                if (ok) perm_scatter_kernel<<<g, 256, 0, p->stream>>>(e->d_perm, p->d_X, e->d_B, n, n, nrhs);
+                ok = ok && cudaMemcpyAsync(X->x, e->d_B, need * sizeof(double), cudaMemcpyDeviceToHost, p->stream) == cudaSuccess &&
+                     cudaStreamSynchronize(p->stream) == cudaSuccess && cudaGetLastError() == cudaSuccess;
+                if (ok) { Common->status = SSB_CHOLMOD_OK; return X; }
+            }
+            (void) cudaGetLastError();
+        }
+    }
+    if (X) {            // the device path failed half way: give the workspace back and let the host library do it
+        typedef int (*free_dense_fn)(ssb_cholmod_dense **, ssb_cholmod_common *);
+        static free_dense_fn free_dense = (free_dense_fn) host_sym("cholmod_l_free_dense");
+        if (free_dense) free_dense(&X, Common);
+    }
+    return fallback();
+}
+
 // ---- cholmod_l_gpu_* (GPU/cholmod_gpu.c:71,170,208,255,364): resource queries and teardown -------------------------
 extern "C" int cholmod_l_gpu_memorysize(size_t *total_mem, size_t *available_mem, ssb_cholmod_common *Common)
 {
@@ -2191,8 +2280,8 @@ extern "C" int cholmod_l_free_factor(ssb_cholmod_factor **LHandle, ssb_cholmod_c
         std::lock_guard<std::mutex> lk(g_cache_mu);
         if (CacheEntry *e = cache_find(*LHandle)) cache_drop(e);
     }
-    static free_factor_fn next = (free_factor_fn) dlsym(RTLD_NEXT, "cholmod_l_free_factor");
-    if (!next) next = (free_factor_fn) dlsym(RTLD_NEXT, "cholmod_l_free_factor");
+    static free_factor_fn next = nullptr;
+    if (!next) next = (free_factor_fn) next_definition("cholmod_l_free_factor", (void *) &cholmod_l_free_factor);
     if (!next) { if (Common) Common->status = SSB_CHOLMOD_INVALID; return 0; }
     return next(LHandle, Common);
 }

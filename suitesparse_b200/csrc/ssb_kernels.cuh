@@ -975,6 +975,24 @@ __global__ void factor_diag_kernel(DevSym sym, const double *__restrict__ Lx, do
     diag[k] = Lx[sym.px[s] + j + j * nsrow];
 }
 
+// Y = P B and X = P' Y of cholmod_solve2 (Cholesky/cholmod_solve.c:1552-1580) on the device: Y(k,:) = B(Perm[k],:), X(Perm[k],:) = Y(k,:)
+__global__ void perm_gather_kernel(const long long *__restrict__ perm, const double *__restrict__ B, long long ldb, double *__restrict__ Y,
+                                   long long n, int nrhs)
+{
+    const long long k = blockIdx.x * (long long) blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const long long src = perm ? perm[k] : k;
+    for (int r = 0; r < nrhs; r++) Y[k + r * n] = B[src + r * ldb];
+}
+__global__ void perm_scatter_kernel(const long long *__restrict__ perm, const double *__restrict__ Y, double *__restrict__ X, long long ldx,
+                                    long long n, int nrhs)
+{
+    const long long k = blockIdx.x * (long long) blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const long long dst = perm ? perm[k] : k;
+    for (int r = 0; r < nrhs; r++) X[dst + r * ldx] = Y[k + r * n];
+}
+
 // Complex Hermitian factors through the real kernels (t_cholmod_super_numeric.c:41-83 are the reference's zherk/zgemm/zpotrf/
 // ztrsm instantiations).  With every complex entry a+ib replaced by the 2x2 block [a -b; b a] (rows/columns 2i, 2i+1), a
 // Hermitian positive definite A becomes a real SPD matrix of twice the order whose Cholesky factor is exactly the

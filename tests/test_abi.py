@@ -105,6 +105,37 @@ def test_invalid_arguments_without_gpu():
     assert g(C.byref(L), C.byref(X), C.byref(E), C.byref(cm)) == 1 and cm.status == 0
 
 
+def test_interposed_host_functions_reach_the_host_library():
+    """cholmod_l_free_factor and cholmod_l_solve are interposed and hand over to the host library's own definitions.  With
+    both libraries dlopen'ed (ctypes) RTLD_NEXT alone does not find them - the walk over the loaded objects must.
+    (In a child process: loading the B200 library globally rebinds the host library's hot-path calls for the whole process.)"""
+    from conftest import REF_LIB
+    if not os.path.exists(REF_LIB):
+        pytest.skip("reference build (host libcholmod) not present")
+    code = """
+import numpy as np, scipy.sparse as sp, sys
+sys.path.insert(0, %r)
+from suitesparse_b200 import gen, cholmod_host as H
+ch = H.Cholmod(gpu=True)
+A, p = gen.make_problem("lap7", 5)
+S = ch.sparse(A, +1)
+L = ch.analyze(S, p)
+before = ch.cm.malloc_count
+ch.free_factor(L)                                   # interposed -> host: the factor's arrays are really freed
+assert ch.cm.malloc_count < before and ch.cm.status == 0, (before, ch.cm.malloc_count, ch.cm.status)
+# a simplicial factor (CPU, host library) solved through the interposed cholmod_l_solve: not the fast path -> host's own
+L2 = ch.analyze(S, p, supernodal=H.CHOLMOD_SIMPLICIAL)
+assert ch.factorize(S, L2) == 1
+x = ch.solve(L2, np.ones(A.shape[0]))
+Af = A + sp.triu(A, 1).T
+assert np.linalg.norm(Af @ x - 1.0) / np.sqrt(A.shape[0]) < 1e-12
+ch.free_factor(L2)
+print("OK")
+""" % REPO
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "OK" in r.stdout, r.stderr[-2000:]
+
+
 def test_header_is_plain_c_and_example_links(tmp_path):
     """include/suitesparse_b200.h compiles as C99 and examples/plain_demo.c links against the library (no run: no GPU here)."""
     exe = tmp_path / "plain_demo"

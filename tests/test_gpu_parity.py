@@ -304,6 +304,41 @@ def test_solve_leading_dimension_and_many_rhs():
     ch.free_factor(L)
 
 
+def test_interposed_cholmod_l_solve_fast_path():
+    """cholmod_l_solve(CHOLMOD_A) interposed: P, L, L', P' on the device in one round trip.  Must equal the host library's own
+    composition of the partial systems (CHOLMOD_P, L, Lt, Pt go to its cholmod_l_solve, which reaches the GPU through the
+    interposed lsolve / ltsolve), also for several right-hand sides with a leading dimension larger than n."""
+    from suitesparse_b200 import gen, cholmod_host as H
+    ch = H.Cholmod(gpu=True)
+    A, p = gen.make_problem("lap27", 12)
+    S = ch.sparse(A, +1); L = ch.analyze(S, p)
+    assert ch.factorize(S, L) == 1
+    n = A.shape[0]
+    rng = np.random.default_rng(42)
+    B = rng.standard_normal((n, 4))
+    X = ch.solve(L, B)                                                   # fast path
+    Y = ch.solve(L, B, system=H.CHOLMOD_P)
+    Y = ch.solve(L, Y, system=H.CHOLMOD_L)
+    Y = ch.solve(L, Y, system=H.CHOLMOD_Lt)
+    Xh = ch.solve(L, Y, system=H.CHOLMOD_Pt)                             # host composition
+    assert np.abs(X - Xh).max() < 1e-12 * np.abs(Xh).max()
+    Af = A + sp.triu(A, 1).T
+    assert np.linalg.norm(Af @ X - B) / np.linalg.norm(B) < TOL_RESID
+    # leading dimension d > nrow
+    d = n + 5
+    buf = np.full((d, 2), np.nan, order="F"); buf[:n, :] = B[:, :2]
+    Bd = H.Dense(); Bd.nrow = n; Bd.ncol = 2; Bd.d = d; Bd.nzmax = d * 2; Bd.x = buf.ctypes.data; Bd.xtype = H.CHOLMOD_REAL
+    ch.b200.cholmod_l_solve.restype = C.POINTER(H.Dense)
+    ch.b200.cholmod_l_solve.argtypes = [C.c_int, C.POINTER(H.Factor), C.POINTER(H.Dense), C.POINTER(H.Common)]
+    Xp = ch.b200.cholmod_l_solve(H.CHOLMOD_A, L, C.byref(Bd), C.byref(ch.cm))
+    assert Xp and Xp.contents.nrow == n and Xp.contents.ncol == 2 and Xp.contents.d == n
+    X2 = H._np_view(Xp.contents.x, n * 2, np.float64).reshape((n, 2), order="F")
+    assert np.abs(X2 - X[:, :2]).max() < 1e-13 * np.abs(X).max()
+    pp = C.POINTER(H.Dense)(Xp.contents); ch.lib.cholmod_l_free_dense(C.byref(pp), C.byref(ch.cm))
+    ch.free_factor(L)
+    assert ch.cm.malloc_count >= 0
+
+
 def test_block_solve_schedule(monkeypatch):
     """SSB200_SOLVE_BLK=1: the big supernodes are solved in fused 256-column block steps (solve_blk_kernel: diagonal CTA and
     row-tile CTAs in one launch).  Off by default (measured slower than the 64-column steps); must give the same solution,
