@@ -1,0 +1,12 @@
+"""Cold start of the drop-in path: analyze, then the FIRST cholmod_l_super_numeric (plan build, L->x allocation + page-lock,
+factorization, host copy) and the second one, timed on the host."""
+import sys, time, ctypes as C, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench
+from suitesparse_b200.cholmod_host import Cholmod
+ch = Cholmod(gpu=True)
+A, perm, S, Lp, S2, t_an = bench.build_problem(ch, "lap7", int(sys.argv[1]) if len(sys.argv) > 1 else 128)
+f = ch.hot("cholmod_l_super_numeric"); beta = (C.c_double * 2)(0.0, 0.0)
+for it in range(3):
+    t0 = time.perf_counter(); ok = f(S2, None, beta, Lp, C.byref(ch.cm)); t1 = time.perf_counter()
+    print("call %d: %.3f s  ok=%d status=%d" % (it, t1 - t0, ok, ch.cm.status), flush=True)

@@ -1274,6 +1274,7 @@ extern "C" ssb200_mg *ssb200_mg_create(ssb_long n, ssb_long nsuper, const ssb_lo
     return m;
 }
 
+static void touch_pages_parallel(void *ptr, size_t bytes);
 // Page-lock the host factor for ALL devices (every device copies its own share out over its own PCIe link).
 extern "C" int ssb200_mg_pin_host(ssb200_mg *m, double *Lx_host)
 {
@@ -1282,6 +1283,7 @@ extern "C" int ssb200_mg_pin_host(ssb200_mg *m, double *Lx_host)
     if (m->pinned_ptr == Lx_host && m->pinned_bytes == bytes) return 0;
     if (m->pinned_ptr) { if (cudaHostUnregister(m->pinned_ptr) != cudaSuccess) (void) cudaGetLastError(); m->pinned_ptr = nullptr; }
     if (!Lx_host || bytes == 0) return 0;
+    touch_pages_parallel(Lx_host, bytes);
     if (cudaHostRegister(Lx_host, bytes, cudaHostRegisterPortable) != cudaSuccess) { (void) cudaGetLastError(); return 1; }   // best effort
     m->pinned_ptr = Lx_host; m->pinned_bytes = bytes;
     return 0;
@@ -1802,6 +1804,29 @@ static bool pin_probe(CacheEntry *e, const ssb_cholmod_factor *L)
     return ok;
 }
 
+// Experiment (SSB200_PRETOUCH=1, off by default): cudaHostRegister on a fresh 29 GB L->x takes 10-14 s of the first call.
+// Touching the pages from 16 threads first (a write of the byte that is already there: existing values survive) did NOT
+// help on the B200 boxes - 16.2 s against 14.4 s for the first call at lap7 128^3: the time is the pinning, not the faults.
+static void touch_pages_parallel(void *ptr, size_t bytes)
+{
+    if (bytes < ((size_t) 256 << 20)) return;
+    static int on = -1;
+    if (on < 0) { const char *v = getenv("SSB200_PRETOUCH"); on = (v && atoi(v) != 0) ? 1 : 0; }
+    if (!on) return;
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const unsigned nt = std::min(16u, hw);
+    const size_t page = 4096, slice = ((bytes / nt) / page + 1) * page;
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nt; t++)
+        th.emplace_back([=] {
+            volatile char *q = (volatile char *) ptr;
+            const size_t lo = (size_t) t * slice, hi = std::min(bytes, lo + slice);
+            for (size_t o = lo; o < hi; o += page) q[o] = q[o];
+            if (hi == bytes && bytes > 0) q[bytes - 1] = q[bytes - 1];
+        });
+    for (auto &x : th) x.join();
+}
+
 static void pin_host_x(CacheEntry *e, const ssb_cholmod_factor *L)
 {
     static int enabled = -1;
@@ -1814,6 +1839,7 @@ static void pin_host_x(CacheEntry *e, const ssb_cholmod_factor *L)
         unpin(e);                                       // stale: the pages behind this range were replaced
     } else unpin(e);
     if (L->xsize < (1u << 16)) return;                   // not worth it for small factors
+    touch_pages_parallel(L->x, bytes);
     cudaError_t err = cudaHostRegister(L->x, bytes, cudaHostRegisterDefault);
     if (err != cudaSuccess) {
         (void) cudaGetLastError();
