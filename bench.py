@@ -440,9 +440,16 @@ def main():
         raise SystemExit(f"factorize failed: status {ch.cm.status}")
     pl = plain.plan_of_factor(Lp)
     sampler = ClockSampler(local); sampler.start()
+    first_staged = bool(pl.stats().get("d2h_staged", 0))
+    # the default policy page-locks L->x only after 32 factorizations into it; the timed calls below are pinned to the
+    # behaviour of the first 32 (staging ring) whatever --steps is; the page-locked variant is timed afterwards
+    ch.b200.ssb200_set_pin_policy.restype = C.c_int; ch.b200.ssb200_set_pin_policy.argtypes = [C.c_int]
+    if world == 1: ch.b200.ssb200_set_pin_policy(0)
     e2e_warm = 1
+    t0 = time.perf_counter()
     for _ in range(e2e_warm):
         f_numeric(S2, None, beta, Lp, C.byref(ch.cm))
+    t_second = time.perf_counter() - t0
     if dist: dist.barrier()
     torch.cuda.synchronize(dev)
     t0 = time.perf_counter()
@@ -453,6 +460,21 @@ def main():
     torch.cuda.synchronize(dev)
     t_e2e = (time.perf_counter() - t0) / args.steps
     st_e2e = pl.stats()
+    # the same call into a page-locked L->x (SSB200_PIN_HOST=2, or the default policy after 32 refactorizations)
+    t_locked = t_lock = None
+    if world == 1:
+        assert st_e2e.get("d2h_staged", 0) == 1
+        ch.b200.ssb200_set_pin_policy(2)
+        t0 = time.perf_counter()
+        f_numeric(S2, None, beta, Lp, C.byref(ch.cm))
+        t_lock = time.perf_counter() - t0
+        ns = max(1, min(3, args.steps))
+        torch.cuda.synchronize(dev); t0 = time.perf_counter()
+        for _ in range(ns):
+            f_numeric(S2, None, beta, Lp, C.byref(ch.cm))
+        t_locked = (time.perf_counter() - t0) / ns
+        assert pl.stats().get("d2h_staged", 0) == 0
+        ch.b200.ssb200_set_pin_policy(-1)
 
     # ---- value: resident factorization (A already uploaded by the calls above), CUDA-event time from the plan
     for _ in range(args.warmup):
@@ -524,12 +546,17 @@ def main():
                "config": {"workload": workload, "n": n, "nnz_tril_A": int(S2.contents.nzmax), "fl": fl, "lnz": lnz, "nsuper": int(nsuper), "xsize": int(xsize),
                           "levels": st_e2e["nlevels"], "updates": st_e2e["nupdates"], "l2": "inputs_exceed_l2 (L is %.1f GB)" % (xsize * 8 / 1e9),
                           "parallelism": "1 GPU",
-                          "analyze_s_host": round(t_an, 2), "first_call_s": round(t_first, 2),
+                          "analyze_s_host": round(t_an, 2), "first_call_s": round(t_first, 2), "first_call_staged": first_staged,
+                          "second_call_s": round(t_second, 2),
                           "hot_path_library": os.path.relpath(ch.b200._name, REPO),
                           "host_cholmod_for_analyze_only": os.path.relpath(ch.lib._name, REPO),
                           "reference_blas_calls_during_our_steps": int(ch.cm.cpu_syrk_calls + ch.cm.cpu_gemm_calls + ch.cm.cpu_potrf_calls + ch.cm.cpu_trsm_calls)},
                "e2e": {"value": round(e2e_v, 1), "unit": "GFLOP/s", "h2d_bytes_per_step": a_bytes, "d2h_bytes_per_step": int(xsize) * 8,
-                       "ms_per_step": round(t_host * 1e3, 2), "call": "cholmod_l_super_numeric(S,NULL,beta,L,Common) via the interposed C ABI, host buffers, L->x page-locked once",
+                       "ms_per_step": round(t_host * 1e3, 2), "call": "cholmod_l_super_numeric(S,NULL,beta,L,Common) via the interposed C ABI, host buffers; pageable L->x, the factor leaves "
+                               "through the pinned staging ring (default for the first 32 factorizations into one L->x)" if world == 1 else
+                               "cholmod_l_super_numeric(S,NULL,beta,L,Common) via the interposed C ABI, host buffers, L->x page-locked once",
+                       "page_locked_ms_per_step": round(t_locked * 1e3, 2) if t_locked else None,
+                       "page_lock_call_s": round(t_lock, 2) if t_lock else None,
                        "ms_h2d": round(st_e2e["ms_h2d"], 2), "ms_d2h_exposed": round(st_e2e["ms_d2h"], 2), "ms_device_factorize": round(st_e2e["ms_total"], 2)},
                "gpu_launches": int(launches),
                "clocks": clocks,

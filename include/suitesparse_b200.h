@@ -177,6 +177,10 @@ int  cholmod_l_free_factor   (ssb_cholmod_factor **L, ssb_cholmod_common *Common
 /* The drop-in entry points fan one factorization out over the devices listed in $SSB200_DEVICES ("0,1,2,3" or "all";
  * two or more -> ssb200_mg_*); this returns the multi-GPU plan cached for L, or NULL. */
 struct ssb200_mg *ssb200_mg_of_factor(const ssb_cholmod_factor *L);
+/* When the drop-in layer page-locks L->x (same values as the SSB200_PIN_HOST environment variable): 0 never - every
+   factorization leaves through the pinned staging ring; 1 (default) once the same L->x has been factorized into
+   SSB200_PIN_AFTER (32) times; 2 at the first call; -1 back to the environment's setting.  Returns the previous policy. */
+int ssb200_set_pin_policy(int policy);
 /* Complex and zomplex matrices (cholmod_super_numeric.c:81-86) go through the real kernels: every entry a+ib becomes the block
  * [a -b; b a]; the Cholesky factor of that real SPD matrix of order 2n is the blockified complex factor, which is written to
  * L->x in CHOLMOD's complex layout.  Test hook: the blockified copy of A (lower != 0: symmetric-lower input). */
@@ -311,6 +315,7 @@ typedef struct ssb200_stats {
     double   ms_kind[6];                      /* device time (CUDA events on the plan's stream) */
     double   flops_kind[6];                   /* algorithmic flops executed by that kernel */
     ssb_long launches_kind[6];
+    ssb_long d2h_staged;                      /* last factorize: 1 = the factor went to pageable host memory through the pinned staging ring */
 } ssb200_stats;
 int ssb200_get_stats(const ssb200_plan *plan, ssb200_stats *out);
 

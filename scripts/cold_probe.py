@@ -7,6 +7,6 @@ from suitesparse_b200.cholmod_host import Cholmod
 ch = Cholmod(gpu=True)
 A, perm, S, Lp, S2, t_an = bench.build_problem(ch, "lap7", int(sys.argv[1]) if len(sys.argv) > 1 else 128)
 f = ch.hot("cholmod_l_super_numeric"); beta = (C.c_double * 2)(0.0, 0.0)
-for it in range(3):
+for it in range(4):
     t0 = time.perf_counter(); ok = f(S2, None, beta, Lp, C.byref(ch.cm)); t1 = time.perf_counter()
     print("call %d: %.3f s  ok=%d status=%d" % (it, t1 - t0, ok, ch.cm.status), flush=True)

@@ -41,26 +41,113 @@ struct DevJobs {
 
 // Device-to-host streaming runs on a helper thread: cudaMemcpyAsync into cudaHostRegister'ed (4 KiB-paged) memory costs
 // the CALLING thread ~100 us per 50 MB (DMA descriptors), which would starve the latency-bound potrf/trsm launch chain.
-struct CopyJob { cudaEvent_t gate; const double *src; double *dst; size_t bytes; };
+//
+// Two kinds of destination.  Page-locked L->x: the copy goes straight there.  Pageable L->x (the first factorization into a
+// fresh factor: page-locking 29 GB of untouched memory costs 9.4 s, scripts/pin_probe.cu): the copy is STAGED - the DMA
+// lands in a small ring of driver-allocated pinned slots and a pool of host threads moves each slot into L->x while the
+// next slots are in flight (16 threads move 31 GB into untouched pageable memory in 1.07 s, 0.25 s once the pages exist).
+struct CopyJob { cudaEvent_t gate; const double *src; double *dst; size_t bytes; bool staged; };
+
+// K threads that split one memcpy; the caller blocks until it is done
+struct HostMover {
+    std::vector<std::thread> th; std::mutex mu; std::condition_variable cv, done_cv;
+    const char *src = nullptr; char *dst = nullptr; size_t bytes = 0; unsigned long long gen = 0; int remaining = 0, K = 0; bool stop = false;
+    void start(int k) { K = k; if (K > 1) for (int t = 0; t < K; t++) th.emplace_back([this, t] { run(t); }); }
+    void run(int t)
+    {
+        unsigned long long seen = 0;
+        for (;;) {
+            std::unique_lock<std::mutex> lk(mu);
+            cv.wait(lk, [&] { return stop || gen != seen; });
+            if (stop) return;
+            seen = gen; const char *s = src; char *d = dst; const size_t n = bytes;
+            lk.unlock();
+            const size_t per = ((n / K) + 4096) & ~(size_t) 4095, lo = std::min(n, per * t), hi = std::min(n, lo + per);
+            if (hi > lo) memcpy(d + lo, s + lo, hi - lo);
+            lk.lock();
+            if (--remaining == 0) done_cv.notify_one();
+        }
+    }
+    void copy(char *d, const char *s, size_t n)
+    {
+        if (n < ((size_t) 1 << 20) || K <= 1) { memcpy(d, s, n); return; }
+        std::unique_lock<std::mutex> lk(mu);
+        src = s; dst = d; bytes = n; remaining = K; gen++;
+        cv.notify_all();
+        done_cv.wait(lk, [&] { return remaining == 0; });
+    }
+    void shutdown() { { std::lock_guard<std::mutex> lk(mu); stop = true; } cv.notify_all(); for (auto &t : th) t.join(); th.clear(); }
+};
+
 struct Copier {
     std::thread th; std::mutex mu; std::condition_variable cv; std::deque<CopyJob> q;
     bool stop = false; std::atomic<int> pending{0}; std::atomic<int> failed{0};
     int device = 0; cudaStream_t stream = nullptr;
+    // staging ring (allocated on first use)
+    char *ring = nullptr; size_t slot_bytes = 0; int nslots = 0; std::vector<cudaEvent_t> slot_ev; HostMover mover;
+    struct Piece { int slot; char *dst; size_t n; bool last; };
     void start(int dev, cudaStream_t s) { device = dev; stream = s; th = std::thread([this] { run(); }); }
+    int ensure_ring(size_t total_bytes)                    // called by the factorizing thread before staged jobs are pushed
+    {
+        if (ring) return 0;
+        size_t mb = 64; int ns = 4, k = (int) std::min(8u, std::max(2u, std::thread::hardware_concurrency() / 2));
+        if (const char *v = getenv("SSB200_STAGE_SLOT_MB")) mb = (size_t) std::max(1, atoi(v));
+        if (const char *v = getenv("SSB200_STAGE_SLOTS")) ns = std::max(2, atoi(v));
+        if (const char *v = getenv("SSB200_STAGE_THREADS")) k = std::max(1, atoi(v));
+        mb = std::max<size_t>(1, std::min(mb, (total_bytes / ns >> 20) + 1));      // a small factor gets a small ring
+        if (total_bytes < ((size_t) 64 << 20)) k = 1;
+        if (cudaHostAlloc((void **) &ring, mb * ns << 20, cudaHostAllocDefault) != cudaSuccess) { (void) cudaGetLastError(); ring = nullptr; return 1; }
+        slot_bytes = mb << 20; nslots = ns; slot_ev.resize(ns);
+        for (auto &e : slot_ev) if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return 1;
+        mover.start(k);
+        return 0;
+    }
     void run()
     {
         cudaSetDevice(device);
+        std::deque<Piece> outstanding;                     // staged pieces whose DMA was issued, oldest first
+        CopyJob cur{}; size_t cur_off = 0; bool have = false; int next_slot = 0;
         for (;;) {
-            CopyJob j;
-            { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [this] { return stop || !q.empty(); }); if (q.empty()) return; j = q.front(); q.pop_front(); }
-            if (j.gate && cudaStreamWaitEvent(stream, j.gate, 0) != cudaSuccess) failed++;
-            if (cudaMemcpyAsync(j.dst, j.src, j.bytes, cudaMemcpyDeviceToHost, stream) != cudaSuccess) failed++;
-            pending--;
+            if (!have) {
+                std::unique_lock<std::mutex> lk(mu);
+                if (outstanding.empty()) cv.wait(lk, [this] { return stop || !q.empty(); });
+                if (!q.empty()) { cur = q.front(); q.pop_front(); have = true; cur_off = 0; }
+                else if (outstanding.empty()) return;      // stop
+            }
+            if (have && !cur.staged) {
+                if (cur.gate && cudaStreamWaitEvent(stream, cur.gate, 0) != cudaSuccess) failed++;
+                if (cudaMemcpyAsync(cur.dst, cur.src, cur.bytes, cudaMemcpyDeviceToHost, stream) != cudaSuccess) failed++;
+                pending--; have = false;
+                continue;
+            }
+            if (have && (int) outstanding.size() < nslots) {
+                // the slot is free: pieces complete in the order they were issued
+                const int slot = next_slot; next_slot = (next_slot + 1) % nslots;
+                const size_t n = std::min(slot_bytes, cur.bytes - cur_off);
+                if (cur_off == 0 && cur.gate && cudaStreamWaitEvent(stream, cur.gate, 0) != cudaSuccess) failed++;
+                if (cudaMemcpyAsync(ring + (size_t) slot * slot_bytes, (const char *) cur.src + cur_off, n, cudaMemcpyDeviceToHost, stream) != cudaSuccess) failed++;
+                if (cudaEventRecord(slot_ev[slot], stream) != cudaSuccess) failed++;
+                outstanding.push_back(Piece{slot, (char *) cur.dst + cur_off, n, cur_off + n == cur.bytes});
+                cur_off += n;
+                if (cur_off == cur.bytes) have = false;
+                continue;
+            }
+            if (!outstanding.empty()) {
+                const Piece pc = outstanding.front(); outstanding.pop_front();
+                if (cudaEventSynchronize(slot_ev[pc.slot]) != cudaSuccess) failed++;
+                else mover.copy(pc.dst, ring + (size_t) pc.slot * slot_bytes, pc.n);
+                if (pc.last) pending--;
+            }
         }
     }
     void push(const CopyJob &j) { pending++; { std::lock_guard<std::mutex> lk(mu); q.push_back(j); } cv.notify_one(); }
+    // direct jobs: every copy has been enqueued on the copy stream; staged jobs: every byte is in its destination
     void drain() { while (pending.load() > 0) std::this_thread::yield(); }
-    void shutdown() { if (th.joinable()) { { std::lock_guard<std::mutex> lk(mu); stop = true; } cv.notify_one(); th.join(); } }
+    void shutdown()
+    {
+        if (th.joinable()) { { std::lock_guard<std::mutex> lk(mu); stop = true; } cv.notify_one(); th.join(); }
+        if (ring) { mover.shutdown(); cudaSetDevice(device); for (auto &e : slot_ev) cudaEventDestroy(e); cudaFreeHost(ring); ring = nullptr; }
+    }
 };
 
 // parameters baked into the captured factorization graph
@@ -623,7 +710,7 @@ static bool host_is_pinned(const void *ptr)
 // capture == true: the calls are being recorded into a CUDA graph (copies are issued here, the copy stream joins the
 // capture through the gate events and is joined back at the end); otherwise the helper thread issues the copies.
 static int enqueue_factorization(ssb200_plan *p, double beta0, double *Lx_host, bool streaming, bool capture, int stop_level,
-                                 bool two_streams, std::vector<std::pair<int, size_t>> &marks, size_t &ev)
+                                 bool two_streams, std::vector<std::pair<int, size_t>> &marks, size_t &ev, bool staged = false)
 {
     HostPlan &hp = p->hp;
     // per-launch events only make sense on one stream; events recorded by graph nodes cannot be used with cudaEventElapsedTime
@@ -665,7 +752,7 @@ static int enqueue_factorization(ssb200_plan *p, double beta0, double *Lx_host, 
                     if (capture)
                         CU_TRY(cudaMemcpyAsync(Lx_host + ct.off, p->d_Lx + ct.off, (size_t) ct.cnt * sizeof(double), cudaMemcpyDeviceToHost, p->copy_stream));
                     else
-                        p->copier->push(CopyJob{first ? gate : nullptr, p->d_Lx + ct.off, Lx_host + ct.off, (size_t) ct.cnt * sizeof(double)});
+                        p->copier->push(CopyJob{first ? gate : nullptr, p->d_Lx + ct.off, Lx_host + ct.off, (size_t) ct.cnt * sizeof(double), staged});
                 }
             }
         }
@@ -705,12 +792,17 @@ static int factorize_impl(ssb200_plan *p, const double beta[2], int quick_return
     static int stream_d2h = -1, use_graph = -2;
     if (stream_d2h < 0) { const char *v = getenv("SSB200_STREAM_D2H"); stream_d2h = (v && atoi(v) == 0) ? 0 : 1; }
     if (use_graph == -2) { const char *v = getenv("SSB200_FACTOR_GRAPH"); use_graph = v ? (atoi(v) ? 1 : 0) : -1; }
-    const bool streaming = Lx_host && stream_d2h && stop_level == INT_MAX && host_is_pinned(Lx_host);
+    // pageable destination: staged through a pinned ring by the helper thread (SSB200_STAGE_D2H=0: one plain copy at the end)
+    static int stage_d2h = -1;
+    if (stage_d2h < 0) { const char *v = getenv("SSB200_STAGE_D2H"); stage_d2h = (v && atoi(v) == 0) ? 0 : 1; }
+    const bool pinned_dst = Lx_host && host_is_pinned(Lx_host);
+    const bool staged = Lx_host && !pinned_dst && stage_d2h && (size_t) hp.xsize >= ((size_t) 1 << 16);
+    const bool streaming = Lx_host && stream_d2h && stop_level == INT_MAX && (pinned_dst || staged);
     // Graph replay (SSB200_FACTOR_GRAPH=1, or by default when the look-ahead is off and the factor streams to the host): with
     // ONE stream the ~2700 dependent launches otherwise wait behind the PCIe link that the streaming saturates (+24 us per
     // launch, round 1).  With the two-stream look-ahead schedule stream launches are faster than the replayed graph (1 125 vs
     // 1 134 ms end to end, 1 069 vs 1 083 ms resident), so that is the default.
-    const bool graph = stop_level == INT_MAX && (use_graph == 1 || (use_graph == -1 && streaming && !(p->lookahead && hp.n_events > 0)));
+    const bool graph = stop_level == INT_MAX && !(streaming && staged) && (use_graph == 1 || (use_graph == -1 && streaming && !(p->lookahead && hp.n_events > 0)));
     const bool two_streams = p->lookahead && hp.n_events > 0 && hp.nranks == 1;
     while ((int) p->la_events.size() < hp.n_events) { cudaEvent_t e; CU_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); p->la_events.push_back(e); }
     // everything the enqueue needs exists before a capture starts
@@ -721,6 +813,8 @@ static int factorize_impl(ssb200_plan *p, const double beta[2], int quick_return
         while (p->copy_gates.size() < groups) { cudaEvent_t e; CU_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); p->copy_gates.push_back(e); }
     }
     if (streaming && !graph && !p->copier) { p->copier = new Copier(); p->copier->start(p->device, p->copy_stream); }
+    if (streaming && staged && p->copier->ensure_ring((size_t) hp.xsize * sizeof(double))) { set_error("cannot allocate the pinned staging ring"); return SSB_CHOLMOD_GPU_PROBLEM; }
+    p->stats.d2h_staged = (streaming && staged) ? 1 : 0;
 
     std::vector<std::pair<int, size_t>> &marks = p->fg_marks;
     size_t ev = 0;
@@ -763,7 +857,7 @@ static int factorize_impl(ssb200_plan *p, const double beta[2], int quick_return
         CU_TRY(cudaGraphLaunch(p->fgraph, p->stream));
         CU_TRY(cudaEventRecord(p->events[1], p->stream));
     } else {
-        if (enqueue_factorization(p, beta0, Lx_host, streaming, false, stop_level, two_streams, marks, ev)) return SSB_CHOLMOD_GPU_PROBLEM;
+        if (enqueue_factorization(p, beta0, Lx_host, streaming, false, stop_level, two_streams, marks, ev, staged)) return SSB_CHOLMOD_GPU_PROBLEM;
     }
     CU_TRY(cudaStreamSynchronize(p->stream));
     // timings: events[0] start, [1] assembled, one per launch, end of compute (marks.back()), [ev-1] end of everything
@@ -795,8 +889,11 @@ static int factorize_impl(ssb200_plan *p, const double beta[2], int quick_return
     int status = 0;
     int sfail = -1;
     for (long long s = 0; s < hp.nsuper; s++) if (p->h_info[s] != INT_MAX) { sfail = (int) s; break; }
+    double staged_tail_ms = 0;
     if (streaming && !graph) {
-        p->copier->drain();                             // every copy has been enqueued on the copy stream
+        const auto t0 = std::chrono::steady_clock::now();
+        p->copier->drain();                             // every copy has been enqueued on the copy stream (staged: has arrived in L->x)
+        staged_tail_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
         if (p->copier->failed.load()) { p->copier->failed = 0; set_error("device-to-host streaming failed"); return SSB_CHOLMOD_GPU_PROBLEM; }
     }
     if (sfail >= 0) {
@@ -818,6 +915,7 @@ static int factorize_impl(ssb200_plan *p, const double beta[2], int quick_return
                 CU_TRY(cudaEventRecord(p->copy_done, p->copy_stream));
                 CU_TRY(cudaStreamSynchronize(p->copy_stream));
                 cudaEventElapsedTime(&ms, p->events[ev_compute_end], p->copy_done); p->stats.ms_d2h = ms > 0 ? ms : 0;
+                if (staged) p->stats.ms_d2h = staged_tail_ms;   // host time after the compute stream finished (DMA tail + the last moves)
             }
         } else {
             CU_TRY(cudaStreamSynchronize(p->copy_stream));
@@ -1716,6 +1814,7 @@ struct CacheEntry {
     std::vector<long long> sample_idx; std::vector<double> sample_val;   // fingerprint of the numeric values last written to L->x
     const void *xptr = nullptr;
     void *pinned_ptr = nullptr;            // L->x range registered with cudaHostRegister (fast D2H into the caller's buffer)
+    void *seen_x = nullptr; long seen_count = 0;   // L->x of the previous factorizations and how many went there (page-lock policy 1)
     size_t pinned_bytes = 0;
     struct CplxAux *cx = nullptr;          // complex factor: the plan works on the real matrix of twice the order
     long long *d_perm = nullptr;           // L->Perm on the device (cholmod_l_solve fast path)
@@ -1804,9 +1903,10 @@ static bool pin_probe(CacheEntry *e, const ssb_cholmod_factor *L)
     return ok;
 }
 
-// Experiment (SSB200_PRETOUCH=1, off by default): cudaHostRegister on a fresh 29 GB L->x takes 10-14 s of the first call.
-// Touching the pages from 16 threads first (a write of the byte that is already there: existing values survive) did NOT
-// help on the B200 boxes - 16.2 s against 14.4 s for the first call at lap7 128^3: the time is the pinning, not the faults.
+// SSB200_PRETOUCH=1 (off by default; only matters with SSB200_PIN_HOST=2, page-locking at the first call): touch the pages
+// of a fresh L->x from 16 threads before cudaHostRegister (a write of the byte that is already there: existing values
+// survive).  scripts/pin_probe.cu on a B200 box, 29 GB: register untouched 9.4 s; touch 0.9 s + register 3.2 s; register
+// resident pages 2.7 s.  Inside the first cholmod_l_super_numeric the gain did not show (16.2 s against 14.4 s).
 static void touch_pages_parallel(void *ptr, size_t bytes)
 {
     if (bytes < ((size_t) 256 << 20)) return;
@@ -1827,11 +1927,25 @@ static void touch_pages_parallel(void *ptr, size_t bytes)
     for (auto &x : th) x.join();
 }
 
+static int g_pin_policy = -1;               // SSB200_PIN_HOST, or ssb200_set_pin_policy
+extern "C" int ssb200_set_pin_policy(int policy)
+{
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    const int old = g_pin_policy;
+    g_pin_policy = policy < 0 ? -1 : std::min(2, policy);   // -1: back to the environment's
+    return old;
+}
+
 static void pin_host_x(CacheEntry *e, const ssb_cholmod_factor *L)
 {
-    static int enabled = -1;
-    if (enabled < 0) { const char *v = getenv("SSB200_PIN_HOST"); enabled = (v && atoi(v) == 0) ? 0 : 1; }
-    if (!enabled) return;
+    // SSB200_PIN_HOST: 0 = never page-lock L->x (every factorization leaves through the staging ring: 1.145 s per call at lap7
+    // 128^3, against 1.119 s into page-locked memory); 1 (default) = page-lock once the SAME L->x has been factorized into
+    // SSB200_PIN_AFTER (32) times - page-locking 29 GB costs 3.1 s even when the pages exist, which 26 ms per call only pays
+    // back after ~120 refactorizations, so a long loop is locked after it has spent a quarter of that; 2 = page-lock at
+    // the first call (9.4 s for a fresh 29 GB factor, the behaviour of round 1).
+    if (g_pin_policy < 0) { const char *v = getenv("SSB200_PIN_HOST"); g_pin_policy = v ? std::max(0, std::min(2, atoi(v))) : 1; }
+    const int enabled = g_pin_policy;
+    if (!enabled) { if (!e->mg) unpin(e); return; }
     if (e->mg) { ssb200_mg_pin_host(e->mg, (double *) L->x); return; }
     const size_t bytes = L->xsize * sizeof(double);
     if (e->pinned_ptr == L->x && e->pinned_bytes == bytes) {
@@ -1839,6 +1953,12 @@ static void pin_host_x(CacheEntry *e, const ssb_cholmod_factor *L)
         unpin(e);                                       // stale: the pages behind this range were replaced
     } else unpin(e);
     if (L->xsize < (1u << 16)) return;                   // not worth it for small factors
+    if (enabled == 1) {
+        static long after = -1;
+        if (after < 0) { const char *v = getenv("SSB200_PIN_AFTER"); after = v ? std::max(1, atoi(v)) : 32; }
+        if (e->seen_x != L->x) { e->seen_x = L->x; e->seen_count = 0; }
+        if (++e->seen_count <= after) return;               // staged copies until the loop has shown itself
+    }
     touch_pages_parallel(L->x, bytes);
     cudaError_t err = cudaHostRegister(L->x, bytes, cudaHostRegisterDefault);
     if (err != cudaSuccess) {
@@ -2084,9 +2204,14 @@ extern "C" int cholmod_l_super_numeric(ssb_cholmod_sparse *A, ssb_cholmod_sparse
         raise_error(Common, status, __LINE__, msg.c_str());
         return 0;
     };
+    static int vtime = -1;
+    if (vtime < 0) { const char *v = getenv("SSB200_VERBOSE"); vtime = (v && atoi(v)) ? 1 : 0; }
+    const auto tv0 = std::chrono::steady_clock::now();
     CacheEntry *e = cache_get_plan(L, cplx, cplx);
     if (!e) return fail(SSB_CHOLMOD_GPU_PROBLEM, ssb200_last_error());
+    const auto tv1 = std::chrono::steady_clock::now();
     if (!cplx) pin_host_x(e, L);
+    const auto tv2 = std::chrono::steady_clock::now();
     ssb_long minor = (ssb_long) L->n;
     const ssb_long *Anz_ = A->packed ? nullptr : (const ssb_long *) A->nz;
     const ssb_long *Fp_ = F ? (const ssb_long *) F->p : nullptr, *Fi_ = F ? (const ssb_long *) F->i : nullptr, *Fnz_ = (F && !F->packed) ? (const ssb_long *) F->nz : nullptr;
@@ -2108,6 +2233,12 @@ extern "C" int cholmod_l_super_numeric(ssb_cholmod_sparse *A, ssb_cholmod_sparse
         rc = ssb200_factorize(e->plan, stype, (const ssb_long *) A->p, (const ssb_long *) A->i, Anz_, (const double *) A->x, (ssb_long) A->ncol,
                               Fp_, Fi_, Fnz_, Fx_, beta, Common->quick_return_if_not_posdef, (double *) L->x, &minor);
     if (rc < 0) return fail(rc == SSB_CHOLMOD_INVALID ? SSB_CHOLMOD_INVALID : SSB_CHOLMOD_GPU_PROBLEM, ssb200_last_error());
+    if (vtime) {
+        const auto tv3 = std::chrono::steady_clock::now();
+        auto sec = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double>(b - a).count(); };
+        fprintf(stderr, "[suitesparse_b200] cholmod_l_super_numeric: plan %.3f s, page-lock %.3f s, factorize + copies %.3f s%s\n", sec(tv0, tv1), sec(tv1, tv2), sec(tv2, tv3),
+                (!e->mg && e->plan && e->plan->stats.d2h_staged) ? " (staged)" : "");
+    }
     take_value_fingerprint(e, L);
     // statistics the reference keeps in Common (cholmod_core.h:1002-1048)
     ssb200_stats st = e->mg ? e->mg->d[0].plan->stats : e->plan->stats;

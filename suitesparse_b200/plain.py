@@ -16,7 +16,8 @@ class Stats(C.Structure):
                 ("ms_factor", C.c_double), ("ms_d2h", C.c_double), ("ms_h2d", C.c_double),
                 ("bytes_update_panel", C.c_double), ("bytes_update_scatter", C.c_double),
                 ("device_bytes", c_long),
-                ("ms_kind", C.c_double * 6), ("flops_kind", C.c_double * 6), ("launches_kind", c_long * 6)]
+                ("ms_kind", C.c_double * 6), ("flops_kind", C.c_double * 6), ("launches_kind", c_long * 6),
+                ("d2h_staged", c_long)]
 
     def asdict(self):
         d = {k: getattr(self, k) for k, _ in self._fields_}

@@ -227,6 +227,16 @@ def test_stale_host_registration_is_detected():
     from suitesparse_b200 import gen, cholmod_host as H
     from oracle import oracle
     ch = H.Cholmod(gpu=True)
+    ch.b200.ssb200_set_pin_policy.restype = C.c_int; ch.b200.ssb200_set_pin_policy.argtypes = [C.c_int]
+    old = ch.b200.ssb200_set_pin_policy(2)                  # page-lock at the first call (the default waits for the second)
+    try:
+        _stale_registration_body(ch, H, oracle)
+    finally:
+        ch.b200.ssb200_set_pin_policy(old)
+
+
+def _stale_registration_body(ch, H, oracle):
+    from suitesparse_b200 import gen
     for rep, N in enumerate((14, 14, 15, 14, 13, 14)):
         A, p = gen.make_problem("lap7", N)
         S = ch.sparse(A, +1)
@@ -244,6 +254,45 @@ def test_stale_host_registration_is_detected():
         # was loaded): our interposed cholmod_l_free_factor is bypassed, so the cache keeps the stale page-lock
         pp = C.POINTER(H.Factor)(L.contents)
         ch.lib.cholmod_l_free_factor(C.byref(pp), C.byref(ch.cm))
+
+
+@pytest.mark.parametrize("kind,N", [("lap7", 24), ("elas", 10)])
+def test_staged_and_page_locked_copies_agree(kind, N):
+    """The factor reaches a pageable L->x through the pinned staging ring (first call / SSB200_PIN_HOST=0) and a page-locked
+    L->x directly; either way the host holds, bit for bit, the factor that is resident in HBM after that call.  (Two
+    factorizations differ in the last bits: conflicting updates of one launch are added with red.global.add.f64.)"""
+    from suitesparse_b200 import gen, cholmod_host as H, plain
+    ch = H.Cholmod(gpu=True)
+    ch.b200.ssb200_set_pin_policy.restype = C.c_int; ch.b200.ssb200_set_pin_policy.argtypes = [C.c_int]
+    old = ch.b200.ssb200_set_pin_policy(1)
+    try:
+        A, p = gen.make_problem(kind, N)
+        S = ch.sparse(A, +1); L = ch.analyze(S, p)
+        assert ch.factorize(S, L) == 1 and ch.cm.status == 0
+        pl = plain.plan_of_factor(L)
+        f = ch.factor_arrays(L)
+        assert f["xsize"] >= (1 << 16)
+        assert pl.stats()["d2h_staged"] == 1                # first call: pageable L->x
+        x_staged = f["x"].copy()
+        ref = np.empty_like(x_staged); pl.download_L(ref)
+        assert np.array_equal(x_staged, ref)
+        f["x"][:] = -7.0
+        ch.b200.ssb200_set_pin_policy(2)                    # page-lock now: direct copies
+        assert ch.factorize(S, L) == 1
+        assert pl.stats()["d2h_staged"] == 0
+        pl.download_L(ref)
+        assert np.array_equal(ch.factor_arrays(L)["x"], ref)
+        assert persuper_relerr(f["px"], ref, x_staged) < 1e-12
+        ch.b200.ssb200_set_pin_policy(0)                    # never page-lock: unpins, staged again
+        f["x"][:] = -7.0
+        assert ch.factorize(S, L) == 1
+        assert pl.stats()["d2h_staged"] == 1
+        pl.download_L(ref)
+        assert np.array_equal(ch.factor_arrays(L)["x"], ref)
+        assert persuper_relerr(f["px"], ref, x_staged) < 1e-12
+        ch.free_factor(L)
+    finally:
+        ch.b200.ssb200_set_pin_policy(old)
 
 
 def test_free_factor_drops_the_cached_plan():
