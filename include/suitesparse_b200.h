@@ -181,6 +181,8 @@ struct ssb200_mg *ssb200_mg_of_factor(const ssb_cholmod_factor *L);
    factorization leaves through the pinned staging ring; 1 (default) once the same L->x has been factorized into
    SSB200_PIN_AFTER (32) times; 2 at the first call; -1 back to the environment's setting.  Returns the previous policy. */
 int ssb200_set_pin_policy(int policy);
+/* Test hook, host only: copy src to dst with the staging ring's mover threads while the first-touch threads fault dst in. */
+int ssb200_debug_first_touch_copy(void *dst, const void *src, size_t bytes, int mover_threads, size_t slot_bytes);
 /* Complex and zomplex matrices (cholmod_super_numeric.c:81-86) go through the real kernels: every entry a+ib becomes the block
  * [a -b; b a]; the Cholesky factor of that real SPD matrix of order 2n is the blockified complex factor, which is written to
  * L->x in CHOLMOD's complex layout.  Test hook: the blockified copy of A (lower != 0: symmetric-lower input). */

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <link.h>
+#include <sys/mman.h>
 #include <climits>
 #include <cstdio>
 #include <cstdlib>
@@ -1927,6 +1928,66 @@ static void touch_pages_parallel(void *ptr, size_t bytes)
     for (auto &x : th) x.join();
 }
 
+// First factorization into a fresh (never touched) pageable L->x: the page faults of 29 GB are the largest part of that call
+// once the page-lock is gone (1.07 s even from 16 threads).  While the device works, a few threads walk L->x ahead of the
+// staged copies and fault the pages in with an atomic `or 0` on one word per page - a write fault that cannot lose a value
+// the moving threads store concurrently - after asking for transparent huge pages on the aligned interior (the boxes run
+// THP in `madvise` mode).  Joined before cholmod_l_super_numeric returns: nothing touches L->x behind the caller's back.
+struct FirstTouch {
+    std::vector<std::thread> th; std::atomic<bool> stop{false};
+    static inline void poke(volatile unsigned long long *w)
+    {
+#if defined(__x86_64__)
+        asm volatile("lock; orq $0, %0" : "+m"(*w) : : "memory");
+#else
+        __atomic_fetch_or((unsigned long long *) w, 0ULL, __ATOMIC_RELAXED);
+#endif
+    }
+    void start(void *ptr, size_t bytes)
+    {
+        size_t min_mb = 256; int on = 1;
+        if (const char *v = getenv("SSB200_FIRST_TOUCH")) on = atoi(v);
+        if (const char *v = getenv("SSB200_FIRST_TOUCH_MIN_MB")) min_mb = (size_t) std::max(0, atoi(v));
+        if (!on || bytes < (min_mb << 20) || bytes < 8192) return;
+        char *base = (char *) ptr;
+        {
+            const size_t huge = (size_t) 2 << 20;
+            char *a = (char *) (((size_t) base + huge - 1) & ~(huge - 1));
+            if (a < base + bytes) { const size_t len = (size_t) (base + bytes - a) & ~(huge - 1); if (len) (void) madvise(a, len, MADV_HUGEPAGE); }
+        }
+        const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+        int nt = (int) std::min(8u, hw > 12 ? hw - 10 : 2u);
+        if (const char *v = getenv("SSB200_FIRST_TOUCH_THREADS")) nt = std::max(1, atoi(v));
+        const size_t chunk = (size_t) 32 << 20, nchunk = (bytes + chunk - 1) / chunk;
+        for (int t = 0; t < nt; t++)
+            th.emplace_back([=] {
+                for (size_t c = t; c < nchunk && !stop.load(std::memory_order_relaxed); c += nt) {
+                    const size_t lo = c * chunk, hi = std::min(bytes, lo + chunk);
+                    // one aligned word per 4 KiB page of [lo, hi)
+                    size_t o = lo == 0 ? 0 : ((((size_t) base + lo + 4095) & ~(size_t) 4095) - (size_t) base);
+                    if (lo == 0) { poke((volatile unsigned long long *) base); o = (((size_t) base + 4096) & ~(size_t) 4095) - (size_t) base; }
+                    for (; o + 8 <= hi; o += 4096) poke((volatile unsigned long long *) (base + o));
+                }
+            });
+    }
+    void finish() { stop = true; for (auto &t : th) t.join(); th.clear(); }
+    ~FirstTouch() { finish(); }
+};
+
+// Host-only exerciser of the two helpers above (tests, no GPU needed): the page-touching threads run against a threaded
+// copy of src into dst, slot by slot as the staged copies do.
+extern "C" int ssb200_debug_first_touch_copy(void *dst, const void *src, size_t bytes, int mover_threads, size_t slot_bytes)
+{
+    if (!dst || !src || !slot_bytes) return 1;
+    HostMover mv; mv.start(std::max(1, mover_threads));
+    {
+        FirstTouch ft; ft.start(dst, bytes);
+        for (size_t o = 0; o < bytes; o += slot_bytes) mv.copy((char *) dst + o, (const char *) src + o, std::min(slot_bytes, bytes - o));
+    }
+    mv.shutdown();
+    return 0;
+}
+
 static int g_pin_policy = -1;               // SSB200_PIN_HOST, or ssb200_set_pin_policy
 extern "C" int ssb200_set_pin_policy(int policy)
 {
@@ -2191,7 +2252,9 @@ extern "C" int cholmod_l_super_numeric(ssb_cholmod_sparse *A, ssb_cholmod_sparse
     }
     // On failure L is given back in the form it had on input (cholmod_super_numeric.c:235-248): a factor that was symbolic
     // goes back to CHOLMOD_PATTERN (its freshly allocated L->x holds garbage), the plan and its page-lock are dropped.
+    FirstTouch first_touch;                              // joined before L->x can go away and before this function returns
     auto fail = [&](int status, const std::string &msg) {
+        first_touch.finish();
         if (CacheEntry *ce = cache_find(L)) {
             if (ce->plan) { ce->plan->factor_on_device = false; ce->plan->winv_valid = false; }
             if (ce->mg) ce->mg->factor_on_devices = false;
@@ -2212,6 +2275,7 @@ extern "C" int cholmod_l_super_numeric(ssb_cholmod_sparse *A, ssb_cholmod_sparse
     const auto tv1 = std::chrono::steady_clock::now();
     if (!cplx) pin_host_x(e, L);
     const auto tv2 = std::chrono::steady_clock::now();
+    if (symbolic && !cplx && !e->mg && L->xsize >= (1u << 16) && !host_is_pinned(L->x)) first_touch.start(L->x, L->xsize * sizeof(double));
     ssb_long minor = (ssb_long) L->n;
     const ssb_long *Anz_ = A->packed ? nullptr : (const ssb_long *) A->nz;
     const ssb_long *Fp_ = F ? (const ssb_long *) F->p : nullptr, *Fi_ = F ? (const ssb_long *) F->i : nullptr, *Fnz_ = (F && !F->packed) ? (const ssb_long *) F->nz : nullptr;

@@ -159,3 +159,26 @@ def test_plain_c_example_runs(tmp_path):
     x = np.linalg.solve(A, np.array([1.0, 2.0, 3.0]))
     got = [float(v) for v in re.search(r"x = ([-0-9.e]+) ([-0-9.e]+) ([-0-9.e]+)", r.stdout).groups()]
     assert np.allclose(got, x, atol=1e-5) and "L(0,0)=2.000000" in r.stdout
+
+
+def test_first_touch_threads_do_not_disturb_the_copies():
+    """The threads that fault a fresh L->x in (atomic `or 0` on one word per page) run against the threaded copies of the
+    staging ring; every byte must still arrive.  Host-only code of the library: no GPU needed."""
+    import mmap
+    import numpy as np
+    lib = C.CDLL(B200_LIB)
+    lib.ssb200_debug_first_touch_copy.restype = C.c_int
+    lib.ssb200_debug_first_touch_copy.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_size_t]
+    nbytes = 192 << 20
+    rng = np.random.default_rng(5)
+    src = rng.integers(0, 2**63, size=nbytes // 8, dtype=np.int64)
+    os.environ["SSB200_FIRST_TOUCH_MIN_MB"] = "0"; os.environ["SSB200_FIRST_TOUCH_THREADS"] = "6"
+    try:
+        for rep in range(3):
+            buf = mmap.mmap(-1, nbytes + 4096)                       # fresh, never touched pages every time
+            dst = np.frombuffer(buf, dtype=np.int64, count=nbytes // 8, offset=8 * (1 + rep))   # not page aligned
+            assert lib.ssb200_debug_first_touch_copy(dst.ctypes.data, src.ctypes.data, nbytes, 4, 8 << 20) == 0
+            assert np.array_equal(dst, src)
+            del dst; buf.close()
+    finally:
+        os.environ.pop("SSB200_FIRST_TOUCH_MIN_MB", None); os.environ.pop("SSB200_FIRST_TOUCH_THREADS", None)

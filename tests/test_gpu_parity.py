@@ -265,6 +265,8 @@ def test_staged_and_page_locked_copies_agree(kind, N):
     ch = H.Cholmod(gpu=True)
     ch.b200.ssb200_set_pin_policy.restype = C.c_int; ch.b200.ssb200_set_pin_policy.argtypes = [C.c_int]
     old = ch.b200.ssb200_set_pin_policy(1)
+    # the first call also runs the page-touching threads (normally only for factors of 256 MB and more) against the copies
+    os.environ["SSB200_FIRST_TOUCH_MIN_MB"] = "0"; os.environ["SSB200_FIRST_TOUCH_THREADS"] = "6"
     try:
         A, p = gen.make_problem(kind, N)
         S = ch.sparse(A, +1); L = ch.analyze(S, p)
@@ -293,6 +295,7 @@ def test_staged_and_page_locked_copies_agree(kind, N):
         ch.free_factor(L)
     finally:
         ch.b200.ssb200_set_pin_policy(old)
+        os.environ.pop("SSB200_FIRST_TOUCH_MIN_MB", None); os.environ.pop("SSB200_FIRST_TOUCH_THREADS", None)
 
 
 def test_free_factor_drops_the_cached_plan():
