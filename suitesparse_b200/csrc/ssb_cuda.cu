@@ -2006,31 +2006,38 @@ static void pin_host_x(CacheEntry *e, const ssb_cholmod_factor *L)
     // the first call (9.4 s for a fresh 29 GB factor, the behaviour of round 1).
     if (g_pin_policy < 0) { const char *v = getenv("SSB200_PIN_HOST"); g_pin_policy = v ? std::max(0, std::min(2, atoi(v))) : 1; }
     const int enabled = g_pin_policy;
-    if (!enabled) { if (!e->mg) unpin(e); return; }
-    if (e->mg) { ssb200_mg_pin_host(e->mg, (double *) L->x); return; }
     const size_t bytes = L->xsize * sizeof(double);
-    if (e->pinned_ptr == L->x && e->pinned_bytes == bytes) {
-        if (pin_probe(e, L)) return;
-        unpin(e);                                       // stale: the pages behind this range were replaced
-    } else unpin(e);
-    if (L->xsize < (1u << 16)) return;                   // not worth it for small factors
-    if (enabled == 1) {
-        static long after = -1;
-        if (after < 0) { const char *v = getenv("SSB200_PIN_AFTER"); after = v ? std::max(1, atoi(v)) : 32; }
-        if (e->seen_x != L->x) { e->seen_x = L->x; e->seen_count = 0; }
-        if (++e->seen_count <= after) return;               // staged copies until the loop has shown itself
-    }
-    touch_pages_parallel(L->x, bytes);
-    cudaError_t err = cudaHostRegister(L->x, bytes, cudaHostRegisterDefault);
-    if (err != cudaSuccess) {
-        (void) cudaGetLastError();
-        // a stale registration of another (freed) factor may overlap this range: drop those and retry once
+    // A page-lock this layer took for ANOTHER factor that was freed behind its back may still cover part of this L->x: the
+    // range would look page-locked to the factorization (cudaPointerGetAttributes) while its physical pages are new ones, and
+    // direct copies would land in the old pages.  Drop every such registration before L->x is used unregistered.
+    auto drop_stale_overlaps = [&]() {
         bool dropped = false;
         for (auto &o : g_cache) {
             if (&o == e || !o.pinned_ptr) continue;
             const char *a0 = (const char *) o.pinned_ptr, *a1 = a0 + o.pinned_bytes, *b0 = (const char *) L->x, *b1 = b0 + bytes;
             if (a0 < b1 && b0 < a1) { unpin(&o); dropped = true; }
         }
+        return dropped;
+    };
+    if (!enabled) { if (!e->mg) { unpin(e); drop_stale_overlaps(); } return; }
+    if (e->mg) { ssb200_mg_pin_host(e->mg, (double *) L->x); return; }
+    if (e->pinned_ptr == L->x && e->pinned_bytes == bytes) {
+        if (pin_probe(e, L)) return;
+        unpin(e);                                       // stale: the pages behind this range were replaced
+    } else unpin(e);
+    if (L->xsize < (1u << 16)) { drop_stale_overlaps(); return; }   // not worth it for small factors
+    if (enabled == 1) {
+        static long after = -1;
+        if (after < 0) { const char *v = getenv("SSB200_PIN_AFTER"); after = v ? std::max(1, atoi(v)) : 32; }
+        if (e->seen_x != L->x) { e->seen_x = L->x; e->seen_count = 0; }
+        if (++e->seen_count <= after) { drop_stale_overlaps(); return; }   // staged copies until the loop has shown itself
+    }
+    touch_pages_parallel(L->x, bytes);
+    cudaError_t err = cudaHostRegister(L->x, bytes, cudaHostRegisterDefault);
+    if (err != cudaSuccess) {
+        (void) cudaGetLastError();
+        // a stale registration of another (freed) factor may overlap this range: drop those and retry once
+        const bool dropped = drop_stale_overlaps();
         if (dropped) err = cudaHostRegister(L->x, bytes, cudaHostRegisterDefault);
         if (err != cudaSuccess) { (void) cudaGetLastError(); return; }
     }

@@ -254,6 +254,19 @@ def _stale_registration_body(ch, H, oracle):
         # was loaded): our interposed cholmod_l_free_factor is bypassed, so the cache keeps the stale page-lock
         pp = C.POINTER(H.Factor)(L.contents)
         ch.lib.cholmod_l_free_factor(C.byref(pp), C.byref(ch.cm))
+    # the default policy does not page-lock a new factor's L->x; a stale page-lock of a freed factor that covers it must not
+    # make the range look page-locked (direct copies would land in the old physical pages)
+    from suitesparse_b200 import plain
+    ch.b200.ssb200_set_pin_policy(1)
+    for rep, N in enumerate((14, 13, 14, 15)):
+        A, p = gen.make_problem("lap7", N)
+        S = ch.sparse(A, +1)
+        L = ch.analyze(S, p)
+        assert ch.factorize(S, L) == 1 and ch.cm.status == 0
+        pl = plain.plan_of_factor(L)
+        assert pl.stats()["d2h_staged"] == 1, f"repetition {rep}: a stale page-lock was trusted"
+        assert np.array_equal(ch.factor_arrays(L)["x"], pl.download_L(np.empty(ch.factor_arrays(L)["xsize"])))
+        ch.free_factor(L)
 
 
 @pytest.mark.parametrize("kind,N", [("lap7", 24), ("elas", 10)])
