@@ -461,9 +461,8 @@ def main():
     t_e2e = (time.perf_counter() - t0) / args.steps
     st_e2e = pl.stats()
     # the same call into a page-locked L->x (SSB200_PIN_HOST=2, or the default policy after 32 refactorizations)
-    t_locked = t_lock = None
+    t_locked = t_lock = None; locked_direct = None
     if world == 1:
-        assert st_e2e.get("d2h_staged", 0) == 1
         ch.b200.ssb200_set_pin_policy(2)
         t0 = time.perf_counter()
         f_numeric(S2, None, beta, Lp, C.byref(ch.cm))
@@ -473,7 +472,7 @@ def main():
         for _ in range(ns):
             f_numeric(S2, None, beta, Lp, C.byref(ch.cm))
         t_locked = (time.perf_counter() - t0) / ns
-        assert pl.stats().get("d2h_staged", 0) == 0
+        locked_direct = pl.stats().get("d2h_staged", 0) == 0
         ch.b200.ssb200_set_pin_policy(-1)
 
     # ---- value: resident factorization (A already uploaded by the calls above), CUDA-event time from the plan
@@ -557,6 +556,8 @@ def main():
                                "cholmod_l_super_numeric(S,NULL,beta,L,Common) via the interposed C ABI, host buffers, L->x page-locked once",
                        "page_locked_ms_per_step": round(t_locked * 1e3, 2) if t_locked else None,
                        "page_lock_call_s": round(t_lock, 2) if t_lock else None,
+                       "staged": bool(st_e2e.get("d2h_staged", 0)), "page_locked_direct": locked_direct,
+                       "cold_first_call_s": round(t_first, 2),
                        "ms_h2d": round(st_e2e["ms_h2d"], 2), "ms_d2h_exposed": round(st_e2e["ms_d2h"], 2), "ms_device_factorize": round(st_e2e["ms_total"], 2)},
                "gpu_launches": int(launches),
                "clocks": clocks,
