@@ -15,10 +15,14 @@ already exists (the refactorization loop of a Newton / time-stepping code: analy
                 `--impl reference` times it on the full workload (fewer steps when a step takes minutes)
 Workload: BASELINE.json configs[1], the 3-D 7-point Laplacian 128^3 (n = 2 097 152, L = 29 GB), geometric nested
 dissection (MESHND) passed as the user permutation.  The other configs are parity-test cases (tests/).
-Multi-GPU (N > 1): ONE factorization sharded over the N GPUs along the elimination tree (suitesparse_b200/dist.py):
-independent subtrees per rank, the wide top supernodes panel-cyclic, NCCL broadcasts of finished Lx ranges.  scaling =
-"strong" (the matrix is fixed); value = fl / (max over ranks of the device time).  e2e at N > 1: every rank uploads S,
-rank 0 streams the finished ranges of L to its pinned host buffer during the factorization.
+Multi-GPU (N > 1): ONE factorization sharded over the N GPUs along the elimination tree, scaling = "strong" (the matrix is
+fixed), value = fl / (max over devices of the device time).  Default (--multi mg): the library's own multi-GPU path - rank 0's
+process drives all N devices through the C ABI (ssb200_mg_*: independent subtrees per device, the wide top supernodes
+panel-cyclic, finished ranges pulled over NVLink by peer loads, no NCCL on the data path), the other torchrun ranks only join
+CPU barriers; e2e = cholmod_l_super_numeric with SSB200_DEVICES, every device copies its share of L to the host.
+--multi nccl: the round-1 path, one process per GPU with NCCL broadcasts (suitesparse_b200/dist.py).
+e2e at N = 1: the caller's L->x is pageable (the host library's malloc); the factor leaves through the pinned staging ring
+(DESIGN.md section 4a); e2e.page_locked_ms_per_step is the same call once L->x has been page-locked.
 """
 from __future__ import annotations
 import argparse, ctypes as C, json, os, subprocess, sys, threading, time
